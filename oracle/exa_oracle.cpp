@@ -1,0 +1,932 @@
+// =============================================================================
+// oracle/exa_oracle.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// A CPU restatement of the reference's (exanauts/ExaModels.jl v0.12.0) per-pattern
+// evaluation path, interpreting the same pattern IR the product consumes.  Only
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs may load this; the product path (examodels.jl_b200/csrc) never links,
+// calls or falls back to it.
+//
+// It is NOT the reference: the reference is pure Julia and there is no Julia in
+// this image.  Parity of this restatement is pinned by the
+// reference's own fixtures where they exist (tests/test_oracle_pins.py):
+//   * per-pattern slot counts / compressor maps hand-derived from the passes
+//      and the raw traversal counts 10 / 21 pinned by
+//     test/JuMPTest/JuMPTest.jl:404-405,
+//   * closed-form cons values of test/NLPTest/conaug_test.jl:86-213,
+//   * derivative tables against finite differences / sympy as in
+//     test/ADTest/ADTest.jl:298-374.
+// No stored numeric derivative vectors exist in the reference tree.
+//
+// Every function cites the reference file:line it restates (paths relative to
+// /root/reference/).  The recursion is kept literal (one C++ function per Julia
+// method family); the only liberty is that the evaluated "adjoint tree" lives in
+// per-thread arrays indexed by a pre-expanded tree instead of nested structs.
+// =============================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <thread>
+
+typedef int64_t i64;
+
+namespace {
+
+// ---- IR (include/exa_b200.h §IR; emitted by examodels.jl_b200/nlp.py) ---------
+enum { T_CONST_I, T_CONST_F, T_DATA_SELF, T_DATA_FIELD, T_VAR, T_PAR, T_NULL, T_OP1, T_OP2, T_VAL };
+enum { KIND_OBJ, KIND_CON, KIND_AUG };
+enum { FT_I64, FT_F64, FT_I32, FT_F32 };
+
+// univariate op codes: order of src/functionlist.jl:6-60
+enum {
+  U_PLUS, U_MINUS, U_INV, U_SQRT, U_CBRT, U_ABS, U_ABS2, U_SIGN, U_EXP, U_EXP2, U_EXP10,
+  U_EXPM1, U_LOG, U_LOG2, U_LOG1P, U_LOG10, U_SIN, U_COS, U_TAN, U_ASIN, U_ACOS, U_ATAN,
+  U_ACOT, U_CSC, U_SEC, U_COT, U_SINH, U_COSH, U_TANH, U_ASINH, U_ACOSH, U_CSCH, U_SECH,
+  U_COTH, U_SIND, U_COSD, U_TAND, U_CSCD, U_SECD, U_COTD, U_ATAND, U_ACOTD, U_SINPI,
+  U_COSPI, U_SINC, U_DEG2RAD, U_RAD2DEG, U_SIGNBIT, U_FLOOR, U_CEIL, U_ATANH, U_ACOTH, U_COUNT
+};
+// bivariate op codes: order of src/functionlist.jl:71-81
+enum { B_ADD, B_SUB, B_MUL, B_DIV, B_POW, B_ATAN, B_HYPOT, B_MAX, B_MIN, B_COUNT };
+
+struct IRNode { i64 tag, a, b, payload; };
+struct Field { i64 off, type; };
+
+// evaluated-node kinds: Real | (Second)AdjointNull | …NodeVar | …Node1 | …Node2  (graph.jl:106-461)
+enum { K_REAL, K_NULL, K_VAR, K_N1, K_N2 };
+// Node1 flavour: plain unary f, or a bivariate f with one Real operand (register.jl:231-266)
+enum { FX_NONE, FX_FIRST, FX_SECOND };
+
+struct TNode {          // one node of the expanded expression TREE
+  int tag, op, c1, c2;  // c1/c2: tree children (value children; VAR/PAR: index-expression child)
+  int ir;               // originating IR node (identity for the === probe)
+  i64 ipay; double fpay;
+  int kind, fx;         // static: evaluated kind and FirstFixed/SecondFixed flavour
+};
+
+struct Pattern {
+  int kind; i64 nitr; int itr_kind; i64 range_start; int databuf; i64 stride;
+  std::vector<Field> fields;
+  i64 o0, o1, o2; int base; std::vector<int> idx_roots_ir; std::vector<i64> dims;
+  std::vector<IRNode> ir; int root_ir;
+  std::vector<TNode> t; int root; std::vector<int> idx_roots;
+  std::vector<int> comp1, comp2; int o1step, o2step;
+  const unsigned char* data;
+};
+
+struct Model {
+  i64 nvar, npar, ncon, nobj, nconaug, nnzg, nnzj, nnzh;
+  std::vector<Pattern> pats;
+  std::vector<double> theta;
+  // KA-extension style scratch (ext/ExaModelsKernelAbstractions.jl:21-31,39-53)
+  std::vector<std::pair<i64, i64>> gsparsity; std::vector<i64> gptr;
+  std::string err;
+  int nthreads;
+};
+
+// ---- scalar helpers (Julia Base semantics used by src/functionlist.jl) --------------
+inline double sq(double x) { return x * x; }              // literal x^2 == x*x
+inline double cube(double x) { return x * x * x; }        // literal x^3 == x*x*x
+const double PI = 3.14159265358979323846;
+inline double jl_powi(double x, i64 n) {                  // Base.^(::Float64, ::Integer)
+  if (n == 0) return 1.0;
+  if (n == 1) return x;
+  if (n == 2) return x * x;
+  if (n == 3) return x * x * x;
+  if (n == -1) return 1.0 / x;
+  if (n == -2) { double r = 1.0 / x; return r * r; }
+  return std::pow(x, (double)n);
+}
+inline double jl_sec(double x) { return 1.0 / std::cos(x); }
+inline double jl_csc(double x) { return 1.0 / std::sin(x); }
+inline double jl_cot(double x) { return 1.0 / std::tan(x); }
+inline double jl_sech(double x) { return 1.0 / std::cosh(x); }
+inline double jl_csch(double x) { return 1.0 / std::sinh(x); }
+inline double jl_coth(double x) { return 1.0 / std::tanh(x); }
+inline double jl_deg2rad(double x) { return x * (PI / 180.0); }
+inline double jl_rad2deg(double x) { return x * (180.0 / PI); }
+inline double jl_sinpi(double x) {
+  double r = std::fmod(x, 2.0);                           // exact
+  if (r > 1.0) r -= 2.0; else if (r < -1.0) r += 2.0;     // r in [-1,1]
+  if (r > 0.5) r = 1.0 - r; else if (r < -0.5) r = -1.0 - r;
+  return std::sin(PI * r);
+}
+inline double jl_cospi(double x) {
+  double r = std::fabs(std::fmod(x, 2.0));                // [0,2)
+  if (r > 1.0) r = 2.0 - r;                               // [0,1]
+  if (r == 0.5) return 0.0;
+  return r > 0.5 ? -std::cos(PI * (1.0 - r)) : std::cos(PI * r);
+}
+inline double jl_sind(double x) { return jl_sinpi(x / 180.0); }
+inline double jl_cosd(double x) { return jl_cospi(x / 180.0); }
+inline double jl_tand(double x) { return jl_sind(x) / jl_cosd(x); }
+inline double jl_cscd(double x) { return 1.0 / jl_sind(x); }
+inline double jl_secd(double x) { return 1.0 / jl_cosd(x); }
+inline double jl_cotd(double x) { return 1.0 / jl_tand(x); }
+inline double jl_sinc(double x) { return x == 0.0 ? 1.0 : jl_sinpi(x) / (PI * x); }
+inline double jl_sign(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : x); }
+const double LOG2 = 0.69314718055994530942, LOG10 = 2.30258509299404568402;
+const double D2R = PI / 180.0;
+
+// ---- univariate table: f, f', f''  (src/functionlist.jl:6-60, formulas kept literally) -----
+void uni(int op, double x, double& f, double& d, double& dd, int order) {
+  switch (op) {
+    case U_PLUS: f = x; d = 1.0; dd = 0.0; break;                                   // :7
+    case U_MINUS: f = -x; d = -1.0; dd = 0.0; break;                                // :8
+    case U_INV: f = 1.0 / x; if (order) { d = -1.0 / sq(x); dd = 2.0 / cube(x); } break;  // :9
+    case U_SQRT: { double s = std::sqrt(x); f = s;
+      if (order) { d = 1.0 / (2.0 * s); dd = -1.0 / (4.0 * cube(s)); } } break;     // :10
+    case U_CBRT: { double c = std::cbrt(x); f = c;
+      if (order) { d = 1.0 / (3.0 * sq(c)); dd = -2.0 / (9.0 * std::pow(c, 5.0)); } } break; // :11
+    case U_ABS: f = std::fabs(x); d = std::signbit(x) ? -1.0 : 1.0; dd = 0.0; break;  // :12
+    case U_ABS2: f = x * x; d = 2.0 * x; dd = 2.0; break;                           // :13
+    case U_SIGN: f = jl_sign(x); d = 0.0; dd = 0.0; break;                          // :14
+    case U_EXP: f = std::exp(x); d = f; dd = f; break;                              // :15
+    case U_EXP2: f = std::exp2(x); d = LOG2 * f; dd = sq(LOG2) * f; break;          // :16
+    case U_EXP10: f = std::pow(10.0, x); d = LOG10 * f; dd = sq(LOG10) * f; break;  // :17
+    case U_EXPM1: f = std::expm1(x); if (order) { d = std::exp(x); dd = d; } break; // :18
+    case U_LOG: f = std::log(x); if (order) { d = 1.0 / x; dd = -1.0 / sq(x); } break; // :19
+    case U_LOG2: f = std::log2(x);
+      if (order) { d = 1.0 / (LOG2 * x); dd = -LOG2 / (sq(LOG2) * sq(x)); } break;  // :20
+    case U_LOG1P: f = std::log1p(x);
+      if (order) { d = 1.0 / (1.0 + x); dd = -1.0 / sq(1.0 + x); } break;           // :21
+    case U_LOG10: f = std::log10(x);
+      if (order) { d = 1.0 / (LOG10 * x); dd = -LOG10 / (sq(LOG10) * sq(x)); } break; // :22
+    case U_SIN: f = std::sin(x); if (order) { d = std::cos(x); dd = -f; } break;    // :23
+    case U_COS: f = std::cos(x); if (order) { d = -std::sin(x); dd = -f; } break;   // :24
+    case U_TAN: f = std::tan(x);
+      if (order) { double s2 = sq(jl_sec(x)); d = s2; dd = 2.0 * s2 * f; } break;   // :25
+    case U_ASIN: f = std::asin(x);
+      if (order) { double q = 1.0 - sq(x); d = 1.0 / std::sqrt(q); dd = x / (q * std::sqrt(q)); } break; // :26
+    case U_ACOS: f = std::acos(x);
+      if (order) { double q = 1.0 - sq(x); d = -1.0 / std::sqrt(q); dd = (-x) / (q * std::sqrt(q)); } break; // :27
+    case U_ATAN: f = std::atan(x);
+      if (order) { double q = 1.0 + sq(x); d = 1.0 / q; dd = (-2.0 * x) / sq(q); } break; // :28
+    case U_ACOT: f = std::atan(1.0 / x);
+      if (order) { double q = 1.0 + sq(x); d = -1.0 / q; dd = (2.0 * x) / sq(q); } break; // :29
+    case U_CSC: { double c = jl_csc(x); f = c;
+      if (order) { double ct = jl_cot(x); d = -ct * c; dd = -(-1.0 - sq(ct)) * c + sq(ct) * c; } } break; // :30
+    case U_SEC: { double s = jl_sec(x); f = s;
+      if (order) { double t = std::tan(x); d = s * t; dd = cube(s) + s * sq(t); } } break; // :31
+    case U_COT: { double ct = jl_cot(x); f = ct;
+      if (order) { d = -1.0 - sq(ct); dd = -2.0 * ct * (-1.0 - sq(ct)); } } break;  // :32
+    case U_SINH: f = std::sinh(x); if (order) { d = std::cosh(x); dd = f; } break;  // :33
+    case U_COSH: f = std::cosh(x); if (order) { d = std::sinh(x); dd = f; } break;  // :34
+    case U_TANH: f = std::tanh(x);
+      if (order) { d = 1.0 - sq(f); dd = -2.0 * f * (1.0 - sq(f)); } break;         // :35
+    case U_ASINH: f = std::asinh(x);
+      if (order) { double q = 1.0 + sq(x); d = 1.0 / std::sqrt(q); dd = (-x) / (q * std::sqrt(q)); } break; // :36
+    case U_ACOSH: f = std::acosh(x);
+      if (order) { double q = -1.0 + sq(x); d = 1.0 / std::sqrt(q); dd = (-x) / (q * std::sqrt(q)); } break; // :37
+    case U_CSCH: { double c = jl_csch(x); f = c;
+      if (order) { double ct = jl_coth(x); d = -c * ct; dd = cube(c) + c * sq(ct); } } break; // :38
+    case U_SECH: { double s = jl_sech(x); f = s;
+      if (order) { double t = std::tanh(x); d = -t * s; dd = -(1.0 - sq(t)) * s + sq(t) * s; } } break; // :39
+    case U_COTH: { double ct = jl_coth(x); f = ct;
+      if (order) { double c = jl_csch(x); d = -sq(c); dd = 2.0 * sq(c) * ct; } } break; // :40
+    case U_SIND: f = jl_sind(x);
+      if (order) { d = jl_deg2rad(jl_cosd(x)); dd = -D2R * jl_deg2rad(f); } break;  // :41
+    case U_COSD: f = jl_cosd(x);
+      if (order) { d = -jl_deg2rad(jl_sind(x)); dd = -D2R * jl_deg2rad(f); } break; // :42
+    case U_TAND: f = jl_tand(x);
+      if (order) { double q = jl_deg2rad(1.0 + sq(f)); d = q; dd = (2.0 * D2R) * f * q; } break; // :43
+    case U_CSCD: { double c = jl_cscd(x); f = c;
+      if (order) { double ct = jl_cotd(x); double a = -jl_deg2rad(c * ct); d = a;
+        dd = -D2R * (a * ct - c * jl_deg2rad(1.0 + sq(ct))); } } break;             // :44
+    case U_SECD: { double s = jl_secd(x); f = s;
+      if (order) { double t = jl_tand(x); double a = jl_deg2rad(t * s); d = a;
+        dd = D2R * (a * t + jl_deg2rad(1.0 + sq(t)) * s); } } break;                // :45
+    case U_COTD: { double ct = jl_cotd(x); f = ct;
+      if (order) { double q = jl_deg2rad(1.0 + sq(ct)); d = -q; dd = (2.0 * D2R) * ct * q; } } break; // :46
+    case U_ATAND: f = jl_rad2deg(std::atan(x));
+      if (order) { double q = jl_deg2rad(1.0 + sq(x)); d = 1.0 / q; dd = (-(2.0 * D2R) * x) / sq(q); } break; // :47
+    case U_ACOTD: f = jl_rad2deg(std::atan(1.0 / x));
+      if (order) { double q = jl_deg2rad(1.0 + sq(x)); d = -1.0 / q; dd = ((2.0 * D2R) * x) / sq(q); } break; // :48
+    case U_SINPI: f = jl_sinpi(x);
+      if (order) { d = PI * jl_cospi(x); dd = -sq(PI) * f; } break;                 // :49
+    case U_COSPI: f = jl_cospi(x);
+      if (order) { d = -PI * jl_sinpi(x); dd = -sq(PI) * f; } break;                // :50
+    case U_SINC: f = jl_sinc(x);
+      if (order) { double s = jl_sinpi(x), c = jl_cospi(x);
+        d = (-s + PI * x * c) / (PI * sq(x));
+        dd = ((2.0 * sq(PI)) * s - (2.0 * cube(PI)) * x * c - std::pow(PI, 4.0) * sq(x) * s) / (cube(PI) * cube(x)); } break; // :51
+    case U_DEG2RAD: f = jl_deg2rad(x); d = D2R; dd = 0.0; break;                    // :52
+    case U_RAD2DEG: f = jl_rad2deg(x); d = 180.0 / PI; dd = 0.0; break;             // :53
+    case U_SIGNBIT: f = std::signbit(x) ? 1.0 : 0.0; d = 0.0; dd = 0.0; break;      // :54
+    case U_FLOOR: f = std::floor(x); d = 0.0; dd = 0.0; break;                      // :55
+    case U_CEIL: f = std::ceil(x); d = 0.0; dd = 0.0; break;                        // :56
+    case U_ATANH: f = std::atanh(x);
+      if (order) { if (std::fabs(x) > 1.0) { d = NAN; dd = NAN; }
+        else { double iv = 1.0 / (1.0 - sq(x)); d = iv; dd = (-sq(iv)) * (-2.0 * x); } } break; // :58
+    case U_ACOTH: f = std::atanh(1.0 / x);
+      if (order) { if (std::fabs(x) < 1.0) { d = NAN; dd = NAN; }
+        else { double iv = 1.0 / (1.0 - sq(x)); d = iv; dd = (-sq(iv)) * (-2.0 * x); } } break; // :59
+    default: f = d = dd = NAN;
+  }
+}
+
+// A Real operand: Int or Float64 (Julia keeps Int arithmetic among Ints).
+struct Real { bool is_int; i64 i; double f; double val() const { return is_int ? (double)i : f; } };
+
+inline double bpow(double x1, const Real& e) {            // x1 ^ x2 with x2 Int or Float64
+  return e.is_int ? jl_powi(x1, e.i) : std::pow(x1, e.f);
+}
+inline Real radd(const Real& e, i64 k) {                  // (k + x2) in the exponent formulas
+  Real r = e; if (e.is_int) r.i = e.i + k; else r.f = e.f + (double)k; return r;
+}
+
+// ---- bivariate table (src/functionlist.jl:71-81) ---------------------------------------
+// Computes f and whichever partials `need` asks for: bit0 first-order, bit1 second-order.
+// `e2` carries the Int/Float nature of the second operand (matters for ^ only).
+struct Bi { double f, y1, y2, h11, h12, h22; };
+void bi(int op, double x1, double x2, const Real& e1, const Real& e2, Bi& r, bool want1, bool want2) {
+  (void)e1;
+  switch (op) {
+    case B_ADD: r.f = x1 + x2; r.y1 = 1.0; r.y2 = 1.0; r.h11 = r.h12 = r.h22 = 0.0; break;   // :72
+    case B_SUB: r.f = x1 - x2; r.y1 = 1.0; r.y2 = -1.0; r.h11 = r.h12 = r.h22 = 0.0; break;  // :73
+    case B_MUL: r.f = x1 * x2; r.y1 = x2; r.y2 = x1; r.h11 = 0.0; r.h12 = 1.0; r.h22 = 0.0; break; // :74
+    case B_DIV: r.f = x1 / x2; r.y1 = 1.0 / x2; r.y2 = (-x1) / sq(x2);
+      r.h11 = 0.0; r.h12 = -1.0 / sq(x2); r.h22 = (2.0 * x1) / cube(x2); break;              // :75
+    case B_POW:                                                                              // :76
+      r.f = bpow(x1, e2);
+      if (want1) {
+        double pm1 = bpow(x1, radd(e2, -1));
+        r.y1 = x2 * pm1;
+        r.h11 = (-1.0 + x2) * x2 * bpow(x1, radd(e2, -2));
+        if (e2.is_int) r.h11 = (double)((-1 + e2.i) * e2.i) * bpow(x1, radd(e2, -2));
+      }
+      if (want2) {
+        double lg = std::log(x1), pm1 = bpow(x1, radd(e2, -1));
+        r.y2 = lg * r.f;
+        r.h12 = pm1 + x2 * pm1 * lg;
+        r.h22 = sq(lg) * r.f;
+      }
+      break;
+    case B_ATAN: { double q = sq(x1) + sq(x2); r.f = std::atan2(x1, x2);                     // :77
+      r.y1 = x2 / q; r.y2 = (-x1) / q; r.h11 = (-2.0 * x1 * x2) / sq(q);
+      r.h12 = (sq(x1) - sq(x2)) / (std::pow(x1, 4.0) + 2.0 * sq(x1) * sq(x2) + std::pow(x2, 4.0));
+      r.h22 = (2.0 * x1 * x2) / sq(q); } break;
+    case B_HYPOT: { double h = std::hypot(x1, x2); r.f = h;                                  // :78
+      r.y1 = x1 / h; r.y2 = x2 / h; r.h11 = (-sq(x1) + sq(h)) / cube(h);
+      r.h12 = (-x1 * x2) / cube(h); r.h22 = (-sq(x2) + sq(h)) / cube(h); } break;
+    case B_MAX: r.f = (x1 < x2 || std::isnan(x2)) ? x2 : x1;                                 // :79
+      r.y1 = x1 > x2 ? 1.0 : 0.0; r.y2 = x1 > x2 ? 0.0 : 1.0; r.h11 = r.h12 = r.h22 = 0.0; break;
+    case B_MIN: r.f = (x2 < x1 || std::isnan(x2)) ? x2 : x1;                                 // :80
+      r.y1 = x1 < x2 ? 1.0 : 0.0; r.y2 = x1 < x2 ? 0.0 : 1.0; r.h11 = r.h12 = r.h22 = 0.0; break;
+    default: r.f = NAN;
+  }
+}
+
+// Real OP Real (both operands free of variables): plain Julia arithmetic.
+Real real_op2(int op, const Real& a, const Real& b) {
+  Real r; r.is_int = false; r.i = 0; r.f = 0;
+  if (a.is_int && b.is_int && (op == B_ADD || op == B_SUB || op == B_MUL || op == B_MAX || op == B_MIN)) {
+    r.is_int = true;
+    switch (op) {
+      case B_ADD: r.i = a.i + b.i; break;
+      case B_SUB: r.i = a.i - b.i; break;
+      case B_MUL: r.i = a.i * b.i; break;
+      case B_MAX: r.i = std::max(a.i, b.i); break;
+      default: r.i = std::min(a.i, b.i);
+    }
+    return r;
+  }
+  if (a.is_int && b.is_int && op == B_POW && b.i >= 0) {   // Int ^ Int (power_by_squaring)
+    r.is_int = true; r.i = 1; for (i64 k = 0; k < b.i; k++) r.i *= a.i; return r;
+  }
+  Bi t; bi(op, a.val(), b.val(), a, b, t, false, false); r.f = t.f; return r;
+}
+Real real_op1(int op, const Real& a) {
+  Real r; r.is_int = false; r.i = 0;
+  if (a.is_int && (op == U_PLUS || op == U_MINUS || op == U_ABS || op == U_ABS2)) {
+    r.is_int = true;
+    r.i = op == U_PLUS ? a.i : op == U_MINUS ? -a.i : op == U_ABS ? (a.i < 0 ? -a.i : a.i) : a.i * a.i;
+    return r;
+  }
+  double f, d, dd; uni(op, a.val(), f, d, dd, 0); r.f = f; return r;
+}
+
+// ---- build: IR parse, tree expansion, static kinds ---------------------------------------
+int expand(Pattern& p, int ir) {
+  const IRNode& n = p.ir[ir];
+  TNode t; std::memset(&t, 0, sizeof t);
+  t.tag = (int)n.tag; t.ir = ir; t.c1 = t.c2 = -1; t.ipay = n.payload; std::memcpy(&t.fpay, &n.payload, 8);
+  t.op = (int)n.payload;
+  if (n.tag == T_VAR || n.tag == T_PAR || n.tag == T_OP1) t.c1 = expand(p, (int)n.a);
+  if (n.tag == T_OP2) { t.c1 = expand(p, (int)n.a); t.c2 = expand(p, (int)n.b); }
+  if (n.tag == T_DATA_FIELD) t.op = (int)n.a;
+  // static kind of the evaluated node under an (Second)AdjointNodeSource:
+  switch (n.tag) {
+    case T_VAR: t.kind = K_VAR; break;                           // graph.jl:397-400,491-494
+    case T_NULL: t.kind = K_NULL; break;                         // graph.jl:499-502
+    case T_OP1: t.kind = p.t[t.c1].kind == K_REAL ? K_REAL : K_N1; break;   // register.jl:65-71
+    case T_OP2: {
+      bool r1 = p.t[t.c1].kind == K_REAL, r2 = p.t[t.c2].kind == K_REAL;
+      if (r1 && r2) t.kind = K_REAL;
+      else if (r2) { t.kind = K_N1; t.fx = FX_SECOND; }          // register.jl:231-248
+      else if (r1) { t.kind = K_N1; t.fx = FX_FIRST; }           // register.jl:249-266
+      else t.kind = K_N2;                                        // register.jl:209-230
+    } break;
+    default: t.kind = K_REAL;                                    // constants, data, θ[...]
+  }
+  p.t.push_back(t);
+  return (int)p.t.size() - 1;
+}
+
+bool ir_equal(const Pattern& p, int a, int b) {   // Julia `===` on immutable node structs
+  if (a == b) return true;
+  const IRNode &x = p.ir[a], &y = p.ir[b];
+  if (x.tag != y.tag) return false;
+  switch (x.tag) {
+    case T_CONST_I: case T_CONST_F: case T_NULL: case T_VAL: return x.payload == y.payload;
+    case T_DATA_SELF: return true;
+    case T_DATA_FIELD: return x.a == y.a;
+    case T_VAR: case T_PAR: return ir_equal(p, (int)x.a, (int)y.a);
+    case T_OP1: return x.payload == y.payload && ir_equal(p, (int)x.a, (int)y.a);
+    case T_OP2: return x.payload == y.payload && ir_equal(p, (int)x.a, (int)y.a) && ir_equal(p, (int)x.b, (int)y.b);
+  }
+  return false;
+}
+
+// ---- per-thread evaluation workspace ---------------------------------------------------
+struct Work {
+  std::vector<double> x, y1, y2, h11, h12, h22;   // per tree node (Node1: y=y1, h=h11)
+  std::vector<Real> re;                           // Real values (kind K_REAL and index exprs)
+  std::vector<i64> vi;                            // VAR: evaluated index
+  void size(size_t n) { x.resize(n); y1.resize(n); y2.resize(n); h11.resize(n); h12.resize(n); h22.resize(n); re.resize(n); vi.resize(n); }
+};
+
+struct Ctx {
+  const Pattern* p; const double* X; const double* TH; Work* w;
+  i64 k;              // 0-based point number
+  const unsigned char* elem;
+};
+
+Real data_value(const Ctx& c, const TNode& t) {
+  Real r; r.is_int = false; r.i = 0; r.f = 0;
+  if (t.tag == T_DATA_SELF) { r.is_int = true; r.i = c.p->range_start + c.k; return r; }
+  const Field& f = c.p->fields[t.op];
+  const unsigned char* q = c.elem + f.off;
+  switch (f.type) {
+    case FT_I64: { i64 v; std::memcpy(&v, q, 8); r.is_int = true; r.i = v; } break;
+    case FT_F64: { double v; std::memcpy(&v, q, 8); r.f = v; } break;
+    case FT_I32: { int32_t v; std::memcpy(&v, q, 4); r.is_int = true; r.i = v; } break;
+    default: { float v; std::memcpy(&v, q, 4); r.f = v; }
+  }
+  return r;
+}
+
+// Evaluate a variable-free subtree: `node(i, x, θ)` on Reals (graph.jl:305-318, register.jl:70,268-273).
+Real eval_real(const Ctx& c, int n) {
+  const TNode& t = c.p->t[n];
+  Real r; r.is_int = false; r.i = 0; r.f = 0;
+  switch (t.tag) {
+    case T_CONST_I: case T_VAL: r.is_int = true; r.i = t.ipay; return r;
+    case T_CONST_F: r.f = t.fpay; return r;
+    case T_DATA_SELF: case T_DATA_FIELD: return data_value(c, t);
+    case T_PAR: { Real ix = eval_real(c, t.c1); r.f = c.TH ? c.TH[ix.i - 1] : NAN; return r; }  // graph.jl:310-311
+    case T_OP1: return real_op1(t.op, eval_real(c, t.c1));
+    case T_OP2: return real_op2(t.op, eval_real(c, t.c1), eval_real(c, t.c2));
+  }
+  r.f = NAN; return r;
+}
+
+// Primal evaluation `f(itr[k], x, θ)` (graph.jl:305-318; register.jl:70-71,268-273).
+double eval0(const Ctx& c, int n) {
+  const TNode& t = c.p->t[n];
+  if (t.kind == K_REAL) return eval_real(c, n).val();
+  switch (t.tag) {
+    case T_VAR: { Real ix = eval_real(c, t.c1); return c.X[ix.i - 1]; }
+    case T_NULL: return t.fpay;                                   // graph.jl:497-498
+    case T_OP1: { double f, d, dd; uni(t.op, eval0(c, t.c1), f, d, dd, 0); return f; }
+    case T_OP2: {
+      const TNode &a = c.p->t[t.c1], &b = c.p->t[t.c2];
+      Real e1, e2; e1.is_int = e2.is_int = false; e1.i = e2.i = 0; e1.f = e2.f = 0;
+      double x1, x2;
+      if (a.kind == K_REAL) { e1 = eval_real(c, t.c1); x1 = e1.val(); } else x1 = eval0(c, t.c1);
+      if (b.kind == K_REAL) { e2 = eval_real(c, t.c2); x2 = e2.val(); } else { x2 = eval0(c, t.c2); e2.f = x2; }
+      Bi r; bi(t.op, x1, x2, e1, e2, r, false, false); return r.f;
+    }
+  }
+  return NAN;
+}
+
+// Forward sweep under (Second)AdjointNodeSource (graph.jl:397-400,491-494;
+// register.jl:65-68,174-266).  order = 1: x,y1,y2 ; order = 2: also h11,h12,h22.
+void fwd(const Ctx& c, int n, int order) {
+  const TNode& t = c.p->t[n];
+  Work& w = *c.w;
+  if (t.kind == K_REAL) { w.re[n] = eval_real(c, n); w.x[n] = w.re[n].val(); return; }
+  switch (t.tag) {
+    case T_VAR: { Real ix = eval_real(c, t.c1); w.vi[n] = ix.i; w.x[n] = c.X ? c.X[ix.i - 1] : NAN; return; }
+    case T_NULL: w.x[n] = t.fpay; return;
+    case T_OP1: {
+      fwd(c, t.c1, order);
+      uni(t.op, w.x[t.c1], w.x[n], w.y1[n], w.h11[n], order);
+      return;
+    }
+    case T_OP2: {
+      fwd(c, t.c1, order); fwd(c, t.c2, order);
+      Real e1, e2; e1.is_int = e2.is_int = false; e1.i = e2.i = 0; e1.f = w.x[t.c1]; e2.f = w.x[t.c2];
+      if (c.p->t[t.c1].kind == K_REAL) e1 = w.re[t.c1];
+      if (c.p->t[t.c2].kind == K_REAL) e2 = w.re[t.c2];
+      Bi r;
+      if (t.kind == K_N2) {
+        bi(t.op, w.x[t.c1], w.x[t.c2], e1, e2, r, true, true);
+        w.x[n] = r.f; w.y1[n] = r.y1; w.y2[n] = r.y2; w.h11[n] = r.h11; w.h12[n] = r.h12; w.h22[n] = r.h22;
+      } else if (t.fx == FX_SECOND) {       // node OP Real: (f, df1, ddf11)   register.jl:239-247
+        bi(t.op, w.x[t.c1], w.x[t.c2], e1, e2, r, true, false);
+        w.x[n] = r.f; w.y1[n] = r.y1; w.h11[n] = r.h11;
+      } else {                              // Real OP node: (f, df2, ddf22)   register.jl:257-265
+        bi(t.op, w.x[t.c1], w.x[t.c2], e1, e2, r, false, true);
+        w.x[n] = r.f; w.y1[n] = r.y2; w.h11[n] = r.h22;
+      }
+      return;
+    }
+  }
+}
+inline int inner_of(const TNode& t) { return (t.tag == T_OP2 && t.fx == FX_FIRST) ? t.c2 : t.c1; }
+
+// ---- reverse passes ---------------------------------------------------------------
+// Sink: where a leaf visit lands.  mode selects the reference method the visit dispatches to.
+enum { M_VALUES, M_PROBE, M_STRUCT, M_DENSE, M_JPROD, M_JTPROD, M_HPROD };
+struct Sink {
+  int mode;
+  double* y; i64 off; const int* comp;            // values:  y[off + comp(++cnt)] += v
+  std::vector<int>* raw1; std::vector<std::pair<int, int>>* raw2;   // probe
+  i64 *rows, *cols; i64 row;                      // structure
+  const double* v; double* out;                   // products
+};
+
+// grpass / jrpass / drpass share one shape (gradient.jl:11-26,71-90; jacobian.jl:16-40,69-83)
+void rpass1(const Ctx& c, int n, Sink& s, int& cnt, double adj) {
+  const TNode& t = c.p->t[n];
+  const Work& w = *c.w;
+  switch (t.kind) {
+    case K_REAL: case K_NULL: return;                                  // gradient.jl:59-69
+    case K_N1: rpass1(c, inner_of(t), s, cnt, adj * w.y1[n]); return;  // gradient.jl:71-74
+    case K_N2:                                                         // gradient.jl:75-79
+      rpass1(c, t.c1, s, cnt, adj * w.y1[n]);
+      rpass1(c, t.c2, s, cnt, adj * w.y2[n]);
+      return;
+    case K_VAR:
+      switch (s.mode) {
+        case M_VALUES: s.y[s.off + s.comp[cnt++] - 1] += adj; return;  // gradient.jl:80-83, jacobian.jl:36-39 (1-based comp)
+        case M_DENSE: s.y[w.vi[n] - 1] += adj; return;                 // gradient.jl:23-26
+        case M_PROBE: s.raw1->push_back(c.p->t[n].ir); return;         // gradient.jl:84-87
+        case M_STRUCT: { i64 ind = s.off + s.comp[cnt++] - 1;          // jacobian.jl:69-83
+          s.rows[ind] = s.row; s.cols[ind] = w.vi[n]; } return;
+        case M_JPROD: s.out[s.row - 1] += adj * s.v[w.vi[n] - 1]; cnt++; return;   // jacobian.jl:41-54
+        case M_JTPROD: s.out[w.vi[n] - 1] += adj * s.v[s.row - 1]; cnt++; return;  // jacobian.jl:55-68
+      }
+  }
+}
+
+void hleaf_pair(const Ctx& c, int a, int b, Sink& s, int& cnt, double adj) {   // hessian.jl:251-315,520-532,622-642
+  const Work& w = *c.w;
+  i64 i = w.vi[a], j = w.vi[b];
+  switch (s.mode) {
+    case M_VALUES: s.y[s.off + s.comp[cnt++] - 1] += (i == j ? 2.0 * adj : adj); return;
+    case M_PROBE: s.raw2->push_back(std::make_pair(c.p->t[a].ir, c.p->t[b].ir)); return;
+    case M_STRUCT: { i64 ind = s.off + s.comp[cnt++] - 1;
+      if (i >= j) { s.rows[ind] = i; s.cols[ind] = j; } else { s.rows[ind] = j; s.cols[ind] = i; } } return;
+    case M_HPROD:
+      if (i == j) s.out[i - 1] += 2.0 * adj * s.v[i - 1];
+      else { s.out[i - 1] += adj * s.v[j - 1]; s.out[j - 1] += adj * s.v[i - 1]; }
+      cnt++; return;
+  }
+}
+
+// hdrpass: cross terms (df1/dx)(df2/dx)'  (hessian.jl:16-320)
+void hdrpass(const Ctx& c, int a, int b, Sink& s, int& cnt, double adj) {
+  const TNode &t1 = c.p->t[a], &t2 = c.p->t[b];
+  const Work& w = *c.w;
+  if (t1.kind == K_NULL || t2.kind == K_NULL) return;                       // :318-320
+  if (t1.kind == K_VAR && t2.kind == K_VAR) { hleaf_pair(c, a, b, s, cnt, adj); return; }   // :251-268
+  if (t1.kind == K_N1 && t2.kind == K_N1) { hdrpass(c, inner_of(t1), inner_of(t2), s, cnt, adj * w.y1[a] * w.y1[b]); return; } // :16-28
+  if (t1.kind == K_VAR && t2.kind == K_N1) { hdrpass(c, a, inner_of(t2), s, cnt, adj * w.y1[b]); return; }   // :44-56
+  if (t1.kind == K_N1 && t2.kind == K_VAR) { hdrpass(c, inner_of(t1), b, s, cnt, adj * w.y1[a]); return; }   // :72-84
+  if (t1.kind == K_N2 && t2.kind == K_N2) {                                 // :100-115
+    hdrpass(c, t1.c1, t2.c1, s, cnt, adj * w.y1[a] * w.y1[b]);
+    hdrpass(c, t1.c1, t2.c2, s, cnt, adj * w.y1[a] * w.y2[b]);
+    hdrpass(c, t1.c2, t2.c1, s, cnt, adj * w.y2[a] * w.y1[b]);
+    hdrpass(c, t1.c2, t2.c2, s, cnt, adj * w.y2[a] * w.y2[b]);
+    return;
+  }
+  if (t1.kind == K_N1 && t2.kind == K_N2) {                                 // :134-147
+    hdrpass(c, inner_of(t1), t2.c1, s, cnt, adj * w.y1[a] * w.y1[b]);
+    hdrpass(c, inner_of(t1), t2.c2, s, cnt, adj * w.y1[a] * w.y2[b]);
+    return;
+  }
+  if (t1.kind == K_N2 && t2.kind == K_N1) {                                 // :163-176
+    hdrpass(c, t1.c1, inner_of(t2), s, cnt, adj * w.y1[a] * w.y1[b]);
+    hdrpass(c, t1.c2, inner_of(t2), s, cnt, adj * w.y2[a] * w.y1[b]);
+    return;
+  }
+  if (t1.kind == K_VAR && t2.kind == K_N2) {                                // :192-205
+    hdrpass(c, a, t2.c1, s, cnt, adj * w.y1[b]);
+    hdrpass(c, a, t2.c2, s, cnt, adj * w.y2[b]);
+    return;
+  }
+  if (t1.kind == K_N2 && t2.kind == K_VAR) {                                // :221-234
+    hdrpass(c, t1.c1, b, s, cnt, adj * w.y1[a]);
+    hdrpass(c, t1.c2, b, s, cnt, adj * w.y2[a]);
+    return;
+  }
+}
+
+// hrpass: d²f/dx² portion (hessian.jl:337-380,533-536,566-621)
+void hrpass(const Ctx& c, int n, Sink& s, int& cnt, double adj, double adj2) {
+  const TNode& t = c.p->t[n];
+  const Work& w = *c.w;
+  switch (t.kind) {
+    case K_REAL: case K_NULL: return;                                       // :337-348
+    case K_N1:                                                              // :349-362
+      hrpass(c, inner_of(t), s, cnt, adj * w.y1[n], adj2 * sq(w.y1[n]) + adj * w.h11[n]);
+      return;
+    case K_N2: {                                                            // :363-380
+      double adj2y1y2 = adj2 * w.y1[n] * w.y2[n];
+      double adjh12 = adj * w.h12[n];
+      hrpass(c, t.c1, s, cnt, adj * w.y1[n], adj2 * sq(w.y1[n]) + adj * w.h11[n]);
+      hrpass(c, t.c2, s, cnt, adj * w.y2[n], adj2 * sq(w.y2[n]) + adj * w.h22[n]);
+      hdrpass(c, t.c1, t.c2, s, cnt, adj2y1y2 + adjh12);
+      return;
+    }
+    case K_VAR:
+      switch (s.mode) {
+        case M_VALUES: s.y[s.off + s.comp[cnt++] - 1] += adj2; return;      // :580-592
+        case M_PROBE: s.raw2->push_back(std::make_pair(t.ir, t.ir)); return;  // :533-536
+        case M_STRUCT: { i64 ind = s.off + s.comp[cnt++] - 1;               // :593-607
+          s.rows[ind] = w.vi[n]; s.cols[ind] = w.vi[n]; } return;
+        case M_HPROD: s.out[w.vi[n] - 1] += adj2 * s.v[w.vi[n] - 1]; cnt++; return;   // :566-579
+      }
+  }
+}
+
+// hrpass0: top-level linear peeling (hessian.jl:382-517)
+void hrpass0(const Ctx& c, int n, Sink& s, int& cnt, double adj, double adj2) {
+  const TNode& t = c.p->t[n];
+  const Work& w = *c.w;
+  if (t.kind == K_VAR) return;                                              // :494-517
+  if (t.kind == K_N1) {
+    int in = inner_of(t);
+    if (t.tag == T_OP2) {                                                   // FirstFixed / SecondFixed flavours
+      if (t.op == B_MUL) { hrpass0(c, in, s, cnt, adj * w.y1[n], adj2 * sq(w.y1[n])); return; }   // :385-397
+      if (t.op == B_ADD) { hrpass0(c, in, s, cnt, adj, adj2); return; }                           // :398-410
+      if (t.op == B_SUB && t.fx == FX_FIRST) { hrpass0(c, in, s, cnt, -adj, adj2); return; }      // :411-423
+      if (t.op == B_SUB && t.fx == FX_SECOND) { hrpass0(c, in, s, cnt, adj, adj2); return; }      // :424-436
+    } else {
+      if (t.op == U_PLUS) { hrpass0(c, in, s, cnt, adj, adj2); return; }    // :438-450
+      if (t.op == U_MINUS) { hrpass0(c, in, s, cnt, -adj, adj2); return; }  // :451-463
+    }
+  }
+  if (t.kind == K_N2 && t.op == B_ADD) {                                    // :465-478
+    hrpass0(c, t.c1, s, cnt, adj, adj2); hrpass0(c, t.c2, s, cnt, adj, adj2); return;
+  }
+  if (t.kind == K_N2 && t.op == B_SUB) {                                    // :480-493
+    hrpass0(c, t.c1, s, cnt, adj, adj2); hrpass0(c, t.c2, s, cnt, -adj, adj2); return;
+  }
+  hrpass(c, n, s, cnt, adj, adj2);                                          // :382
+}
+
+// ---- pattern build: probe + compressors (simdfunction.jl:66-100) ---------------------------
+void probe(Pattern& p) {
+  Work w; w.size(p.t.size());
+  Ctx c; c.p = &p; c.X = nullptr; c.TH = nullptr; c.w = &w; c.k = 0; c.elem = nullptr;
+  // The probe evaluates at `Identity()`: data leaves answer NaN and no index is ever
+  // evaluated (graph.jl:307-308,317-318).  Kinds are static, so only the traversal matters.
+  std::vector<int> raw1; std::vector<std::pair<int, int>> raw2;
+  Sink s; std::memset(&s, 0, sizeof s); s.mode = M_PROBE; s.raw1 = &raw1; s.raw2 = &raw2;
+  int cnt = 0;
+  // traversal uses only kinds; feed NaN tapes
+  std::fill(w.y1.begin(), w.y1.end(), NAN); std::fill(w.y2.begin(), w.y2.end(), NAN);
+  std::fill(w.h11.begin(), w.h11.end(), NAN); std::fill(w.h12.begin(), w.h12.end(), NAN); std::fill(w.h22.begin(), w.h22.end(), NAN);
+  rpass1(c, p.root, s, cnt, NAN);                                           // simdfunction.jl:81-83
+  cnt = 0;
+  hrpass0(c, p.root, s, cnt, NAN, NAN);                                     // simdfunction.jl:85-87
+  std::vector<int> u1;                                                      // _ident_unique, :66-76
+  for (int v : raw1) {
+    int found = -1;
+    for (size_t q = 0; q < u1.size(); q++) if (ir_equal(p, u1[q], v)) { found = (int)q; break; }
+    if (found < 0) { u1.push_back(v); found = (int)u1.size() - 1; }
+    p.comp1.push_back(found + 1);
+  }
+  p.o1step = (int)u1.size();
+  std::vector<std::pair<int, int>> u2;
+  for (auto& v : raw2) {
+    int found = -1;
+    for (size_t q = 0; q < u2.size(); q++)
+      if (ir_equal(p, u2[q].first, v.first) && ir_equal(p, u2[q].second, v.second)) { found = (int)q; break; }
+    if (found < 0) { u2.push_back(v); found = (int)u2.size() - 1; }
+    p.comp2.push_back(found + 1);
+  }
+  p.o2step = (int)u2.size();
+}
+
+bool parse(Model& m, const i64* w, size_t nw, const void* const* bufs, int nbufs) {
+  size_t q = 0;
+  auto rd = [&](i64& out) { if (q >= nw) return false; out = w[q++]; return true; };
+  i64 magic, ver, npat, nb;
+  if (!rd(magic) || magic != 0x0031425845LL) { m.err = "bad IR magic"; return false; }
+  if (!rd(ver) || ver != 1) { m.err = "bad IR version"; return false; }
+  rd(m.nvar); rd(m.npar); rd(npat); rd(nb);
+  if (nb > nbufs) { m.err = "IR references more data buffers than were passed"; return false; }
+  m.pats.resize((size_t)npat);
+  for (auto& p : m.pats) {
+    i64 v, nf, nidx, nn;
+    rd(v); p.kind = (int)v; rd(p.nitr); rd(v); p.itr_kind = (int)v; rd(p.range_start);
+    rd(v); p.databuf = (int)v; rd(p.stride); rd(nf);
+    p.fields.resize((size_t)nf);
+    for (auto& f : p.fields) { rd(f.off); rd(f.type); }
+    rd(p.o0); rd(p.o1); rd(p.o2); rd(v); p.base = (int)v; rd(nidx);
+    p.idx_roots_ir.resize((size_t)nidx); p.dims.resize((size_t)nidx);
+    for (auto& r : p.idx_roots_ir) { rd(v); r = (int)v; }
+    for (auto& d : p.dims) rd(d);
+    rd(nn); p.ir.resize((size_t)nn);
+    for (auto& n : p.ir) { rd(n.tag); rd(n.a); rd(n.b); rd(n.payload); }
+    rd(v); p.root_ir = (int)v;
+    i64 nc1 = 0, nc2 = 0; rd(nc1); q += (size_t)nc1; rd(nc2); q += (size_t)nc2;   // supplied comps are ignored: recomputed
+    if (q > nw) { m.err = "truncated IR"; return false; }
+    p.data = p.databuf >= 0 ? (const unsigned char*)bufs[p.databuf] : nullptr;
+    p.root = expand(p, p.root_ir);
+    for (int r : p.idx_roots_ir) p.idx_roots.push_back(expand(p, r));
+    probe(p);
+  }
+  // running counters in add order (nlp.jl:1474-1482, 1597-1611, 1730-1738)
+  m.ncon = m.nobj = m.nconaug = m.nnzg = m.nnzj = m.nnzh = 0;
+  for (auto& p : m.pats) {
+    if (p.kind == KIND_OBJ) {
+      p.o0 = m.nobj; p.o1 = m.nnzg; p.o2 = m.nnzh;                          // nlp.jl:1450
+      m.nobj += p.nitr; m.nnzg += p.nitr * p.o1step; m.nnzh += p.nitr * p.o2step;
+    } else if (p.kind == KIND_CON) {
+      p.o0 = m.ncon; p.o1 = m.nnzj; p.o2 = m.nnzh;                          // nlp.jl:1587
+      m.ncon += p.nitr; m.nnzj += p.nitr * p.o1step; m.nnzh += p.nitr * p.o2step;
+    } else {
+      p.o0 = m.pats[(size_t)p.base].o0; p.o1 = m.nnzj; p.o2 = m.nnzh;       // nlp.jl:1683 (offset0(c1, 0))
+      m.nconaug += p.nitr; m.nnzj += p.nitr * p.o1step; m.nnzh += p.nitr * p.o2step;
+    }
+  }
+  return true;
+}
+
+inline void point(Ctx& c, i64 k) {
+  c.k = k;
+  c.elem = c.p->data ? c.p->data + (size_t)k * (size_t)c.p->stride : nullptr;
+}
+
+// offset0 (nlp.jl:1980-2001): 1-based global row (constraints) / objbuffer slot (objectives)
+i64 offset0(const Ctx& c) {
+  const Pattern& p = *c.p;
+  if (p.kind != KIND_AUG) return p.o0 + c.k + 1;                            // nlp.jl:1989
+  if (p.idx_roots.size() == 1) return p.o0 + eval_real(c, p.idx_roots[0]).i;   // nlp.jl:1994-1997
+  i64 a = 1, lin = 0;                                                       // idxx, nlp.jl:2012-2015
+  for (size_t d = 0; d < p.idx_roots.size(); d++) {
+    lin += a * (eval_real(c, p.idx_roots[d]).i - 1);
+    a *= p.dims[d];
+  }
+  return p.o0 + lin + 1;
+}
+
+int nthreads_of(const Model& m) { return m.nthreads > 0 ? m.nthreads : 1; }
+
+template <class F>
+void for_points(const Model& m, const Pattern& p, const double* X, F body) {
+  int nt = nthreads_of(m);
+  if (nt <= 1 || p.nitr < 1024) {
+    Work w; w.size(p.t.size());
+    Ctx c; c.p = &p; c.X = X; c.TH = m.theta.data(); c.w = &w;
+    for (i64 k = 0; k < p.nitr; k++) { point(c, k); body(c); }
+    return;
+  }
+  // static partition of the data points over host threads: the shape of
+  // KernelAbstractions.CPU() under `julia -t N` (docs/src/gpu.jl:2-5,48)
+  std::vector<std::thread> th;
+  for (int r = 0; r < nt; r++) {
+    i64 lo = p.nitr * r / nt, hi = p.nitr * (r + 1) / nt;
+    th.emplace_back([&, lo, hi]() {
+      Work w; w.size(p.t.size());
+      Ctx c; c.p = &p; c.X = X; c.TH = m.theta.data(); c.w = &w;
+      for (i64 k = lo; k < hi; k++) { point(c, k); body(c); }
+    });
+  }
+  for (auto& t : th) t.join();
+}
+
+}  // namespace
+
+// =============================================================================
+// C interface (ctypes: tests/oracle_api.py)
+// =============================================================================
+extern "C" {
+
+void* ora_create(const void* ir, size_t ir_bytes, const void* const* bufs, int nbufs) {
+  Model* m = new Model(); m->nthreads = 1;
+  parse(*m, (const i64*)ir, ir_bytes / 8, bufs, nbufs);
+  m->theta.assign((size_t)m->npar, 0.0);
+  return m;
+}
+const char* ora_error(void* h) { return ((Model*)h)->err.c_str(); }
+void ora_destroy(void* h) { delete (Model*)h; }
+void ora_set_threads(void* h, int n) { ((Model*)h)->nthreads = n; }
+int ora_max_threads() { unsigned n = std::thread::hardware_concurrency(); return n ? (int)n : 1; }
+void ora_set_params(void* h, const double* th) { Model* m = (Model*)h; m->theta.assign(th, th + m->npar); }
+
+// out[0..7] = nvar, ncon, nnzj, nnzh, nobj, nnzg, nconaug, npar
+void ora_dims(void* h, i64* out) {
+  Model* m = (Model*)h;
+  out[0] = m->nvar; out[1] = m->ncon; out[2] = m->nnzj; out[3] = m->nnzh;
+  out[4] = m->nobj; out[5] = m->nnzg; out[6] = m->nconaug; out[7] = m->npar;
+}
+int ora_npatterns(void* h) { return (int)((Model*)h)->pats.size(); }
+// out[0..6] = kind, nitr, o0, o1, o2, o1step, o2step ; returns sizes of comp1/comp2 in out[7], out[8]
+void ora_pattern_info(void* h, int k, i64* out) {
+  const Pattern& p = ((Model*)h)->pats[(size_t)k];
+  out[0] = p.kind; out[1] = p.nitr; out[2] = p.o0; out[3] = p.o1; out[4] = p.o2;
+  out[5] = p.o1step; out[6] = p.o2step; out[7] = (i64)p.comp1.size(); out[8] = (i64)p.comp2.size();
+}
+void ora_pattern_comp(void* h, int k, int which, i64* out) {
+  const Pattern& p = ((Model*)h)->pats[(size_t)k];
+  const std::vector<int>& c = which == 1 ? p.comp1 : p.comp2;
+  for (size_t q = 0; q < c.size(); q++) out[q] = c[q];
+}
+
+// obj (nlp.jl:1827-1839): sequential sum, patterns oldest first, points in order.
+double ora_obj(void* h, const double* x) {
+  Model* m = (Model*)h;
+  double s = 0.0;
+  for (auto& p : m->pats) {
+    if (p.kind != KIND_OBJ) continue;
+    if (nthreads_of(*m) <= 1) {
+      Work w; w.size(p.t.size());
+      Ctx c; c.p = &p; c.X = x; c.TH = m->theta.data(); c.w = &w;
+      for (i64 k = 0; k < p.nitr; k++) { point(c, k); s += eval0(c, p.root); }
+    } else {   // KA shape: objbuffer + sum (ext:253-271)
+      std::vector<double> buf((size_t)p.nitr);
+      for_points(*m, p, x, [&](Ctx& c) { buf[(size_t)c.k] = eval0(c, c.p->root); });
+      for (double v : buf) s += v;
+    }
+  }
+  return s;
+}
+
+// cons_nln! (nlp.jl:1841-1854)
+void ora_cons(void* h, const double* x, double* g) {
+  Model* m = (Model*)h;
+  std::fill(g, g + m->ncon, 0.0);
+  for (auto& p : m->pats) {
+    if (p.kind == KIND_OBJ) continue;
+    if (p.kind == KIND_CON) for_points(*m, p, x, [&](Ctx& c) { g[offset0(c) - 1] += eval0(c, c.p->root); });
+    else {   // augmentation rows collide across points: sequential (CPU path is sequential, nlp.jl:1849-1851)
+      Work w; w.size(p.t.size());
+      Ctx c; c.p = &p; c.X = x; c.TH = m->theta.data(); c.w = &w;
+      for (i64 k = 0; k < p.nitr; k++) { point(c, k); g[offset0(c) - 1] += eval0(c, p.root); }
+    }
+  }
+}
+
+// grad! (nlp.jl:1858-1868 -> gradient.jl:39-49 -> drpass)
+void ora_grad(void* h, const double* x, double* g) {
+  Model* m = (Model*)h;
+  std::fill(g, g + m->nvar, 0.0);
+  for (auto& p : m->pats) {
+    if (p.kind != KIND_OBJ) continue;
+    Work w; w.size(p.t.size());
+    Ctx c; c.p = &p; c.X = x; c.TH = m->theta.data(); c.w = &w;
+    Sink s; std::memset(&s, 0, sizeof s); s.mode = M_DENSE; s.y = g;
+    for (i64 k = 0; k < p.nitr; k++) {
+      point(c, k); fwd(c, p.root, 1); int cnt = 0; rpass1(c, p.root, s, cnt, 1.0);
+    }
+  }
+}
+
+// sparse gradient slots (ext:310-336 without the final compress): gradbuffer[nnzg]
+void ora_sgrad(void* h, const double* x, double* gb) {
+  Model* m = (Model*)h;
+  std::fill(gb, gb + m->nnzg, 0.0);
+  for (auto& p : m->pats) {
+    if (p.kind != KIND_OBJ) continue;
+    for_points(*m, p, x, [&](Ctx& c) {
+      const Pattern& q = *c.p;
+      fwd(c, q.root, 1);
+      Sink s; std::memset(&s, 0, sizeof s); s.mode = M_VALUES; s.y = gb; s.comp = q.comp1.data();
+      s.off = q.o1 + q.o1step * c.k; int cnt = 0; rpass1(c, q.root, s, cnt, 1.0);
+    });
+  }
+}
+
+// jac_coord! (nlp.jl:1870-1880 -> jacobian.jl:112-132)
+void ora_jac(void* h, const double* x, double* jac) {
+  Model* m = (Model*)h;
+  std::fill(jac, jac + m->nnzj, 0.0);
+  for (auto& p : m->pats) {
+    if (p.kind == KIND_OBJ) continue;
+    for_points(*m, p, x, [&](Ctx& c) {
+      const Pattern& q = *c.p;
+      fwd(c, q.root, 1);
+      Sink s; std::memset(&s, 0, sizeof s); s.mode = M_VALUES; s.y = jac; s.comp = q.comp1.data();
+      s.off = q.o1 + q.o1step * c.k; int cnt = 0; rpass1(c, q.root, s, cnt, 1.0);
+    });
+  }
+}
+
+// jac_structure! (nlp.jl:1798-1807 -> jacobian.jl:69-83): 1-based rows/cols
+void ora_jac_structure(void* h, i64* rows, i64* cols) {
+  Model* m = (Model*)h;
+  for (auto& p : m->pats) {
+    if (p.kind == KIND_OBJ) continue;
+    for_points(*m, p, nullptr, [&](Ctx& c) {
+      const Pattern& q = *c.p;
+      fwd(c, q.root, 1);
+      Sink s; std::memset(&s, 0, sizeof s); s.mode = M_STRUCT; s.rows = rows; s.cols = cols; s.comp = q.comp1.data();
+      s.off = q.o1 + q.o1step * c.k; s.row = offset0(c); int cnt = 0; rpass1(c, q.root, s, cnt, NAN);
+    });
+  }
+}
+
+// hess_coord! (nlp.jl:1906-1940 -> hessian.jl:681-717).  y == NULL: objective-only form (nlp.jl:1906-1915).
+void ora_hess(void* h, const double* x, const double* y, double obj_weight, double* hess) {
+  Model* m = (Model*)h;
+  std::fill(hess, hess + m->nnzh, 0.0);
+  for (auto& p : m->pats) {
+    if (p.kind != KIND_OBJ && !y) continue;
+    for_points(*m, p, x, [&](Ctx& c) {
+      const Pattern& q = *c.p;
+      fwd(c, q.root, 2);
+      double adj1 = q.kind == KIND_OBJ ? obj_weight : y[offset0(c) - 1];     // hessian.jl:708
+      Sink s; std::memset(&s, 0, sizeof s); s.mode = M_VALUES; s.y = hess; s.comp = q.comp2.data();
+      s.off = q.o2 + q.o2step * c.k; int cnt = 0; hrpass0(c, q.root, s, cnt, adj1, 0.0);
+    });
+  }
+}
+
+// hess_structure! (nlp.jl:1809-1825): lower triangle, 1-based
+void ora_hess_structure(void* h, i64* rows, i64* cols) {
+  Model* m = (Model*)h;
+  for (auto& p : m->pats) {
+    for_points(*m, p, nullptr, [&](Ctx& c) {
+      const Pattern& q = *c.p;
+      fwd(c, q.root, 2);
+      Sink s; std::memset(&s, 0, sizeof s); s.mode = M_STRUCT; s.rows = rows; s.cols = cols; s.comp = q.comp2.data();
+      s.off = q.o2 + q.o2step * c.k; int cnt = 0; hrpass0(c, q.root, s, cnt, NAN, NAN);
+    });
+  }
+}
+
+// jprod_nln! / jtprod_nln! / hprod! (nlp.jl:1882-1978): sequential (rows/cols collide)
+void ora_jprod(void* h, const double* x, const double* v, double* Jv) {
+  Model* m = (Model*)h;
+  std::fill(Jv, Jv + m->ncon, 0.0);
+  for (auto& p : m->pats) {
+    if (p.kind == KIND_OBJ) continue;
+    Work w; w.size(p.t.size());
+    Ctx c; c.p = &p; c.X = x; c.TH = m->theta.data(); c.w = &w;
+    for (i64 k = 0; k < p.nitr; k++) {
+      point(c, k); fwd(c, p.root, 1);
+      Sink s; std::memset(&s, 0, sizeof s); s.mode = M_JPROD; s.v = v; s.out = Jv; s.row = offset0(c);
+      int cnt = 0; rpass1(c, p.root, s, cnt, 1.0);
+    }
+  }
+}
+void ora_jtprod(void* h, const double* x, const double* v, double* Jtv) {
+  Model* m = (Model*)h;
+  std::fill(Jtv, Jtv + m->nvar, 0.0);
+  for (auto& p : m->pats) {
+    if (p.kind == KIND_OBJ) continue;
+    Work w; w.size(p.t.size());
+    Ctx c; c.p = &p; c.X = x; c.TH = m->theta.data(); c.w = &w;
+    for (i64 k = 0; k < p.nitr; k++) {
+      point(c, k); fwd(c, p.root, 1);
+      Sink s; std::memset(&s, 0, sizeof s); s.mode = M_JTPROD; s.v = v; s.out = Jtv; s.row = offset0(c);
+      int cnt = 0; rpass1(c, p.root, s, cnt, 1.0);
+    }
+  }
+}
+void ora_hprod(void* h, const double* x, const double* y, const double* v, double obj_weight, double* Hv) {
+  Model* m = (Model*)h;
+  std::fill(Hv, Hv + m->nvar, 0.0);
+  for (auto& p : m->pats) {
+    if (p.kind != KIND_OBJ && !y) continue;
+    Work w; w.size(p.t.size());
+    Ctx c; c.p = &p; c.X = x; c.TH = m->theta.data(); c.w = &w;
+    for (i64 k = 0; k < p.nitr; k++) {
+      point(c, k); fwd(c, p.root, 2);
+      double adj1 = p.kind == KIND_OBJ ? obj_weight : y[offset0(c) - 1];
+      Sink s; std::memset(&s, 0, sizeof s); s.mode = M_HPROD; s.v = v; s.out = Hv;
+      int cnt = 0; hrpass0(c, p.root, s, cnt, adj1, 0.0);
+    }
+  }
+}
+
+// Scalar tables for the ADTest-style pins (test/ADTest/ADTest.jl:298-342)
+void ora_uni(int op, double x, double* out) { uni(op, x, out[0], out[1], out[2], 1); }
+void ora_bi(int op, double x1, double x2, int e2_is_int, double* out) {
+  Real e1, e2; e1.is_int = false; e1.i = 0; e1.f = x1;
+  e2.is_int = e2_is_int != 0; e2.i = (i64)x2; e2.f = x2;
+  Bi r; bi(op, x1, x2, e1, e2, r, true, true);
+  out[0] = r.f; out[1] = r.y1; out[2] = r.y2; out[3] = r.h11; out[4] = r.h12; out[5] = r.h22;
+}
+
+}  // extern "C"
