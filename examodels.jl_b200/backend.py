@@ -1,0 +1,283 @@
+"""Host-side mirror of `ExaModel` + the NLPModels callback surface over the C ABI.
+
+Mirrors (reference file:line):
+  * `ExaModel(c; prod)` and `build_extension`          src/nlp.jl:765-798, 898;
+                                                      ext/ExaModelsKernelAbstractions.jl:33-191
+  * `obj, cons_nln!, grad!, jac_structure!, jac_coord!, hess_structure!, hess_coord!`
+                                                      src/nlp.jl:1798-1940 | ext:212-547
+  * meta (`NLPModelMeta`): nvar, ncon, nnzj, nnzh, x0, lvar, uvar, y0, lcon, ucon, minimize
+
+Every callback is ONE call into `libexa_b200.so` (include/exa_b200.h).  Arguments may be
+torch CUDA tensors (device pointers are passed through, work is enqueued on torch's current
+stream and not synchronised -- the KA callbacks never synchronise either) or numpy arrays
+(the `exb_host_*` shims copy through pinned staging, like `WrapperNLPModel`,
+src/utils.jl:16-267).  Mutating callbacks return their output argument, as in the reference.
+
+There is no CPU evaluation path here: without the CUDA library / a B200 every callback raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_LIBPATH = os.path.join(_CSRC, "libexa_b200.so")
+_LIB = None
+
+EXB_FLAG_NO_COMPILE = 1
+_ERRS = {1: "invalid handle", 2: "internal error", 3: "malformed IR", 4: "kernel module compile/load failed",
+         5: "CUDA error / no device", 6: "bad argument"}
+
+_SYMBOLS = """exb_plan_create exb_plan_destroy exb_plan_dims exb_plan_npatterns exb_plan_pattern exb_plan_comp
+exb_plan_source exb_plan_module_path exb_plan_compile exb_create exb_destroy exb_dims exb_set_params exb_obj
+exb_obj_async exb_grad exb_cons exb_jac_structure64 exb_jac_structure32 exb_jac exb_hess_structure64
+exb_hess_structure32 exb_hess exb_host_obj exb_host_grad exb_host_cons exb_host_jac exb_host_hess
+exb_host_jac_structure64 exb_host_hess_structure64 exb_shard exb_stats exb_last_error exb_abi_version""".split()
+
+
+class ExbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libexa_b200: {_ERRS.get(code, code)}: {msg}")
+        self.code = code
+
+
+def build_library(force=False):
+    """Compile libexa_b200.so in-tree (nvcc cross-compiles for sm_100a without a GPU)."""
+    srcs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)
+            if f.endswith((".cpp", ".cu", ".cuh", ".hpp", ".h")) and f != "exb_embed.cpp"]
+    srcs.append(os.path.join(_HERE, "..", "include", "exa_b200.h"))
+    stale = (not os.path.exists(_LIBPATH)
+             or any(os.path.getmtime(s) > os.path.getmtime(_LIBPATH) for s in srcs))
+    if force or stale:
+        subprocess.check_call(["make", "-s", "-C", _CSRC, "libexa_b200.so"])
+    return _LIBPATH
+
+
+def lib():
+    """Load the C-ABI library.  Raises if it is missing: there is no fallback path."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_LIBPATH):
+            raise ExbError(4, f"{_LIBPATH} is not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(_LIBPATH)
+        L.exb_last_error.restype = C.c_char_p
+        for s in _SYMBOLS:
+            getattr(L, s)  # every declared symbol must be exported
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise ExbError(rc, lib().exb_last_error().decode(errors="replace"))
+
+
+class _Options(C.Structure):
+    _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("flags", C.c_int32),
+                ("fuse_below", C.c_int64)]
+
+
+def _np_ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+class Plan:
+    """Host-only analysis of a core (no GPU needed): dims, per-pattern layout, generated source."""
+
+    def __init__(self, core):
+        self.ir, self.bufs = core.to_ir()
+        self.h = C.c_void_p()
+        _check(lib().exb_plan_create(self.ir, C.c_size_t(len(self.ir)), None, C.byref(self.h)))
+        d = np.zeros(8, dtype=np.int64)
+        _check(lib().exb_plan_dims(self.h, _np_ptr(d)))
+        (self.nvar, self.ncon, self.nnzj, self.nnzh, self.nobj, self.nnzg, self.nconaug,
+         self.npar) = (int(v) for v in d)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().exb_plan_destroy(self.h)
+        except Exception:
+            pass
+
+    def npatterns(self):
+        return int(lib().exb_plan_npatterns(self.h))
+
+    def pattern_info(self, k):
+        o = np.zeros(9, dtype=np.int64)
+        _check(lib().exb_plan_pattern(self.h, k, _np_ptr(o)))
+        keys = ("kind", "nitr", "o0", "o1", "o2", "o1step", "o2step", "ncomp1", "ncomp2")
+        return dict(zip(keys, (int(v) for v in o)))
+
+    def comp(self, k, which):
+        info = self.pattern_info(k)
+        o = np.zeros(max(1, info["ncomp1" if which == 1 else "ncomp2"]), dtype=np.int64)
+        _check(lib().exb_plan_comp(self.h, k, which, _np_ptr(o)))
+        return o[: info["ncomp1" if which == 1 else "ncomp2"]]
+
+    def source(self):
+        src, n = C.c_char_p(), C.c_size_t()
+        _check(lib().exb_plan_source(self.h, C.byref(src), C.byref(n)))
+        return src.value.decode()
+
+    def module_path(self):
+        buf = C.create_string_buffer(4096)
+        _check(lib().exb_plan_module_path(self.h, buf, C.c_size_t(4096)))
+        return buf.value.decode()
+
+    def compile(self):
+        """Run nvcc for this model's kernel module if it is not cached (works without a GPU)."""
+        _check(lib().exb_plan_compile(self.h))
+        return self.module_path()
+
+
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
+class ExaModel:
+    """`ExaModel(core)` on one B200 (or on shard `rank` of `world` when sharded)."""
+
+    def __init__(self, core, device=None, rank=0, world=1, allow_compile=True):
+        import torch  # device memory + streams only
+
+        self._torch = torch
+        if not torch.cuda.is_available():
+            raise ExbError(5, "no CUDA device: this evaluator has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device) \
+            if not isinstance(device, torch.device) else device
+        self.rank, self.world = int(rank), int(world)
+        self.core = core
+        meta = core.meta()
+        self.meta = meta
+        self.minimize = meta["minimize"]
+        self.x0, self.lvar, self.uvar = meta["x0"], meta["lvar"], meta["uvar"]
+        self.y0, self.lcon, self.ucon = meta["y0"], meta["lcon"], meta["ucon"]
+        ir, bufs = core.to_ir()
+        self._ir, self._bufs = ir, bufs
+        arr = (C.c_void_p * max(1, len(bufs)))(*[b.ctypes.data for b in bufs])
+        opt = _Options(self.device.index, self.rank, self.world, 0 if allow_compile else EXB_FLAG_NO_COMPILE, 0)
+        self.h = C.c_void_p()
+        _check(lib().exb_create(ir, C.c_size_t(len(ir)), arr, len(bufs), C.byref(opt), C.byref(self.h)))
+        d = np.zeros(8, dtype=np.int64)
+        _check(lib().exb_dims(self.h, _np_ptr(d)))
+        (self.nvar, self.ncon, self.nnzj, self.nnzh, self.nobj, self.nnzg, self.nconaug,
+         self.npar) = (int(v) for v in d)
+        self.npatterns = len(core.patterns)
+        if self.npar:
+            self.set_params(meta["theta"])
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().exb_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # -- helpers -----------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(self._torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, t, n, dtype=None):
+        torch = self._torch
+        dtype = torch.float64 if dtype is None else dtype
+        assert t.is_cuda and t.dtype == dtype and t.is_contiguous() and t.numel() == n, \
+            f"expected a contiguous CUDA {dtype} tensor of length {n}"
+        return C.c_void_p(t.data_ptr())
+
+    def _host(self, a, n, dtype=np.float64):
+        assert isinstance(a, np.ndarray) and a.dtype == dtype and a.flags.c_contiguous and a.size == n, \
+            f"expected a contiguous {dtype} array of length {n}"
+        return _np_ptr(a)
+
+    def new(self, n, dtype=None):
+        torch = self._torch
+        return torch.empty(n, dtype=torch.float64 if dtype is None else dtype, device=self.device)
+
+    def set_params(self, theta):
+        """`set_value!` on parameters (src/nlp.jl:1217-1287): upload θ."""
+        t = np.ascontiguousarray(theta, dtype=np.float64)
+        assert t.size == self.npar
+        _check(lib().exb_set_params(self.h, _np_ptr(t), self._stream()))
+        self._torch.cuda.current_stream(self.device).synchronize()
+
+    # -- callbacks (src/nlp.jl:1798-1940) --------------------------------------------
+    def obj(self, x):
+        out = C.c_double()
+        if _is_torch(x):
+            _check(lib().exb_obj(self.h, self._dev(x, self.nvar), C.byref(out), self._stream()))
+        else:
+            _check(lib().exb_host_obj(self.h, self._host(x, self.nvar), C.byref(out)))
+        return out.value
+
+    def obj_async(self, x, out):
+        """Objective left on the device (no synchronisation): `out` is a 1-element CUDA tensor."""
+        _check(lib().exb_obj_async(self.h, self._dev(x, self.nvar), self._dev(out, 1), self._stream()))
+        return out
+
+    def grad(self, x, g):
+        if _is_torch(x):
+            _check(lib().exb_grad(self.h, self._dev(x, self.nvar), self._dev(g, self.nvar), self._stream()))
+        else:
+            _check(lib().exb_host_grad(self.h, self._host(x, self.nvar), self._host(g, self.nvar)))
+        return g
+
+    def cons_nln(self, x, c):
+        if _is_torch(x):
+            _check(lib().exb_cons(self.h, self._dev(x, self.nvar), self._dev(c, self.ncon), self._stream()))
+        else:
+            _check(lib().exb_host_cons(self.h, self._host(x, self.nvar), self._host(c, self.ncon)))
+        return c
+
+    cons = cons_nln
+
+    def jac_coord(self, x, vals):
+        if _is_torch(x):
+            _check(lib().exb_jac(self.h, self._dev(x, self.nvar), self._dev(vals, self.nnzj), self._stream()))
+        else:
+            _check(lib().exb_host_jac(self.h, self._host(x, self.nvar), self._host(vals, self.nnzj)))
+        return vals
+
+    def hess_coord(self, x, y, vals, obj_weight=1.0):
+        """`hess_coord!(m, x, y, hess; obj_weight)`; `y=None` is the objective-only form."""
+        w = C.c_double(float(obj_weight))
+        if _is_torch(x):
+            yp = None if y is None else self._dev(y, self.ncon)
+            _check(lib().exb_hess(self.h, self._dev(x, self.nvar), yp, w, self._dev(vals, self.nnzh), self._stream()))
+        else:
+            yp = None if y is None else self._host(y, self.ncon)
+            _check(lib().exb_host_hess(self.h, self._host(x, self.nvar), yp, w, self._host(vals, self.nnzh)))
+        return vals
+
+    def _structure(self, which, n, rows, cols):
+        torch = self._torch
+        if _is_torch(rows):
+            assert rows.dtype == cols.dtype and rows.dtype in (torch.int64, torch.int32)
+            f = getattr(lib(), f"exb_{which}_structure{64 if rows.dtype == torch.int64 else 32}")
+            _check(f(self.h, self._dev(rows, n, rows.dtype), self._dev(cols, n, cols.dtype), self._stream()))
+        else:
+            f = getattr(lib(), f"exb_host_{which}_structure64")
+            _check(f(self.h, self._host(rows, n, np.int64), self._host(cols, n, np.int64)))
+        return rows, cols
+
+    def jac_structure(self, rows, cols):
+        return self._structure("jac", self.nnzj, rows, cols)
+
+    def hess_structure(self, rows, cols):
+        return self._structure("hess", self.nnzh, rows, cols)
+
+    # -- sharding / introspection ------------------------------------------------------
+    def shard(self, k):
+        o = np.zeros(6, dtype=np.int64)
+        _check(lib().exb_shard(self.h, k, _np_ptr(o)))
+        return dict(zip(("lo", "hi", "jac_lo", "jac_hi", "hess_lo", "hess_hi"), (int(v) for v in o)))
+
+    def stats(self):
+        o = np.zeros(4, dtype=np.int64)
+        _check(lib().exb_stats(self.h, _np_ptr(o)))
+        return dict(zip(("launches", "last_launches", "device_bytes", "module_cached"), (int(v) for v in o)))

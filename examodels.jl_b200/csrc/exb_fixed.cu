@@ -1,0 +1,133 @@
+// Fixed (model-independent) device code of the runtime library: the deterministic reductions
+// that follow the generated per-pattern kernels, and the build-time sort that prepares them.
+//
+//   exb_fx_compress   <- compress_to_dense   ext/ExaModelsKernelAbstractions.jl:691-697
+//   exb_fx_sum        <- sum(objbuffer)      ext:259
+//   exb_fx_sort_runs  <- sort! + getptr      ext:12-18,44-53,699-715   (build time; CUB radix sort)
+//
+// No atomics: every dense target is owned by one thread which adds its (pre-sorted) slots in a
+// fixed order, so grad! and the augmentation part of cons! are bitwise reproducible run to run.
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "exb_fixed.h"
+
+namespace {
+
+// one thread per distinct target: y[target[t]] (+)= sum_{l in [ptr[t], ptr[t+1])} buf[slot[l]]
+template <bool ACC>
+__global__ void __launch_bounds__(256) k_compress(const double* __restrict__ buf, const long long* __restrict__ ptr,
+                                                  const long long* __restrict__ slot, const long long* __restrict__ target,
+                                                  long long nt, double* __restrict__ y) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= nt) return;
+  const long long lo = __ldg(ptr + t), hi = __ldg(ptr + t + 1);
+  double s = 0.0;
+  for (long long l = lo; l < hi; l++) s += __ldg(buf + __ldg(slot + l));
+  const long long k = __ldg(target + t) - 1;
+  if (ACC) y[k] += s; else y[k] = s;
+}
+
+// deterministic sum of n partials into out[0]: fixed per-thread strided order + fixed tree
+__global__ void __launch_bounds__(1024) k_sum(const double* __restrict__ part, long long n, double* __restrict__ out) {
+  __shared__ double sm[32];
+  double v = 0.0;
+  for (long long k = threadIdx.x; k < n; k += 1024) v += part[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = sm[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) out[0] = v;
+  }
+}
+
+__global__ void k_fill_ll(long long* p, long long n, long long v) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t < n) p[t] = v;
+}
+__global__ void k_iota_ll(long long* p, long long n) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t < n) p[t] = t;
+}
+
+}  // namespace
+
+cudaError_t exb_fx_compress(const double* buf, const long long* ptr, const long long* slot, const long long* target,
+                            long long nt, double* y, int accumulate, cudaStream_t st) {
+  if (nt <= 0) return cudaSuccess;
+  const unsigned grid = (unsigned)((nt + 255) / 256);
+  if (accumulate) k_compress<true><<<grid, 256, 0, st>>>(buf, ptr, slot, target, nt, y);
+  else k_compress<false><<<grid, 256, 0, st>>>(buf, ptr, slot, target, nt, y);
+  return cudaGetLastError();
+}
+
+cudaError_t exb_fx_sum(const double* part, long long n, double* out, cudaStream_t st) {
+  k_sum<<<1, 1024, 0, st>>>(part, n, out);
+  return cudaGetLastError();
+}
+
+cudaError_t exb_fx_fill(long long* p, long long n, long long v, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  k_fill_ll<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
+  return cudaGetLastError();
+}
+
+// keys[n] (1-based targets; EXB_FX_SENTINEL = not owned by this handle) -> stable sort by key with the
+// slot number as payload, then run-length encode.  Outputs are freshly cudaMalloc'ed arrays sized to the
+// number of owned runs: *slot_out[n_owned], *target_out[nruns], *ptr_out[nruns + 1].
+cudaError_t exb_fx_sort_runs(const long long* keys, long long n, long long** slot_out, long long** target_out,
+                             long long** ptr_out, long long* nruns_out, cudaStream_t st) {
+  *slot_out = *target_out = *ptr_out = nullptr; *nruns_out = 0;
+  if (n <= 0) return cudaSuccess;
+  cudaError_t e;
+  long long *vals_in = nullptr, *keys_s = nullptr, *vals_s = nullptr, *uniq = nullptr, *cnt = nullptr, *d_nruns = nullptr;
+  void* tmp = nullptr; size_t tb = 0, tb2 = 0, tb3 = 0;
+#define EXB_FX_TRY(x) do { e = (x); if (e != cudaSuccess) goto fail; } while (0)
+  EXB_FX_TRY(cudaMalloc(&vals_in, n * 8)); EXB_FX_TRY(cudaMalloc(&keys_s, n * 8)); EXB_FX_TRY(cudaMalloc(&vals_s, n * 8));
+  EXB_FX_TRY(cudaMalloc(&uniq, n * 8)); EXB_FX_TRY(cudaMalloc(&cnt, (n + 1) * 8)); EXB_FX_TRY(cudaMalloc(&d_nruns, 8));
+  k_iota_ll<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(vals_in, n);
+  EXB_FX_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys_s, vals_in, vals_s, n, 0, 64, st));
+  EXB_FX_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, tb2, keys_s, uniq, cnt, d_nruns, n, st));
+  EXB_FX_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tb3, cnt, cnt, n + 1, st));
+  tb = tb > tb2 ? tb : tb2; tb = tb > tb3 ? tb : tb3;
+  EXB_FX_TRY(cudaMalloc(&tmp, tb ? tb : 8));
+  EXB_FX_TRY(cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys_s, vals_in, vals_s, n, 0, 64, st));
+  EXB_FX_TRY(cub::DeviceRunLengthEncode::Encode(tmp, tb, keys_s, uniq, cnt, d_nruns, n, st));
+  {
+    long long nruns = 0;
+    EXB_FX_TRY(cudaMemcpyAsync(&nruns, d_nruns, 8, cudaMemcpyDeviceToHost, st));
+    EXB_FX_TRY(cudaStreamSynchronize(st));
+    // the sentinel run (if any) sorts last: drop it
+    long long last_key = 0;
+    if (nruns > 0) {
+      EXB_FX_TRY(cudaMemcpy(&last_key, uniq + (nruns - 1), 8, cudaMemcpyDeviceToHost));
+      if (last_key == EXB_FX_SENTINEL) nruns -= 1;
+    }
+    if (nruns > 0) {
+      // counts -> ptr (exclusive scan over nruns + 1 entries; entry nruns is scratch)
+      EXB_FX_TRY(cudaMemsetAsync(cnt + nruns, 0, 8, st));
+      EXB_FX_TRY(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, cnt, nruns + 1, st));
+      long long nowned = 0;
+      EXB_FX_TRY(cudaMemcpyAsync(&nowned, cnt + nruns, 8, cudaMemcpyDeviceToHost, st));
+      EXB_FX_TRY(cudaStreamSynchronize(st));
+      EXB_FX_TRY(cudaMalloc(slot_out, (nowned ? nowned : 1) * 8));
+      EXB_FX_TRY(cudaMalloc(target_out, nruns * 8));
+      EXB_FX_TRY(cudaMalloc(ptr_out, (nruns + 1) * 8));
+      EXB_FX_TRY(cudaMemcpyAsync(*slot_out, vals_s, nowned * 8, cudaMemcpyDeviceToDevice, st));
+      EXB_FX_TRY(cudaMemcpyAsync(*target_out, uniq, nruns * 8, cudaMemcpyDeviceToDevice, st));
+      EXB_FX_TRY(cudaMemcpyAsync(*ptr_out, cnt, (nruns + 1) * 8, cudaMemcpyDeviceToDevice, st));
+      EXB_FX_TRY(cudaStreamSynchronize(st));
+    }
+    *nruns_out = nruns;
+  }
+  e = cudaSuccess;
+fail:
+#undef EXB_FX_TRY
+  cudaFree(vals_in); cudaFree(keys_s); cudaFree(vals_s); cudaFree(uniq); cudaFree(cnt); cudaFree(d_nruns); cudaFree(tmp);
+  return e;
+}

@@ -1,0 +1,678 @@
+// Plan = host-only analysis of a pattern IR + generation of the model's CUDA C++ kernel module.
+//
+// What is restated here (reference file:line, paths relative to /root/reference/):
+//   * the sparsity probe and `===` dedupe that fix o1step / o2step and the two Compressors
+//     (src/simdfunction.jl:66-100), by running the reverse passes symbolically;
+//   * the running counters that assign o0 / o1 / o2 in add order
+//     (src/nlp.jl:1448-1482, 1551-1611, 1680-1738);
+//   * the reverse passes themselves -- grpass / jrpass (src/gradient.jl:59-90,
+//     src/jacobian.jl:16-40), hrpass0 / hrpass / hdrpass (src/hessian.jl:16-517) -- which are
+//     UNROLLED AT GENERATION TIME into straight-line FP64 code per pattern: the recursion
+//     over the (static) tree happens here on the host, every adjoint product becomes one SSA
+//     temporary, and every leaf visit becomes an accumulation into a register-resident slot.
+//     Multiplications by the structural constants 1 / -1 / 0 of the linear operators
+//     (`+`, `-`, `c*x`, h12 of `*`) are folded away, which is where most of the
+//     reference's per-point FLOPs go.
+//
+// The device never sees a tree: a pattern is a struct with static member functions
+// (val / d1 / d2 / s1 / s2 / row) that the kernel templates of exb_device.cuh call.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "exb_ir.hpp"
+
+namespace exb {
+
+enum { K_REAL, K_NULL, K_VAR, K_N1, K_N2 };
+enum { FX_NONE, FX_FIRST, FX_SECOND };
+
+static const int EXB_MAXF_HOST = 16;  // must equal EXB_MAXF in exb_device.cuh
+static const int EXB_MAXD_HOST = 4;
+static const int EXB_TILE_MAX_NS_HOST = 20;
+
+struct NodeInfo { int kind = K_REAL; int fx = FX_NONE; bool is_int = false; };
+
+struct PatternPlan {
+  PatternIR ir;
+  std::vector<NodeInfo> info;
+  std::vector<int> comp1, comp2;
+  int o1step = 0, o2step = 0;
+  i64 o0 = 0, o1 = 0, o2 = 0;  // 0-based bases (SIMDFunction offsets)
+  i64 oa = 0;                  // aug: first conbuffer slot (ConstraintAugmentation.oa)
+  i64 ob = 0;                  // obj: first objbuffer slot
+  std::vector<int> leaf1;      // representative Var IR node per first-order slot
+  std::vector<std::pair<int, int>> leaf2;
+};
+
+struct Plan {
+  ModelIR m;
+  std::vector<PatternPlan> pats;
+  i64 ncon = 0, nobj = 0, nconaug = 0, nnzg = 0, nnzj = 0, nnzh = 0;
+  std::string source;  // generated module (without the device header)
+  std::string error;
+  // pattern lists per kernel (indices into pats), fixed at generation time
+  std::vector<int> k_hess, k_jac, k_sgrad, k_cons, k_obj, k_aug;
+};
+
+// ---------------------------------------------------------------------------------------
+// static analysis
+// ---------------------------------------------------------------------------------------
+inline bool real_op_int(int tag, int op, bool a_int, bool b_int) {
+  // Julia keeps Int arithmetic among Ints for these; everything else promotes to Float64
+  if (tag == T_OP1) return a_int && (op == U_PLUS || op == U_MINUS || op == U_ABS || op == U_ABS2);
+  return a_int && b_int && (op == B_ADD || op == B_SUB || op == B_MUL || op == B_MAX || op == B_MIN || op == B_POW);
+}
+
+inline void classify(PatternPlan& p) {
+  const auto& N = p.ir.nodes;
+  p.info.assign(N.size(), NodeInfo());
+  for (size_t k = 0; k < N.size(); k++) {
+    const IRNode& n = N[k];
+    NodeInfo& q = p.info[k];
+    switch (n.tag) {
+      case T_CONST_I: case T_VAL: case T_DATA_SELF: q.kind = K_REAL; q.is_int = true; break;
+      case T_CONST_F: case T_PAR: q.kind = K_REAL; break;
+      case T_DATA_FIELD: { q.kind = K_REAL; i64 t = p.ir.fields[(size_t)n.a].type; q.is_int = (t == FT_I64 || t == FT_I32); } break;
+      case T_VAR: q.kind = K_VAR; break;                               // graph.jl:397-400,491-494
+      case T_NULL: q.kind = K_NULL; break;                             // graph.jl:499-502
+      case T_OP1: {
+        const NodeInfo& a = p.info[(size_t)n.a];
+        if (a.kind == K_REAL) { q.kind = K_REAL; q.is_int = real_op_int(T_OP1, (int)n.payload, a.is_int, false); }
+        else q.kind = K_N1;                                            // register.jl:65-71
+      } break;
+      case T_OP2: {
+        const NodeInfo &a = p.info[(size_t)n.a], &b = p.info[(size_t)n.b];
+        bool r1 = a.kind == K_REAL, r2 = b.kind == K_REAL;
+        if (r1 && r2) { q.kind = K_REAL; q.is_int = real_op_int(T_OP2, (int)n.payload, a.is_int, b.is_int); }
+        else if (r2) { q.kind = K_N1; q.fx = FX_SECOND; }              // register.jl:231-248
+        else if (r1) { q.kind = K_N1; q.fx = FX_FIRST; }               // register.jl:249-266
+        else q.kind = K_N2;                                            // register.jl:209-230
+      } break;
+    }
+  }
+}
+
+inline bool ir_equal(const PatternIR& p, int a, int b) {   // Julia `===` on immutable node structs
+  if (a == b) return true;
+  const IRNode &x = p.nodes[(size_t)a], &y = p.nodes[(size_t)b];
+  if (x.tag != y.tag) return false;
+  switch (x.tag) {
+    case T_CONST_I: case T_CONST_F: case T_NULL: case T_VAL: return x.payload == y.payload;
+    case T_DATA_SELF: return true;
+    case T_DATA_FIELD: return x.a == y.a;
+    case T_VAR: case T_PAR: return ir_equal(p, (int)x.a, (int)y.a);
+    case T_OP1: return x.payload == y.payload && ir_equal(p, (int)x.a, (int)y.a);
+    case T_OP2: return x.payload == y.payload && ir_equal(p, (int)x.a, (int)y.a) && ir_equal(p, (int)x.b, (int)y.b);
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------
+// symbolic scalar: either a compile-time constant or the name of an SSA temporary
+// ---------------------------------------------------------------------------------------
+struct Ex { std::string s; bool c = false; double v = 0.0; };
+
+inline std::string dlit(double v) {
+  if (std::isnan(v)) return "exb_nan()";
+  if (std::isinf(v)) return v > 0 ? "exb_inf()" : "(-exb_inf())";
+  char buf[64];
+  snprintf(buf, sizeof buf, "%.17g", v);
+  std::string s = buf;
+  if (s.find_first_of(".eE") == std::string::npos) s += ".0";
+  if (v < 0 || (v == 0 && std::signbit(v))) s = "(" + s + ")";
+  return s;
+}
+inline Ex K(double v) { Ex e; e.c = true; e.v = v; e.s = dlit(v); return e; }
+inline Ex Sym(const std::string& s) { Ex e; e.s = s; return e; }
+
+// A generated function body: SSA lines with hash-consing of identical right-hand sides.
+struct Body {
+  std::vector<std::string> lines;
+  std::map<std::string, std::string> memo;
+  int ntmp = 0;
+  bool quiet = false;  // probe mode: no code is produced
+  std::string tmp(const std::string& type, const std::string& rhs) {
+    if (quiet) return "_";
+    auto it = memo.find(rhs);
+    if (it != memo.end()) return it->second;
+    std::string name = "t" + std::to_string(ntmp++);
+    lines.push_back("const " + type + " " + name + " = " + rhs + ";");
+    memo[rhs] = name;
+    return name;
+  }
+  void raw(const std::string& l) { if (!quiet) lines.push_back(l); }
+  Ex mul(const Ex& a, const Ex& b) {
+    if (a.c && b.c) return K(a.v * b.v);
+    if (a.c) { if (a.v == 0) return K(0); if (a.v == 1) return b; if (a.v == -1) return neg(b); }
+    if (b.c) { if (b.v == 0) return K(0); if (b.v == 1) return a; if (b.v == -1) return neg(a); }
+    return Sym(tmp("double", a.s + " * " + b.s));
+  }
+  Ex add(const Ex& a, const Ex& b) {
+    if (a.c && b.c) return K(a.v + b.v);
+    if (a.c && a.v == 0) return b;
+    if (b.c && b.v == 0) return a;
+    return Sym(tmp("double", a.s + " + " + b.s));
+  }
+  Ex sub(const Ex& a, const Ex& b) {
+    if (a.c && b.c) return K(a.v - b.v);
+    if (b.c && b.v == 0) return a;
+    if (a.c && a.v == 0) return neg(b);
+    return Sym(tmp("double", a.s + " - " + b.s));
+  }
+  Ex neg(const Ex& a) {
+    if (a.c) return K(-a.v);
+    return Sym(tmp("double", "-" + a.s));
+  }
+  Ex sq(const Ex& a) { return mul(a, a); }
+};
+
+// forward image of one IR node inside one generated function
+struct NV {
+  bool done = false;
+  // K_REAL
+  bool is_int = false, lit = false; i64 iv = 0; std::string rs;  // rs: C++ expression (name or literal)
+  // value kinds
+  Ex x, y1, y2, h11, h12, h22;
+  std::string idx;  // K_VAR: name of the evaluated (1-based) variable index
+};
+
+struct Gen {
+  const PatternPlan& p;
+  Body& B;
+  int order;  // 0 value, 1 first-order tape, 2 second-order tape
+  std::vector<NV> nv;
+  // leaf sinks
+  int cnt = 0;
+  std::vector<Ex> slot;                           // symbolic accumulators
+  std::vector<int>* raw1 = nullptr;               // probe outputs
+  std::vector<std::pair<int, int>>* raw2 = nullptr;
+  const std::vector<int>* comp = nullptr;
+
+  Gen(const PatternPlan& pp, Body& b, int ord) : p(pp), B(b), order(ord), nv(pp.ir.nodes.size()) {}
+
+  const IRNode& N(int n) const { return p.ir.nodes[(size_t)n]; }
+  const NodeInfo& I(int n) const { return p.info[(size_t)n]; }
+  int inner_of(int n) const { return (N(n).tag == T_OP2 && I(n).fx == FX_FIRST) ? (int)N(n).b : (int)N(n).a; }
+
+  // ---- Real (variable-free) subtrees: graph.jl:305-318, register.jl:70,268-273 ----------
+  static std::string ilit(i64 v) { return v < 0 ? "(" + std::to_string(v) + "LL)" : std::to_string(v) + "LL"; }
+  std::string as_double(const NV& r) {
+    if (r.is_int) return r.lit ? dlit((double)r.iv) : "(double)" + r.rs;
+    return r.rs;
+  }
+  Ex real_ex(int n) {   // a Real node as a double-valued symbolic scalar
+    NV& r = real(n);
+    if (r.lit) return K(r.is_int ? (double)r.iv : r.x.v);
+    return Sym(as_double(r));
+  }
+  NV& real(int n) {
+    NV& r = nv[(size_t)n];
+    if (r.done) return r;
+    r.done = true;
+    const IRNode& q = N(n);
+    r.is_int = I(n).is_int;
+    switch (q.tag) {
+      case T_CONST_I: case T_VAL: r.lit = true; r.iv = q.payload; r.rs = ilit(q.payload); break;
+      case T_CONST_F: { double v; std::memcpy(&v, &q.payload, 8); r.lit = true; r.x = K(v); r.rs = dlit(v); } break;
+      case T_DATA_SELF: r.rs = B.tmp("long long", "pa.start + kg"); break;
+      case T_DATA_FIELD:
+        if (r.is_int) r.rs = B.tmp("long long", "exb_ld_i(pa, " + std::to_string(q.a) + ", kg)");
+        else r.rs = B.tmp("double", "exb_ld_f(pa, " + std::to_string(q.a) + ", kg)");
+        break;
+      case T_PAR: { NV& ix = real((int)q.a); r.rs = B.tmp("double", "__ldg(th + (" + ix.rs + " - 1))"); } break;  // graph.jl:310-311
+      case T_OP1: {
+        NV& a = real((int)q.a);
+        int op = (int)q.payload;
+        if (r.is_int) {
+          const char* f = op == U_PLUS ? "+" : op == U_MINUS ? "-" : nullptr;
+          if (f) r.rs = B.tmp("long long", std::string(f) + a.rs);
+          else if (op == U_ABS) r.rs = B.tmp("long long", "(" + a.rs + " < 0 ? -" + a.rs + " : " + a.rs + ")");
+          else r.rs = B.tmp("long long", a.rs + " * " + a.rs);
+        } else {
+          r.rs = B.tmp("double", "exb_f1<" + std::to_string(op) + ">(" + as_double(a) + ")");
+        }
+      } break;
+      case T_OP2: {
+        NV &a = real((int)q.a), &b = real((int)q.b);
+        int op = (int)q.payload;
+        if (r.is_int) {
+          switch (op) {
+            case B_ADD: r.rs = B.tmp("long long", a.rs + " + " + b.rs); break;
+            case B_SUB: r.rs = B.tmp("long long", a.rs + " - " + b.rs); break;
+            case B_MUL: r.rs = B.tmp("long long", a.rs + " * " + b.rs); break;
+            case B_MAX: r.rs = B.tmp("long long", "exb_imax(" + a.rs + ", " + b.rs + ")"); break;
+            case B_MIN: r.rs = B.tmp("long long", "exb_imin(" + a.rs + ", " + b.rs + ")"); break;
+            default: r.rs = B.tmp("long long", "exb_ipow(" + a.rs + ", " + b.rs + ")");
+          }
+        } else if (op == B_POW && b.is_int) {   // Float64 ^ Int
+          r.rs = B.tmp("double", "exb_powi(" + as_double(a) + ", " + b.rs + ")");
+        } else {
+          r.rs = B.tmp("double", "exb_f2<" + std::to_string(op) + ">(" + as_double(a) + ", " + as_double(b) + ")");
+        }
+      } break;
+      default: r.rs = "exb_nan()";
+    }
+    return r;
+  }
+
+  // ---- forward sweep over value kinds (graph.jl:397-400,491-494; register.jl:65-68,174-266) ----
+  std::string fresh(const char* pre, int n) { return std::string(pre) + std::to_string(n); }
+  NV& fwd(int n) {
+    NV& r = nv[(size_t)n];
+    if (r.done) return r;
+    const IRNode& q = N(n);
+    const NodeInfo& in = I(n);
+    if (in.kind == K_REAL) { NV& rr = real(n); rr.x = real_ex(n); return rr; }
+    r.done = true;
+    const std::string O = std::to_string(order);
+    if (in.kind == K_NULL) { double v; std::memcpy(&v, &q.payload, 8); r.x = K(v); return r; }
+    if (in.kind == K_VAR) {
+      NV& ix = real((int)q.a);
+      r.idx = ix.rs;
+      r.x = Sym(B.tmp("double", "__ldg(x + (" + ix.rs + " - 1))"));
+      return r;
+    }
+    if (q.tag == T_OP1) {
+      NV& a = fwd((int)q.a);
+      int op = (int)q.payload;
+      switch (op) {
+        case U_PLUS: r.x = a.x; r.y1 = K(1); r.h11 = K(0); return r;
+        case U_MINUS: r.x = B.neg(a.x); r.y1 = K(-1); r.h11 = K(0); return r;
+        case U_ABS2: r.x = B.mul(a.x, a.x); r.y1 = B.mul(K(2), a.x); r.h11 = K(2); return r;
+      }
+      if (order == 0) { r.x = Sym(B.tmp("double", "exb_f1<" + std::to_string(op) + ">(" + a.x.s + ")")); return r; }
+      std::string f = fresh("f", n), d = fresh("d", n), dd = fresh("dd", n);
+      B.raw("double " + f + ", " + d + ", " + dd + "; exb_uni<" + std::to_string(op) + ", " + O + ">(" + a.x.s + ", " + f + ", " + d + ", " + dd + ");");
+      r.x = Sym(f); r.y1 = Sym(d); r.h11 = Sym(dd);
+      switch (op) {   // structurally constant derivatives
+        case U_ABS: case U_DEG2RAD: case U_RAD2DEG: r.h11 = K(0); break;
+        case U_SIGN: case U_SIGNBIT: case U_FLOOR: case U_CEIL: r.y1 = K(0); r.h11 = K(0); break;
+      }
+      return r;
+    }
+    // T_OP2
+    int op = (int)q.payload;
+    if (in.kind == K_N2) {
+      NV &a = fwd((int)q.a), &b = fwd((int)q.b);
+      switch (op) {
+        case B_ADD: r.x = B.add(a.x, b.x); r.y1 = K(1); r.y2 = K(1); r.h11 = r.h12 = r.h22 = K(0); return r;
+        case B_SUB: r.x = B.sub(a.x, b.x); r.y1 = K(1); r.y2 = K(-1); r.h11 = r.h12 = r.h22 = K(0); return r;
+        case B_MUL: r.x = B.mul(a.x, b.x); r.y1 = b.x; r.y2 = a.x; r.h11 = K(0); r.h12 = K(1); r.h22 = K(0); return r;
+      }
+      if (order == 0) { r.x = Sym(B.tmp("double", "exb_f2<" + std::to_string(op) + ">(" + a.x.s + ", " + b.x.s + ")")); return r; }
+      std::string f = fresh("f", n), u1 = fresh("ya", n), u2 = fresh("yb", n), g11 = fresh("haa", n), g12 = fresh("hab", n), g22 = fresh("hbb", n);
+      B.raw("double " + f + ", " + u1 + ", " + u2 + ", " + g11 + ", " + g12 + ", " + g22 + "; exb_bi<" + std::to_string(op) + ", " + O + ">(" +
+            a.x.s + ", " + b.x.s + ", " + f + ", " + u1 + ", " + u2 + ", " + g11 + ", " + g12 + ", " + g22 + ");");
+      r.x = Sym(f); r.y1 = Sym(u1); r.y2 = Sym(u2); r.h11 = Sym(g11); r.h12 = Sym(g12); r.h22 = Sym(g22);
+      if (op == B_DIV) r.h11 = K(0);
+      if (op == B_MAX || op == B_MIN) r.h11 = r.h12 = r.h22 = K(0);
+      return r;
+    }
+    // one Real operand: a Node1 carrying (f, df, ddf) w.r.t. the node operand only
+    const bool second_fixed = in.fx == FX_SECOND;   // node OP real
+    NV& a = fwd(second_fixed ? (int)q.a : (int)q.b);
+    const int rn = second_fixed ? (int)q.b : (int)q.a;
+    NV& cr = real(rn);
+    Ex c = real_ex(rn);
+    switch (op) {
+      case B_ADD: r.x = second_fixed ? B.add(a.x, c) : B.add(c, a.x); r.y1 = K(1); r.h11 = K(0); return r;
+      case B_SUB:
+        if (second_fixed) { r.x = B.sub(a.x, c); r.y1 = K(1); } else { r.x = B.sub(c, a.x); r.y1 = K(-1); }
+        r.h11 = K(0); return r;
+      case B_MUL: r.x = second_fixed ? B.mul(a.x, c) : B.mul(c, a.x); r.y1 = c; r.h11 = K(0); return r;
+    }
+    if (op == B_DIV && second_fixed) {   // x / c: (1/c, 0)
+      r.x = Sym(B.tmp("double", a.x.s + " / " + c.s));
+      r.y1 = c.c ? K(1.0 / c.v) : Sym(B.tmp("double", "1.0 / " + c.s));
+      r.h11 = K(0);
+      return r;
+    }
+    if (op == B_POW && second_fixed) {
+      if (order == 0) {
+        r.x = cr.is_int ? Sym(B.tmp("double", "exb_powi(" + a.x.s + ", " + cr.rs + ")"))
+                        : Sym(B.tmp("double", "pow(" + a.x.s + ", " + c.s + ")"));
+        return r;
+      }
+      std::string f = fresh("f", n), d = fresh("d", n), dd = fresh("dd", n);
+      if (cr.is_int) B.raw("double " + f + ", " + d + ", " + dd + "; exb_pow_int<" + O + ">(" + a.x.s + ", " + cr.rs + ", " + f + ", " + d + ", " + dd + ");");
+      else B.raw("double " + f + ", " + d + ", " + dd + "; exb_pow_flt<" + O + ">(" + a.x.s + ", " + c.s + ", " + f + ", " + d + ", " + dd + ");");
+      r.x = Sym(f); r.y1 = Sym(d); r.h11 = Sym(dd);
+      if (cr.is_int && cr.lit && (cr.iv == 0 || cr.iv == 1)) r.h11 = K(0);
+      return r;
+    }
+    // generic: evaluate the full bivariate table and keep the operand's entries
+    {
+      const std::string x1 = second_fixed ? a.x.s : c.s, x2 = second_fixed ? c.s : a.x.s;
+      if (order == 0) { r.x = Sym(B.tmp("double", "exb_f2<" + std::to_string(op) + ">(" + x1 + ", " + x2 + ")")); return r; }
+      std::string f = fresh("f", n), u1 = fresh("ya", n), u2 = fresh("yb", n), g11 = fresh("haa", n), g12 = fresh("hab", n), g22 = fresh("hbb", n);
+      B.raw("double " + f + ", " + u1 + ", " + u2 + ", " + g11 + ", " + g12 + ", " + g22 + "; exb_bi<" + std::to_string(op) + ", " + O + ">(" +
+            x1 + ", " + x2 + ", " + f + ", " + u1 + ", " + u2 + ", " + g11 + ", " + g12 + ", " + g22 + ");");
+      r.x = Sym(f);
+      r.y1 = Sym(second_fixed ? u1 : u2);
+      r.h11 = Sym(second_fixed ? g11 : g22);
+      if (op == B_MAX || op == B_MIN) r.h11 = K(0);
+      return r;
+    }
+  }
+
+  // ---- leaf sinks ------------------------------------------------------------------------
+  void leaf1(int n, const Ex& adj) {
+    if (raw1) { raw1->push_back(n); return; }
+    int j = (*comp)[(size_t)cnt++] - 1;
+    slot[(size_t)j] = B.add(slot[(size_t)j], adj);
+  }
+  void leafd(int n, const Ex& adj2) {   // hessian.jl:580-592 (values), :533-536 (probe)
+    if (raw2) { raw2->push_back(std::make_pair(n, n)); return; }
+    int j = (*comp)[(size_t)cnt++] - 1;
+    slot[(size_t)j] = B.add(slot[(size_t)j], adj2);
+  }
+  void leaf2(int a, int b, const Ex& adj) {   // hessian.jl:251-268 (values), :520-532 (probe)
+    if (raw2) { raw2->push_back(std::make_pair(a, b)); return; }
+    int j = (*comp)[(size_t)cnt++] - 1;
+    if (adj.c && adj.v == 0) return;
+    Ex v;
+    if (ir_equal(p.ir, (int)N(a).a, (int)N(b).a)) v = B.mul(K(2), adj);     // i == j structurally
+    else v = Sym(B.tmp("double", "exb_twice_if_eq(" + nv[(size_t)a].idx + ", " + nv[(size_t)b].idx + ", " + adj.s + ")"));
+    slot[(size_t)j] = B.add(slot[(size_t)j], v);
+  }
+
+  // ---- reverse passes, unrolled symbolically ----------------------------------------------
+  const NV& T(int n) const { return nv[(size_t)n]; }
+  void rpass1(int n, const Ex& adj) {   // gradient.jl:59-90, jacobian.jl:16-40
+    switch (I(n).kind) {
+      case K_REAL: case K_NULL: return;
+      case K_N1: rpass1(inner_of(n), B.mul(adj, T(n).y1)); return;
+      case K_N2:
+        rpass1((int)N(n).a, B.mul(adj, T(n).y1));
+        rpass1((int)N(n).b, B.mul(adj, T(n).y2));
+        return;
+      case K_VAR: leaf1(n, adj); return;
+    }
+  }
+  void hdrpass(int a, int b, const Ex& adj) {   // hessian.jl:16-320
+    const int k1 = I(a).kind, k2 = I(b).kind;
+    if (k1 == K_NULL || k2 == K_NULL || k1 == K_REAL || k2 == K_REAL) return;   // :318-320
+    if (k1 == K_VAR && k2 == K_VAR) { leaf2(a, b, adj); return; }                // :251-268
+    if (k1 == K_N1 && k2 == K_N1) { hdrpass(inner_of(a), inner_of(b), B.mul(B.mul(adj, T(a).y1), T(b).y1)); return; }   // :16-28
+    if (k1 == K_VAR && k2 == K_N1) { hdrpass(a, inner_of(b), B.mul(adj, T(b).y1)); return; }   // :44-56
+    if (k1 == K_N1 && k2 == K_VAR) { hdrpass(inner_of(a), b, B.mul(adj, T(a).y1)); return; }   // :72-84
+    if (k1 == K_N2 && k2 == K_N2) {                                              // :100-115
+      hdrpass((int)N(a).a, (int)N(b).a, B.mul(B.mul(adj, T(a).y1), T(b).y1));
+      hdrpass((int)N(a).a, (int)N(b).b, B.mul(B.mul(adj, T(a).y1), T(b).y2));
+      hdrpass((int)N(a).b, (int)N(b).a, B.mul(B.mul(adj, T(a).y2), T(b).y1));
+      hdrpass((int)N(a).b, (int)N(b).b, B.mul(B.mul(adj, T(a).y2), T(b).y2));
+      return;
+    }
+    if (k1 == K_N1 && k2 == K_N2) {                                              // :134-147
+      hdrpass(inner_of(a), (int)N(b).a, B.mul(B.mul(adj, T(a).y1), T(b).y1));
+      hdrpass(inner_of(a), (int)N(b).b, B.mul(B.mul(adj, T(a).y1), T(b).y2));
+      return;
+    }
+    if (k1 == K_N2 && k2 == K_N1) {                                              // :163-176
+      hdrpass((int)N(a).a, inner_of(b), B.mul(B.mul(adj, T(a).y1), T(b).y1));
+      hdrpass((int)N(a).b, inner_of(b), B.mul(B.mul(adj, T(a).y2), T(b).y1));
+      return;
+    }
+    if (k1 == K_VAR && k2 == K_N2) {                                             // :192-205
+      hdrpass(a, (int)N(b).a, B.mul(adj, T(b).y1));
+      hdrpass(a, (int)N(b).b, B.mul(adj, T(b).y2));
+      return;
+    }
+    if (k1 == K_N2 && k2 == K_VAR) {                                             // :221-234
+      hdrpass((int)N(a).a, b, B.mul(adj, T(a).y1));
+      hdrpass((int)N(a).b, b, B.mul(adj, T(a).y2));
+      return;
+    }
+  }
+  void hrpass(int n, const Ex& adj, const Ex& adj2) {   // hessian.jl:337-380
+    switch (I(n).kind) {
+      case K_REAL: case K_NULL: return;
+      case K_N1:
+        hrpass(inner_of(n), B.mul(adj, T(n).y1), B.add(B.mul(adj2, B.sq(T(n).y1)), B.mul(adj, T(n).h11)));
+        return;
+      case K_N2: {
+        Ex cross = B.add(B.mul(B.mul(adj2, T(n).y1), T(n).y2), B.mul(adj, T(n).h12));
+        hrpass((int)N(n).a, B.mul(adj, T(n).y1), B.add(B.mul(adj2, B.sq(T(n).y1)), B.mul(adj, T(n).h11)));
+        hrpass((int)N(n).b, B.mul(adj, T(n).y2), B.add(B.mul(adj2, B.sq(T(n).y2)), B.mul(adj, T(n).h22)));
+        hdrpass((int)N(n).a, (int)N(n).b, cross);
+        return;
+      }
+      case K_VAR: leafd(n, adj2); return;
+    }
+  }
+  void hrpass0(int n, const Ex& adj, const Ex& adj2) {   // hessian.jl:382-517
+    const NodeInfo& in = I(n);
+    if (in.kind == K_VAR) return;                                                // :494-517
+    if (in.kind == K_N1) {
+      int c = inner_of(n);
+      int op = (int)N(n).payload;
+      if (N(n).tag == T_OP2) {
+        if (op == B_MUL) { hrpass0(c, B.mul(adj, T(n).y1), B.mul(adj2, B.sq(T(n).y1))); return; }   // :385-397
+        if (op == B_ADD) { hrpass0(c, adj, adj2); return; }                                        // :398-410
+        if (op == B_SUB && in.fx == FX_FIRST) { hrpass0(c, B.neg(adj), adj2); return; }            // :411-423
+        if (op == B_SUB && in.fx == FX_SECOND) { hrpass0(c, adj, adj2); return; }                  // :424-436
+      } else {
+        if (op == U_PLUS) { hrpass0(c, adj, adj2); return; }                     // :438-450
+        if (op == U_MINUS) { hrpass0(c, B.neg(adj), adj2); return; }             // :451-463
+      }
+    }
+    if (in.kind == K_N2 && N(n).payload == B_ADD) {                              // :465-478
+      hrpass0((int)N(n).a, adj, adj2); hrpass0((int)N(n).b, adj, adj2); return;
+    }
+    if (in.kind == K_N2 && N(n).payload == B_SUB) {                              // :480-493
+      hrpass0((int)N(n).a, adj, adj2); hrpass0((int)N(n).b, B.neg(adj), adj2); return;
+    }
+    hrpass(n, adj, adj2);                                                        // :382
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// probe + counters
+// ---------------------------------------------------------------------------------------
+inline void probe(PatternPlan& p) {   // simdfunction.jl:66-100
+  Body B; B.quiet = true;
+  std::vector<int> raw1; std::vector<std::pair<int, int>> raw2;
+  {
+    Gen g(p, B, 1); g.raw1 = &raw1;
+    g.rpass1(p.ir.root, K(1));
+  }
+  {
+    Gen g(p, B, 2); g.raw2 = &raw2;
+    g.hrpass0(p.ir.root, Sym("_"), K(0));
+  }
+  p.comp1.clear(); p.comp2.clear(); p.leaf1.clear(); p.leaf2.clear();
+  for (int v : raw1) {   // _ident_unique, :66-76
+    int found = -1;
+    for (size_t q = 0; q < p.leaf1.size(); q++) if (ir_equal(p.ir, p.leaf1[q], v)) { found = (int)q; break; }
+    if (found < 0) { p.leaf1.push_back(v); found = (int)p.leaf1.size() - 1; }
+    p.comp1.push_back(found + 1);
+  }
+  p.o1step = (int)p.leaf1.size();
+  for (auto& v : raw2) {
+    int found = -1;
+    for (size_t q = 0; q < p.leaf2.size(); q++)
+      if (ir_equal(p.ir, p.leaf2[q].first, v.first) && ir_equal(p.ir, p.leaf2[q].second, v.second)) { found = (int)q; break; }
+    if (found < 0) { p.leaf2.push_back(v); found = (int)p.leaf2.size() - 1; }
+    p.comp2.push_back(found + 1);
+  }
+  p.o2step = (int)p.leaf2.size();
+}
+
+// ---------------------------------------------------------------------------------------
+// code generation
+// ---------------------------------------------------------------------------------------
+inline void emit_fn(std::ostringstream& o, const std::string& sig, const Body& B, const std::vector<std::string>& tail) {
+  o << "  __device__ static __forceinline__ " << sig << " {\n";
+  for (auto& l : B.lines) o << "    " << l << "\n";
+  for (auto& l : tail) o << "    " << l << "\n";
+  o << "  }\n";
+}
+
+inline std::string gen_pattern(const PatternPlan& p, int index) {
+  std::ostringstream o;
+  const int ns1 = p.o1step, ns2 = p.o2step;
+  const int a1 = ns1 > 0 ? ns1 : 1, a2 = ns2 > 0 ? ns2 : 1;
+  const std::string A = "const ExbPatArgs& pa, const long long kg";
+  o << "struct P" << index << " {\n";
+  o << "  static constexpr int KIND = " << p.ir.kind << ", NS1 = " << ns1 << ", NS2 = " << ns2 << ";\n";
+  {  // row (offset0, nlp.jl:1980-2001; idxx :2012-2015)
+    Body B; Gen g(p, B, 0);
+    std::vector<std::string> tail;
+    if (p.ir.kind == KIND_CON) tail.push_back("return pa.o0 + kg + 1;");
+    else if (p.ir.kind == KIND_OBJ) tail.push_back("return 0;");
+    else if (p.ir.idx_roots.size() == 1) {
+      NV& r = g.real(p.ir.idx_roots[0]);
+      tail.push_back("return pa.o0 + " + r.rs + ";");
+    } else {
+      std::string lin = "0LL", a = "1LL";
+      for (size_t d = 0; d < p.ir.idx_roots.size(); d++) {
+        NV& r = g.real(p.ir.idx_roots[d]);
+        lin = B.tmp("long long", lin + " + " + a + " * (" + r.rs + " - 1)");
+        a = B.tmp("long long", a + " * pa.dim[" + std::to_string(d) + "]");
+      }
+      tail.push_back("return pa.o0 + " + lin + " + 1;");
+    }
+    emit_fn(o, "long long row(" + A + ")", B, tail);
+  }
+  {  // val
+    Body B; Gen g(p, B, 0);
+    NV& r = g.fwd(p.ir.root);
+    emit_fn(o, "double val(" + A + ", const double* __restrict__ x, const double* __restrict__ th)", B, {"return " + r.x.s + ";"});
+  }
+  {  // d1
+    Body B; Gen g(p, B, 1);
+    std::vector<std::string> tail;
+    if (ns1 > 0) {
+      g.fwd(p.ir.root);
+      g.comp = &p.comp1; g.slot.assign((size_t)ns1, K(0));
+      g.rpass1(p.ir.root, K(1));
+      for (int j = 0; j < ns1; j++) tail.push_back("s[" + std::to_string(j) + "] = " + g.slot[(size_t)j].s + ";");
+    }
+    emit_fn(o, "void d1(" + A + ", const double* __restrict__ x, const double* __restrict__ th, double (&s)[" + std::to_string(a1) + "])", B, tail);
+  }
+  {  // d2
+    Body B; Gen g(p, B, 2);
+    std::vector<std::string> tail;
+    if (ns2 > 0) {
+      g.fwd(p.ir.root);
+      g.comp = &p.comp2; g.slot.assign((size_t)ns2, K(0));
+      g.hrpass0(p.ir.root, Sym("a0"), K(0));
+      for (int j = 0; j < ns2; j++) tail.push_back("s[" + std::to_string(j) + "] = " + g.slot[(size_t)j].s + ";");
+    }
+    emit_fn(o, "void d2(" + A + ", const double* __restrict__ x, const double* __restrict__ th, const double a0, double (&s)[" + std::to_string(a2) + "])", B, tail);
+  }
+  {  // s1: variable index per first-order slot (jacobian.jl:69-83)
+    Body B; Gen g(p, B, 0);
+    std::vector<std::string> tail;
+    for (int j = 0; j < ns1; j++) {
+      NV& ix = g.real((int)p.ir.nodes[(size_t)p.leaf1[(size_t)j]].a);
+      tail.push_back("col[" + std::to_string(j) + "] = " + ix.rs + ";");
+    }
+    emit_fn(o, "void s1(" + A + ", long long (&col)[" + std::to_string(a1) + "])", B, tail);
+  }
+  {  // s2: (max, min) per second-order slot (hessian.jl:593-607,622-642)
+    Body B; Gen g(p, B, 0);
+    std::vector<std::string> tail;
+    for (int j = 0; j < ns2; j++) {
+      NV& ia = g.real((int)p.ir.nodes[(size_t)p.leaf2[(size_t)j].first].a);
+      NV& ib = g.real((int)p.ir.nodes[(size_t)p.leaf2[(size_t)j].second].a);
+      tail.push_back("r[" + std::to_string(j) + "] = exb_imax(" + ia.rs + ", " + ib.rs + "); c[" + std::to_string(j) + "] = exb_imin(" + ia.rs + ", " + ib.rs + ");");
+    }
+    emit_fn(o, "void s2(" + A + ", long long (&r)[" + std::to_string(a2) + "], long long (&c)[" + std::to_string(a2) + "])", B, tail);
+  }
+  o << "};\n";
+  return o.str();
+}
+
+inline std::string plist(const std::vector<int>& v) {
+  std::string s;
+  for (size_t k = 0; k < v.size(); k++) { if (k) s += ", "; s += "P" + std::to_string(v[k]); }
+  return s;
+}
+
+inline bool build_plan(Plan& pl, const void* ir, size_t bytes) {
+  if (!parse_ir(ir, bytes, pl.m, pl.error)) return false;
+  pl.pats.resize(pl.m.pats.size());
+  for (size_t k = 0; k < pl.pats.size(); k++) {
+    PatternPlan& p = pl.pats[k];
+    p.ir = pl.m.pats[k];
+    if ((int)p.ir.fields.size() > EXB_MAXF_HOST) { pl.error = "a pattern reads more than 16 distinct iterator fields"; return false; }
+    if ((int)p.ir.idx_roots.size() > EXB_MAXD_HOST) { pl.error = "augmentation index has more than 4 dimensions"; return false; }
+    classify(p);
+    for (size_t q = 0; q < p.ir.nodes.size(); q++) {
+      const IRNode& n = p.ir.nodes[q];
+      if ((n.tag == T_VAR || n.tag == T_PAR) && !(p.info[(size_t)n.a].kind == K_REAL && p.info[(size_t)n.a].is_int)) {
+        pl.error = "variable / parameter index expression is not an integer expression"; return false;
+      }
+    }
+    for (int r : p.ir.idx_roots)
+      if (!(p.info[(size_t)r].kind == K_REAL && p.info[(size_t)r].is_int)) { pl.error = "augmentation row index is not an integer expression"; return false; }
+    probe(p);
+    // comps supplied by the emitter (e.g. the Julia shim passing SIMDFunction.comp1/comp2) must agree
+    if (!p.ir.comp1_given.empty()) {
+      bool same = p.ir.comp1_given.size() == p.comp1.size();
+      for (size_t q = 0; same && q < p.comp1.size(); q++) same = p.ir.comp1_given[q] == p.comp1[q];
+      if (!same) { pl.error = "comp1 supplied in the IR disagrees with the probe"; return false; }
+    }
+    if (!p.ir.comp2_given.empty()) {
+      bool same = p.ir.comp2_given.size() == p.comp2.size();
+      for (size_t q = 0; same && q < p.comp2.size(); q++) same = p.ir.comp2_given[q] == p.comp2[q];
+      if (!same) { pl.error = "comp2 supplied in the IR disagrees with the probe"; return false; }
+    }
+  }
+  // running counters in add order (nlp.jl:1474-1482, 1597-1611, 1730-1738)
+  for (auto& p : pl.pats) {
+    const i64 n = p.ir.nitr;
+    if (p.ir.kind == KIND_OBJ) {
+      p.o0 = pl.nobj; p.ob = pl.nobj; p.o1 = pl.nnzg; p.o2 = pl.nnzh;          // nlp.jl:1450
+      pl.nobj += n; pl.nnzg += n * p.o1step; pl.nnzh += n * p.o2step;
+    } else if (p.ir.kind == KIND_CON) {
+      p.o0 = pl.ncon; p.o1 = pl.nnzj; p.o2 = pl.nnzh;                          // nlp.jl:1587
+      pl.ncon += n; pl.nnzj += n * p.o1step; pl.nnzh += n * p.o2step;
+    } else {
+      p.o0 = pl.pats[(size_t)p.ir.base].o0; p.oa = pl.nconaug; p.o1 = pl.nnzj; p.o2 = pl.nnzh;   // nlp.jl:1683
+      pl.nconaug += n; pl.nnzj += n * p.o1step; pl.nnzh += n * p.o2step;
+    }
+    if (p.ir.o0 >= 0 && p.ir.kind != KIND_OBJ && p.ir.o0 != p.o0) { pl.error = "o0 supplied in the IR disagrees with the counters"; return false; }
+    if (p.ir.o1 >= 0 && p.ir.o1 != p.o1) { pl.error = "o1 supplied in the IR disagrees with the counters"; return false; }
+    if (p.ir.o2 >= 0 && p.ir.o2 != p.o2) { pl.error = "o2 supplied in the IR disagrees with the counters"; return false; }
+  }
+  // kernel pattern lists
+  for (size_t k = 0; k < pl.pats.size(); k++) {
+    const PatternPlan& p = pl.pats[k];
+    if (p.o2step > 0) pl.k_hess.push_back((int)k);
+    if (p.ir.kind == KIND_OBJ) { pl.k_obj.push_back((int)k); if (p.o1step > 0) pl.k_sgrad.push_back((int)k); }
+    else { pl.k_cons.push_back((int)k); if (p.o1step > 0) pl.k_jac.push_back((int)k); }
+    if (p.ir.kind == KIND_AUG) pl.k_aug.push_back((int)k);
+  }
+  // module source
+  std::ostringstream o;
+  o << "// generated by exb_plan.hpp -- one struct per pattern, kernels per callback\n";
+  for (size_t k = 0; k < pl.pats.size(); k++) o << gen_pattern(pl.pats[k], (int)k);
+  auto kern = [&](const char* name, const char* body, const std::vector<int>& v, const char* targ) {
+    if (v.empty()) return;
+    o << "extern \"C\" __global__ void __launch_bounds__(EXB_BLOCK) " << name << "(const ExbGroup g, const ExbCall c) { "
+      << body << "<" << targ << plist(v) << ">(g, c); }\n";
+  };
+  kern("exb_hess_g0", "exb_hess_body", pl.k_hess, "");
+  kern("exb_jac_g0", "exb_d1_body", pl.k_jac, "");
+  kern("exb_sgrad_g0", "exb_d1_body", pl.k_sgrad, "");
+  kern("exb_cons_g0", "exb_cons_body", pl.k_cons, "");
+  kern("exb_obj_g0", "exb_obj_body", pl.k_obj, "");
+  kern("exb_jstruct64_g0", "exb_jstruct_body", pl.k_jac, "long long, ");
+  kern("exb_jstruct32_g0", "exb_jstruct_body", pl.k_jac, "int, ");
+  kern("exb_gstruct64_g0", "exb_jstruct_body", pl.k_sgrad, "long long, ");
+  kern("exb_hstruct64_g0", "exb_hstruct_body", pl.k_hess, "long long, ");
+  kern("exb_hstruct32_g0", "exb_hstruct_body", pl.k_hess, "int, ");
+  kern("exb_augrow_g0", "exb_augrow_body", pl.k_aug, "");
+  pl.source = o.str();
+  return true;
+}
+
+}  // namespace exb

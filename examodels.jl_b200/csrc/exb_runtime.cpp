@@ -1,0 +1,723 @@
+// C-ABI runtime of the B200 evaluator (include/exa_b200.h).
+//
+// Replaces, behind one handle, what ext/ExaModelsKernelAbstractions.jl does in Julia:
+//   build_extension (ext:33-191)      -> exb_create: plan, generate + nvcc + load the model's
+//                                        kernel module, re-lay-out iterator data as SoA columns,
+//                                        build the sorted (target, slot) lists for grad! / cons!
+//   the callbacks (ext:212-547)       -> exb_obj / exb_cons / exb_grad / exb_jac / exb_hess /
+//                                        exb_*_structure*: ONE generated launch per callback
+//                                        (all patterns), plus a fixed deterministic reduction
+//                                        where the reference has one.
+// Host-only C++ (g++); generated kernels are launched through driver entry points obtained
+// from the CUDA runtime, fixed kernels live in exb_fixed.cu.  There is no CPU fallback.
+#include <cuda.h>
+#include <cuda_runtime_api.h>
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/file.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/exa_b200.h"
+#include "exb_device.cuh"
+#include "exb_fixed.h"
+#include "exb_plan.hpp"
+
+extern const char* exb_device_header_text;  // exb_embed.cpp
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+const char* NVCC_FLAGS_CLEAN = "-cubin -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17";
+
+uint64_t fnv1a(const std::string& s, uint64_t h = 1469598103934665603ULL) {
+  for (unsigned char c : s) { h ^= c; h *= 1099511628211ULL; }
+  return h;
+}
+
+std::string lib_dir() {
+  Dl_info info;
+  if (dladdr((void*)&fnv1a, &info) && info.dli_fname) {
+    std::string p = info.dli_fname;
+    size_t k = p.find_last_of('/');
+    return k == std::string::npos ? "." : p.substr(0, k);
+  }
+  return ".";
+}
+
+std::string cache_dir() {
+  const char* e = getenv("EXB_CACHE_DIR");
+  std::string d = e && *e ? e : lib_dir() + "/../_kcache";
+  mkdir(d.c_str(), 0777);
+  return d;
+}
+
+std::string nvcc_path() {
+  const char* e = getenv("EXB_NVCC");
+  if (e && *e) return e;
+  if (access("/usr/local/cuda/bin/nvcc", X_OK) == 0) return "/usr/local/cuda/bin/nvcc";
+  return "nvcc";
+}
+
+// ---- driver entry points (no link-time dependency on libcuda) ---------------------------
+struct Drv {
+  CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+  CUresult (*ModuleUnload)(CUmodule) = nullptr;
+  CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+  CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+  CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  bool ok = false;
+};
+Drv g_drv;
+std::once_flag g_drv_once;
+
+template <class F>
+bool entry(const char* name, F& f) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+  f = (F)p;
+  return true;
+}
+bool load_driver() {
+  std::call_once(g_drv_once, [] {
+    g_drv.ok = entry("cuModuleLoadData", g_drv.ModuleLoadData) && entry("cuModuleUnload", g_drv.ModuleUnload) &&
+               entry("cuModuleGetFunction", g_drv.ModuleGetFunction) && entry("cuLaunchKernel", g_drv.LaunchKernel) &&
+               entry("cuFuncGetAttribute", g_drv.FuncGetAttribute) && entry("cuGetErrorString", g_drv.GetErrorString);
+  });
+  return g_drv.ok;
+}
+std::string cu_err(CUresult r) {
+  const char* s = nullptr;
+  if (g_drv.GetErrorString) g_drv.GetErrorString(r, &s);
+  return s ? s : "CUDA driver error " + std::to_string((int)r);
+}
+
+enum { KN_HESS, KN_JAC, KN_SGRAD, KN_CONS, KN_OBJ, KN_JSTRUCT64, KN_JSTRUCT32, KN_GSTRUCT64, KN_HSTRUCT64, KN_HSTRUCT32, KN_AUGROW, KN_COUNT };
+const char* KNAME[KN_COUNT] = {"exb_hess_g0", "exb_jac_g0", "exb_sgrad_g0", "exb_cons_g0", "exb_obj_g0", "exb_jstruct64_g0",
+                               "exb_jstruct32_g0", "exb_gstruct64_g0", "exb_hstruct64_g0", "exb_hstruct32_g0", "exb_augrow_g0"};
+
+}  // namespace
+
+struct exb_plan {
+  exb::Plan pl;
+  std::string full_source;
+  std::string hash;
+  std::string cubin_path, cu_path;
+  bool from_cache = false;
+  const std::vector<int>& list(int kn) const {
+    switch (kn) {
+      case KN_HESS: case KN_HSTRUCT64: case KN_HSTRUCT32: return pl.k_hess;
+      case KN_JAC: case KN_JSTRUCT64: case KN_JSTRUCT32: return pl.k_jac;
+      case KN_SGRAD: case KN_GSTRUCT64: return pl.k_sgrad;
+      case KN_CONS: return pl.k_cons;
+      case KN_OBJ: return pl.k_obj;
+      default: return pl.k_aug;
+    }
+  }
+};
+
+namespace {
+
+struct Launch {          // one generated kernel of the module, ready to launch
+  CUfunction fn = nullptr;
+  ExbGroup g{};          // device pointers
+  unsigned nblocks = 0;
+  unsigned smem = 0;
+};
+
+int make_plan(const void* ir, size_t bytes, exb_plan** out) {
+  if (!ir || !out) return fail(EXB_ERR_ARG, "null argument");
+  exb_plan* p = new exb_plan();
+  if (!exb::build_plan(p->pl, ir, bytes)) {
+    std::string e = p->pl.error;
+    delete p;
+    return fail(EXB_ERR_IR, e);
+  }
+  p->full_source = std::string(exb_device_header_text) + "\n" + p->pl.source;
+  char buf[32];
+  snprintf(buf, sizeof buf, "%016llx", (unsigned long long)fnv1a(NVCC_FLAGS_CLEAN, fnv1a(p->full_source)));
+  p->hash = buf;
+  std::string d = cache_dir();
+  p->cubin_path = d + "/exb_" + p->hash + ".cubin";
+  p->cu_path = d + "/exb_" + p->hash + ".cu";
+  *out = p;
+  return EXB_OK;
+}
+
+bool file_exists(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 && st.st_size > 0; }
+
+int compile_plan(exb_plan* p, bool allow_compile) {
+  if (file_exists(p->cubin_path)) { p->from_cache = true; return EXB_OK; }
+  if (!allow_compile) return fail(EXB_ERR_COMPILE, "kernel module " + p->cubin_path + " is not cached and EXB_FLAG_NO_COMPILE is set");
+  // serialise concurrent builders of the same module (ranks of one job, parallel tests)
+  std::string lock = p->cubin_path + ".lock";
+  int fd = open(lock.c_str(), O_CREAT | O_RDWR, 0666);
+  if (fd >= 0) flock(fd, LOCK_EX);
+  int rc = EXB_OK;
+  if (!file_exists(p->cubin_path)) {
+    {
+      std::ofstream f(p->cu_path);
+      f << p->full_source;
+    }
+    std::string tmp = p->cubin_path + ".tmp" + std::to_string((long)getpid());
+    std::string log = p->cubin_path + ".log";
+    std::string cmd = nvcc_path() + " " + NVCC_FLAGS_CLEAN + " -o " + tmp + " " + p->cu_path + " > " + log + " 2>&1";
+    int st = system(cmd.c_str());
+    if (st != 0 || !file_exists(tmp)) {
+      std::ifstream lf(log);
+      std::stringstream ss; ss << lf.rdbuf();
+      std::string msg = ss.str();
+      if (msg.size() > 4000) msg = msg.substr(0, 4000);
+      rc = fail(EXB_ERR_COMPILE, "nvcc failed (" + cmd + "): " + msg);
+      unlink(tmp.c_str());
+    } else {
+      rename(tmp.c_str(), p->cubin_path.c_str());
+    }
+  } else {
+    p->from_cache = true;
+  }
+  if (fd >= 0) { flock(fd, LOCK_UN); close(fd); }
+  return rc;
+}
+
+}  // namespace
+
+struct exb_model {
+  exb_plan* plan = nullptr;
+  int device = 0, rank = 0, world = 1;
+  CUmodule mod = nullptr;
+  Launch k[KN_COUNT];
+  std::vector<void*> dev;      // everything cudaMalloc'ed by the handle
+  size_t dev_bytes = 0;
+  double* d_theta = nullptr;
+  double* d_objpart = nullptr; double* d_obj = nullptr;
+  double* d_gradbuf = nullptr; double* d_conbuf = nullptr;
+  // sorted (target, slot) lists: grad (ext:39-46) and constraint augmentation (ext:48-53)
+  long long *g_slot = nullptr, *g_target = nullptr, *g_ptr = nullptr, g_runs = 0;
+  long long *a_slot = nullptr, *a_target = nullptr, *a_ptr = nullptr, a_runs = 0;
+  std::vector<long long> lo, hi;   // local point range per pattern
+  // host shims
+  cudaStream_t hstream = nullptr;
+  double *hx = nullptr, *hy = nullptr, *hout = nullptr; size_t hx_n = 0, hy_n = 0, hout_n = 0;
+  double *dx = nullptr, *dy = nullptr, *dout = nullptr; size_t dx_n = 0, dy_n = 0, dout_n = 0;
+  long long launches = 0, last_launches = 0;
+};
+
+namespace {
+
+#define CU_TRY(m, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(EXB_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct DeviceGuard {
+  int prev = -1; bool active = false;
+  explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) { cudaSetDevice(dev); active = true; } }
+  ~DeviceGuard() { if (active) cudaSetDevice(prev); }
+};
+
+int dmalloc(exb_model* m, void** p, size_t bytes) {
+  *p = nullptr;
+  if (bytes == 0) bytes = 8;
+  CU_TRY(m, cudaMalloc(p, bytes));
+  m->dev.push_back(*p);
+  m->dev_bytes += bytes;
+  return EXB_OK;
+}
+
+int launch(exb_model* m, int kn, const ExbCall& c, cudaStream_t st) {
+  Launch& L = m->k[kn];
+  if (!L.fn || L.nblocks == 0) return EXB_OK;
+  ExbGroup g = L.g;
+  ExbCall cc = c;
+  void* params[2] = {&g, &cc};
+  CUresult r = g_drv.LaunchKernel(L.fn, L.nblocks, 1, 1, EXB_BLOCK, 1, 1, L.smem, (CUstream)st, params, nullptr);
+  if (r != CUDA_SUCCESS) return fail(EXB_ERR_CUDA, std::string("launch of ") + KNAME[kn] + ": " + cu_err(r));
+  m->launches++; m->last_launches++;
+  return EXB_OK;
+}
+
+// Re-lay-out one AoS field as a device column (int fields narrowed to int32 when they fit).
+int upload_column(exb_model* m, const unsigned char* base, long long n, long long stride, const exb::Field& f, const void** col, bool* is32) {
+  *is32 = false;
+  const bool is_int = f.type == exb::FT_I64 || f.type == exb::FT_I32;
+  if (is_int) {
+    std::vector<long long> v((size_t)n);
+    bool fits = true;
+    for (long long k = 0; k < n; k++) {
+      const unsigned char* q = base + (size_t)k * (size_t)stride + f.off;
+      long long x;
+      if (f.type == exb::FT_I64) { int64_t t; memcpy(&t, q, 8); x = t; } else { int32_t t; memcpy(&t, q, 4); x = t; }
+      v[(size_t)k] = x;
+      if (x > 2147483647LL || x < -2147483648LL) fits = false;
+    }
+    void* d = nullptr;
+    if (fits) {
+      std::vector<int> w((size_t)n);
+      for (long long k = 0; k < n; k++) w[(size_t)k] = (int)v[(size_t)k];
+      int rc = dmalloc(m, &d, (size_t)n * 4); if (rc) return rc;
+      CU_TRY(m, cudaMemcpy(d, w.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+      *is32 = true;
+    } else {
+      int rc = dmalloc(m, &d, (size_t)n * 8); if (rc) return rc;
+      CU_TRY(m, cudaMemcpy(d, v.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+    }
+    *col = d;
+  } else {
+    std::vector<double> v((size_t)n);
+    for (long long k = 0; k < n; k++) {
+      const unsigned char* q = base + (size_t)k * (size_t)stride + f.off;
+      if (f.type == exb::FT_F64) memcpy(&v[(size_t)k], q, 8); else { float t; memcpy(&t, q, 4); v[(size_t)k] = t; }
+    }
+    void* d = nullptr;
+    int rc = dmalloc(m, &d, (size_t)n * 8); if (rc) return rc;
+    CU_TRY(m, cudaMemcpy(d, v.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+    *col = d;
+  }
+  return EXB_OK;
+}
+
+int build_model(exb_model* m, const void* const* host_data, int n_data) {
+  exb_plan* P = m->plan;
+  const exb::Plan& pl = P->pl;
+  if (pl.m.ndatabufs > n_data) return fail(EXB_ERR_ARG, "IR references more data buffers than were passed");
+  CU_TRY(m, cudaFree(0));
+  if (!load_driver()) return fail(EXB_ERR_CUDA, "CUDA driver entry points unavailable");
+  {  // sm_100 only
+    cudaDeviceProp prop;
+    CU_TRY(m, cudaGetDeviceProperties(&prop, m->device));
+    if (prop.major != 10) return fail(EXB_ERR_CUDA, "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + "; this evaluator targets sm_100a (B200) only");
+  }
+  // module
+  std::vector<char> image;
+  {
+    std::ifstream f(P->cubin_path, std::ios::binary);
+    image.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+    if (image.empty()) return fail(EXB_ERR_COMPILE, "cannot read " + P->cubin_path);
+  }
+  CUresult r = g_drv.ModuleLoadData(&m->mod, image.data());
+  if (r != CUDA_SUCCESS) return fail(EXB_ERR_COMPILE, "cuModuleLoadData(" + P->cubin_path + "): " + cu_err(r));
+
+  // per-pattern arguments
+  const size_t np = pl.pats.size();
+  std::vector<ExbPatArgs> pa(np);
+  m->lo.resize(np); m->hi.resize(np);
+  for (size_t k = 0; k < np; k++) {
+    const exb::PatternPlan& p = pl.pats[k];
+    ExbPatArgs& a = pa[k];
+    memset(&a, 0, sizeof a);
+    const long long n = p.ir.nitr;
+    m->lo[k] = n * m->rank / m->world; m->hi[k] = n * (m->rank + 1) / m->world;
+    a.n = m->hi[k] - m->lo[k]; a.k0 = m->lo[k];
+    a.start = p.ir.range_start;
+    a.o0 = p.o0; a.o1 = p.o1; a.o2 = p.o2; a.aux = p.oa;
+    for (size_t d = 0; d < p.ir.dims.size() && d < EXB_MAXD; d++) a.dim[d] = p.ir.dims[d];
+    if (p.ir.itr_kind == exb::ITR_AOS) {
+      const unsigned char* base = (const unsigned char*)host_data[p.ir.databuf];
+      if (!base && n > 0) return fail(EXB_ERR_ARG, "null data buffer");
+      for (size_t f = 0; f < p.ir.fields.size(); f++) {
+        bool is32 = false;
+        int rc = upload_column(m, base, n, p.ir.stride, p.ir.fields[f], &a.col[f], &is32);
+        if (rc) return rc;
+        if (is32) a.i32mask |= (1LL << f);
+      }
+    }
+  }
+  // kernels
+  for (int kn = 0; kn < KN_COUNT; kn++) {
+    const std::vector<int>& lst = P->list(kn);
+    if (lst.empty()) continue;
+    Launch& L = m->k[kn];
+    r = g_drv.ModuleGetFunction(&L.fn, m->mod, KNAME[kn]);
+    if (r != CUDA_SUCCESS) return fail(EXB_ERR_COMPILE, std::string("kernel ") + KNAME[kn] + " missing from module: " + cu_err(r));
+    std::vector<ExbPatArgs> args(lst.size());
+    std::vector<int> blk_end(lst.size());
+    long long tot = 0; int maxns = 1;
+    for (size_t q = 0; q < lst.size(); q++) {
+      args[q] = pa[(size_t)lst[q]];
+      tot += (args[q].n + EXB_BLOCK - 1) / EXB_BLOCK;
+      if (tot > 2147483647LL) return fail(EXB_ERR_ARG, "too many blocks");
+      blk_end[q] = (int)tot;
+      const exb::PatternPlan& p = pl.pats[(size_t)lst[q]];
+      int ns = (kn == KN_HESS) ? p.o2step : (kn == KN_JAC || kn == KN_SGRAD) ? p.o1step : 1;
+      if (ns <= EXB_TILE_MAX_NS && ns > maxns) maxns = ns;
+    }
+    void *d_args = nullptr, *d_blk = nullptr;
+    int rc = dmalloc(m, &d_args, args.size() * sizeof(ExbPatArgs)); if (rc) return rc;
+    rc = dmalloc(m, &d_blk, blk_end.size() * sizeof(int)); if (rc) return rc;
+    CU_TRY(m, cudaMemcpy(d_args, args.data(), args.size() * sizeof(ExbPatArgs), cudaMemcpyHostToDevice));
+    CU_TRY(m, cudaMemcpy(d_blk, blk_end.data(), blk_end.size() * sizeof(int), cudaMemcpyHostToDevice));
+    L.g.pat = (const ExbPatArgs*)d_args; L.g.blk_end = (const int*)d_blk; L.g.np = (int)lst.size();
+    L.nblocks = (unsigned)tot;
+    L.smem = (kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD) ? (maxns > 1 ? (unsigned)(EXB_BLOCK * maxns * 8) : 16u) : 0u;
+  }
+  // scratch owned by the handle (ext:21-31,180-190)
+  int rc;
+  rc = dmalloc(m, (void**)&m->d_theta, (size_t)pl.m.npar * 8); if (rc) return rc;
+  CU_TRY(m, cudaMemset(m->d_theta, 0, (size_t)(pl.m.npar ? pl.m.npar : 1) * 8));
+  rc = dmalloc(m, (void**)&m->d_objpart, (size_t)(m->k[KN_OBJ].nblocks + 1) * 8); if (rc) return rc;
+  rc = dmalloc(m, (void**)&m->d_obj, 8); if (rc) return rc;
+  rc = dmalloc(m, (void**)&m->d_gradbuf, (size_t)pl.nnzg * 8); if (rc) return rc;
+  rc = dmalloc(m, (void**)&m->d_conbuf, (size_t)pl.nconaug * 8); if (rc) return rc;
+  // gradient sparsity: (var, slot) sorted by var (ext:39-46)
+  if (pl.nnzg > 0 && m->k[KN_GSTRUCT64].nblocks > 0) {
+    long long* keys = nullptr;
+    CU_TRY(m, cudaMalloc((void**)&keys, (size_t)pl.nnzg * 8));
+    cudaError_t e = exb_fx_fill(keys, pl.nnzg, EXB_FX_SENTINEL, 0);
+    ExbCall c{}; c.cols = keys; c.rows = nullptr;
+    int lrc = e == cudaSuccess ? launch(m, KN_GSTRUCT64, c, 0) : fail(EXB_ERR_CUDA, cudaGetErrorString(e));
+    if (!lrc) {
+      e = exb_fx_sort_runs(keys, pl.nnzg, &m->g_slot, &m->g_target, &m->g_ptr, &m->g_runs, 0);
+      if (e != cudaSuccess) lrc = fail(EXB_ERR_CUDA, std::string("gradient sparsity sort: ") + cudaGetErrorString(e));
+    }
+    cudaFree(keys);
+    if (lrc) return lrc;
+    for (void* q : {(void*)m->g_slot, (void*)m->g_target, (void*)m->g_ptr}) if (q) m->dev.push_back(q);
+  }
+  // constraint-augmentation sparsity: (row, slot) sorted by row (ext:48-53, kers ext:199-202)
+  if (pl.nconaug > 0 && m->k[KN_AUGROW].nblocks > 0) {
+    long long* keys = nullptr;
+    CU_TRY(m, cudaMalloc((void**)&keys, (size_t)pl.nconaug * 8));
+    cudaError_t e = exb_fx_fill(keys, pl.nconaug, EXB_FX_SENTINEL, 0);
+    ExbCall c{}; c.rows = keys;
+    int lrc = e == cudaSuccess ? launch(m, KN_AUGROW, c, 0) : fail(EXB_ERR_CUDA, cudaGetErrorString(e));
+    if (!lrc) {
+      e = exb_fx_sort_runs(keys, pl.nconaug, &m->a_slot, &m->a_target, &m->a_ptr, &m->a_runs, 0);
+      if (e != cudaSuccess) lrc = fail(EXB_ERR_CUDA, std::string("augmentation sparsity sort: ") + cudaGetErrorString(e));
+    }
+    cudaFree(keys);
+    if (lrc) return lrc;
+    for (void* q : {(void*)m->a_slot, (void*)m->a_target, (void*)m->a_ptr}) if (q) m->dev.push_back(q);
+  }
+  CU_TRY(m, cudaDeviceSynchronize());
+  m->launches = 0; m->last_launches = 0;
+  return EXB_OK;
+}
+
+void free_model(exb_model* m) {
+  if (!m) return;
+  DeviceGuard dg(m->device);
+  for (void* p : m->dev) cudaFree(p);
+  if (m->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(m->mod);
+  if (m->hx) cudaFreeHost(m->hx);
+  if (m->hy) cudaFreeHost(m->hy);
+  if (m->hout) cudaFreeHost(m->hout);
+  if (m->dx) cudaFree(m->dx);
+  if (m->dy) cudaFree(m->dy);
+  if (m->dout) cudaFree(m->dout);
+  if (m->hstream) cudaStreamDestroy(m->hstream);
+  delete m->plan;
+  delete m;
+}
+
+int ensure_host(exb_model* m, double** h, size_t* hn, double** d, size_t* dn, size_t n) {
+  if (n == 0) n = 1;
+  if (*hn < n) {
+    if (*h) cudaFreeHost(*h);
+    *h = nullptr; *hn = 0;
+    CU_TRY(m, cudaMallocHost((void**)h, n * 8));
+    *hn = n;
+  }
+  if (*dn < n) {
+    if (*d) cudaFree(*d);
+    *d = nullptr; *dn = 0;
+    CU_TRY(m, cudaMalloc((void**)d, n * 8));
+    *dn = n;
+  }
+  return EXB_OK;
+}
+
+}  // namespace
+
+#define EXB_GUARD(m) if (!(m) || !(m)->plan) return fail(EXB_ERR_HANDLE, "invalid handle"); DeviceGuard dg_((m)->device); (m)->last_launches = 0
+#define EXB_BEGIN try {
+#define EXB_END } catch (const std::exception& e) { return fail(EXB_ERR_INTERNAL, e.what()); } catch (...) { return fail(EXB_ERR_INTERNAL, "unknown exception"); }
+
+extern "C" {
+
+const char* exb_last_error(void) { return g_err.c_str(); }
+int exb_abi_version(void) { return EXB_ABI_VERSION; }
+
+int exb_plan_create(const void* ir, size_t ir_bytes, const exb_options* opt, exb_plan** out) {
+  EXB_BEGIN
+  (void)opt;
+  return make_plan(ir, ir_bytes, out);
+  EXB_END
+}
+int exb_plan_destroy(exb_plan* p) { delete p; return EXB_OK; }
+int exb_plan_dims(const exb_plan* p, int64_t* o) {
+  if (!p || !o) return fail(EXB_ERR_HANDLE, "invalid handle");
+  const exb::Plan& pl = p->pl;
+  o[0] = pl.m.nvar; o[1] = pl.ncon; o[2] = pl.nnzj; o[3] = pl.nnzh; o[4] = pl.nobj; o[5] = pl.nnzg; o[6] = pl.nconaug; o[7] = pl.m.npar;
+  return EXB_OK;
+}
+int exb_plan_npatterns(const exb_plan* p) { return p ? (int)p->pl.pats.size() : -1; }
+int exb_plan_pattern(const exb_plan* p, int k, int64_t* o) {
+  if (!p || !o) return fail(EXB_ERR_HANDLE, "invalid handle");
+  if (k < 0 || (size_t)k >= p->pl.pats.size()) return fail(EXB_ERR_ARG, "pattern index out of range");
+  const exb::PatternPlan& q = p->pl.pats[(size_t)k];
+  o[0] = q.ir.kind; o[1] = q.ir.nitr; o[2] = q.o0; o[3] = q.o1; o[4] = q.o2; o[5] = q.o1step; o[6] = q.o2step;
+  o[7] = (int64_t)q.comp1.size(); o[8] = (int64_t)q.comp2.size();
+  return EXB_OK;
+}
+int exb_plan_comp(const exb_plan* p, int k, int which, int64_t* o) {
+  if (!p || !o) return fail(EXB_ERR_HANDLE, "invalid handle");
+  if (k < 0 || (size_t)k >= p->pl.pats.size()) return fail(EXB_ERR_ARG, "pattern index out of range");
+  const std::vector<int>& c = which == 1 ? p->pl.pats[(size_t)k].comp1 : p->pl.pats[(size_t)k].comp2;
+  for (size_t q = 0; q < c.size(); q++) o[q] = c[q];
+  return EXB_OK;
+}
+int exb_plan_source(const exb_plan* p, const char** src, size_t* len) {
+  if (!p || !src) return fail(EXB_ERR_HANDLE, "invalid handle");
+  *src = p->full_source.c_str();
+  if (len) *len = p->full_source.size();
+  return EXB_OK;
+}
+int exb_plan_module_path(const exb_plan* p, char* buf, size_t buflen) {
+  if (!p || !buf) return fail(EXB_ERR_HANDLE, "invalid handle");
+  if (p->cubin_path.size() + 1 > buflen) return fail(EXB_ERR_ARG, "buffer too small");
+  memcpy(buf, p->cubin_path.c_str(), p->cubin_path.size() + 1);
+  return EXB_OK;
+}
+int exb_plan_compile(exb_plan* p) {
+  EXB_BEGIN
+  if (!p) return fail(EXB_ERR_HANDLE, "invalid handle");
+  return compile_plan(p, true);
+  EXB_END
+}
+
+int exb_create(const void* ir, size_t ir_bytes, const void* const* host_data, int n_data, const exb_options* opt, exb_model** out) {
+  EXB_BEGIN
+  if (!out) return fail(EXB_ERR_ARG, "null argument");
+  *out = nullptr;
+  exb_options o{-1, 0, 1, 0, 0};
+  if (opt) o = *opt;
+  if (o.world < 1 || o.rank < 0 || o.rank >= o.world) return fail(EXB_ERR_ARG, "bad rank / world");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(EXB_ERR_CUDA, "no CUDA device: this evaluator has no CPU fallback");
+  int dev = o.device;
+  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) return fail(EXB_ERR_CUDA, "cudaGetDevice failed"); }
+  if (dev >= ndev) return fail(EXB_ERR_ARG, "device ordinal out of range");
+  exb_plan* P = nullptr;
+  int rc = make_plan(ir, ir_bytes, &P);
+  if (rc) return rc;
+  rc = compile_plan(P, !(o.flags & EXB_FLAG_NO_COMPILE));
+  if (rc) { delete P; return rc; }
+  exb_model* m = new exb_model();
+  m->plan = P; m->device = dev; m->rank = o.rank; m->world = o.world;
+  DeviceGuard dg(dev);
+  rc = build_model(m, host_data, n_data);
+  if (rc) { std::string keep = g_err; free_model(m); g_err = keep; return rc; }
+  *out = m;
+  return EXB_OK;
+  EXB_END
+}
+
+int exb_destroy(exb_model* m) { free_model(m); return EXB_OK; }
+
+int exb_dims(const exb_model* m, int64_t* o) {
+  if (!m) return fail(EXB_ERR_HANDLE, "invalid handle");
+  return exb_plan_dims(m->plan, o);
+}
+
+int exb_set_params(exb_model* m, const double* theta, void* stream) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  const long long n = m->plan->pl.m.npar;
+  if (n > 0) CU_TRY(m, cudaMemcpyAsync(m->d_theta, theta, (size_t)n * 8, cudaMemcpyDefault, (cudaStream_t)stream));
+  return EXB_OK;
+  EXB_END
+}
+
+int exb_obj_async(exb_model* m, const double* x, double* out_dev, void* stream) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  cudaStream_t st = (cudaStream_t)stream;
+  ExbCall c{}; c.x = x; c.th = m->d_theta; c.out2 = m->d_objpart;
+  int rc = launch(m, KN_OBJ, c, st); if (rc) return rc;
+  CU_TRY(m, exb_fx_sum(m->d_objpart, m->k[KN_OBJ].nblocks, out_dev, st));
+  m->launches++; m->last_launches++;
+  return EXB_OK;
+  EXB_END
+}
+int exb_obj(exb_model* m, const double* x, double* out_host, void* stream) {
+  EXB_BEGIN
+  if (!m) return fail(EXB_ERR_HANDLE, "invalid handle");
+  int rc = exb_obj_async(m, x, m->d_obj, stream); if (rc) return rc;
+  DeviceGuard dg(m->device);
+  CU_TRY(m, cudaMemcpyAsync(out_host, m->d_obj, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CU_TRY(m, cudaStreamSynchronize((cudaStream_t)stream));
+  return EXB_OK;
+  EXB_END
+}
+
+int exb_grad(exb_model* m, const double* x, double* g, void* stream) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  cudaStream_t st = (cudaStream_t)stream;
+  const exb::Plan& pl = m->plan->pl;
+  ExbCall c{}; c.x = x; c.th = m->d_theta; c.out = m->d_gradbuf;
+  int rc = launch(m, KN_SGRAD, c, st); if (rc) return rc;                        // kerg, ext:669-679
+  CU_TRY(m, cudaMemsetAsync(g, 0, (size_t)pl.m.nvar * 8, st));                   // fill!(g, 0), ext:317
+  CU_TRY(m, exb_fx_compress(m->d_gradbuf, m->g_ptr, m->g_slot, m->g_target, m->g_runs, g, 0, st));   // ext:691-697
+  if (m->g_runs > 0) { m->launches++; m->last_launches++; }
+  return EXB_OK;
+  EXB_END
+}
+
+int exb_cons(exb_model* m, const double* x, double* cvals, void* stream) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  cudaStream_t st = (cudaStream_t)stream;
+  const exb::Plan& pl = m->plan->pl;
+  // a sharded handle owns only part of the base rows: zero the rest so that ranks can be summed
+  if (m->world > 1) CU_TRY(m, cudaMemsetAsync(cvals, 0, (size_t)pl.ncon * 8, st));
+  ExbCall c{}; c.x = x; c.th = m->d_theta; c.out = cvals; c.out2 = m->d_conbuf;
+  int rc = launch(m, KN_CONS, c, st); if (rc) return rc;                         // kerf + kerf2, ext:681-688
+  CU_TRY(m, exb_fx_compress(m->d_conbuf, m->a_ptr, m->a_slot, m->a_target, m->a_runs, cvals, 1, st));   // ext:691-697
+  if (m->a_runs > 0) { m->launches++; m->last_launches++; }
+  return EXB_OK;
+  EXB_END
+}
+
+int exb_jac(exb_model* m, const double* x, double* vals, void* stream) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  ExbCall c{}; c.x = x; c.th = m->d_theta; c.out = vals;
+  return launch(m, KN_JAC, c, (cudaStream_t)stream);
+  EXB_END
+}
+
+int exb_hess(exb_model* m, const double* x, const double* y, double obj_weight, double* vals, void* stream) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  ExbCall c{}; c.x = x; c.y = y; c.th = m->d_theta; c.sigma = obj_weight; c.out = vals;
+  return launch(m, KN_HESS, c, (cudaStream_t)stream);
+  EXB_END
+}
+
+static int structure(exb_model* m, int kn, void* rows, void* cols, void* stream) {
+  ExbCall c{}; c.rows = rows; c.cols = cols;
+  if (!rows || !cols) return fail(EXB_ERR_ARG, "null rows / cols");
+  return launch(m, kn, c, (cudaStream_t)stream);
+}
+int exb_jac_structure64(exb_model* m, int64_t* rows, int64_t* cols, void* stream) {
+  EXB_BEGIN EXB_GUARD(m); return structure(m, KN_JSTRUCT64, rows, cols, stream); EXB_END
+}
+int exb_jac_structure32(exb_model* m, int32_t* rows, int32_t* cols, void* stream) {
+  EXB_BEGIN EXB_GUARD(m); return structure(m, KN_JSTRUCT32, rows, cols, stream); EXB_END
+}
+int exb_hess_structure64(exb_model* m, int64_t* rows, int64_t* cols, void* stream) {
+  EXB_BEGIN EXB_GUARD(m); return structure(m, KN_HSTRUCT64, rows, cols, stream); EXB_END
+}
+int exb_hess_structure32(exb_model* m, int32_t* rows, int32_t* cols, void* stream) {
+  EXB_BEGIN EXB_GUARD(m); return structure(m, KN_HSTRUCT32, rows, cols, stream); EXB_END
+}
+
+// ---- host-buffer shims (the WrapperNLPModel role, src/utils.jl:16-267) -----------------------
+static int host_stream(exb_model* m) {
+  if (!m->hstream) CU_TRY(m, cudaStreamCreateWithFlags(&m->hstream, cudaStreamNonBlocking));
+  return EXB_OK;
+}
+static int host_in(exb_model* m, const double* x, const double* y) {
+  const exb::Plan& pl = m->plan->pl;
+  int rc = host_stream(m); if (rc) return rc;
+  rc = ensure_host(m, &m->hx, &m->hx_n, &m->dx, &m->dx_n, (size_t)pl.m.nvar); if (rc) return rc;
+  memcpy(m->hx, x, (size_t)pl.m.nvar * 8);
+  CU_TRY(m, cudaMemcpyAsync(m->dx, m->hx, (size_t)pl.m.nvar * 8, cudaMemcpyHostToDevice, m->hstream));
+  if (y) {
+    rc = ensure_host(m, &m->hy, &m->hy_n, &m->dy, &m->dy_n, (size_t)pl.ncon); if (rc) return rc;
+    memcpy(m->hy, y, (size_t)pl.ncon * 8);
+    CU_TRY(m, cudaMemcpyAsync(m->dy, m->hy, (size_t)pl.ncon * 8, cudaMemcpyHostToDevice, m->hstream));
+  }
+  return EXB_OK;
+}
+static int host_out(exb_model* m, double* out, size_t n) {
+  CU_TRY(m, cudaMemcpyAsync(m->hout, m->dout, n * 8, cudaMemcpyDeviceToHost, m->hstream));
+  CU_TRY(m, cudaStreamSynchronize(m->hstream));
+  memcpy(out, m->hout, n * 8);
+  return EXB_OK;
+}
+int exb_host_obj(exb_model* m, const double* x, double* out) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  int rc = host_in(m, x, nullptr); if (rc) return rc;
+  return exb_obj(m, m->dx, out, m->hstream);
+  EXB_END
+}
+#define EXB_HOST_VEC(NAME, N, CALL)                                                                   \
+  EXB_BEGIN                                                                                           \
+  EXB_GUARD(m);                                                                                       \
+  const exb::Plan& pl = m->plan->pl; (void)pl;                                                        \
+  int rc = host_in(m, x, yy); if (rc) return rc;                                                      \
+  rc = ensure_host(m, &m->hout, &m->hout_n, &m->dout, &m->dout_n, (size_t)(N)); if (rc) return rc;    \
+  rc = CALL; if (rc) return rc;                                                                       \
+  return host_out(m, out, (size_t)(N));                                                               \
+  EXB_END
+int exb_host_grad(exb_model* m, const double* x, double* out) {
+  const double* yy = nullptr;
+  EXB_HOST_VEC(grad, pl.m.nvar, exb_grad(m, m->dx, m->dout, m->hstream))
+}
+int exb_host_cons(exb_model* m, const double* x, double* out) {
+  const double* yy = nullptr;
+  EXB_HOST_VEC(cons, pl.ncon, exb_cons(m, m->dx, m->dout, m->hstream))
+}
+int exb_host_jac(exb_model* m, const double* x, double* out) {
+  const double* yy = nullptr;
+  EXB_HOST_VEC(jac, pl.nnzj, exb_jac(m, m->dx, m->dout, m->hstream))
+}
+int exb_host_hess(exb_model* m, const double* x, const double* y, double obj_weight, double* out) {
+  const double* yy = y;
+  EXB_HOST_VEC(hess, pl.nnzh, exb_hess(m, m->dx, y ? m->dy : nullptr, obj_weight, m->dout, m->hstream))
+}
+static int host_structure(exb_model* m, int kn, long long n, int64_t* rows, int64_t* cols) {
+  int rc = host_stream(m); if (rc) return rc;
+  long long *dr = nullptr, *dc = nullptr;
+  CU_TRY(m, cudaMalloc((void**)&dr, (size_t)(n ? n : 1) * 8));
+  cudaError_t e = cudaMalloc((void**)&dc, (size_t)(n ? n : 1) * 8);
+  if (e != cudaSuccess) { cudaFree(dr); return fail(EXB_ERR_CUDA, cudaGetErrorString(e)); }
+  rc = structure(m, kn, dr, dc, m->hstream);
+  if (!rc) {
+    cudaMemcpyAsync(rows, dr, (size_t)n * 8, cudaMemcpyDeviceToHost, m->hstream);
+    cudaMemcpyAsync(cols, dc, (size_t)n * 8, cudaMemcpyDeviceToHost, m->hstream);
+    e = cudaStreamSynchronize(m->hstream);
+    if (e != cudaSuccess) rc = fail(EXB_ERR_CUDA, cudaGetErrorString(e));
+  }
+  cudaFree(dr); cudaFree(dc);
+  return rc;
+}
+int exb_host_jac_structure64(exb_model* m, int64_t* rows, int64_t* cols) {
+  EXB_BEGIN EXB_GUARD(m); return host_structure(m, KN_JSTRUCT64, m->plan->pl.nnzj, rows, cols); EXB_END
+}
+int exb_host_hess_structure64(exb_model* m, int64_t* rows, int64_t* cols) {
+  EXB_BEGIN EXB_GUARD(m); return host_structure(m, KN_HSTRUCT64, m->plan->pl.nnzh, rows, cols); EXB_END
+}
+
+int exb_shard(const exb_model* m, int k, int64_t* o) {
+  if (!m || !o) return fail(EXB_ERR_HANDLE, "invalid handle");
+  if (k < 0 || (size_t)k >= m->plan->pl.pats.size()) return fail(EXB_ERR_ARG, "pattern index out of range");
+  const exb::PatternPlan& p = m->plan->pl.pats[(size_t)k];
+  o[0] = m->lo[(size_t)k]; o[1] = m->hi[(size_t)k];
+  const bool in_jac = p.ir.kind != exb::KIND_OBJ;
+  o[2] = in_jac ? p.o1 + o[0] * p.o1step : 0; o[3] = in_jac ? p.o1 + o[1] * p.o1step : 0;
+  o[4] = p.o2 + o[0] * p.o2step; o[5] = p.o2 + o[1] * p.o2step;
+  return EXB_OK;
+}
+int exb_stats(const exb_model* m, int64_t* o) {
+  if (!m || !o) return fail(EXB_ERR_HANDLE, "invalid handle");
+  o[0] = m->launches; o[1] = m->last_launches; o[2] = (int64_t)m->dev_bytes; o[3] = m->plan->from_cache ? 1 : 0;
+  return EXB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+/* =============================================================================
+ * exa_b200.h — C ABI of the B200-native evaluator for the ExaModels.jl per-pattern
+ * NLP callback path (obj, cons!, grad!, jac_coord!, jac_structure!, hess_coord!,
+ * hess_structure!).
+ *
+ * This is the drop-in boundary: what a `B200Backend` method of the reference's
+ * `build_extension(c::ExaCore; prod)` (/root/reference/src/nlp.jl:898, KA method at
+ * ext/ExaModelsKernelAbstractions.jl:33-191) would `ccall` once at model build, and
+ * what the callback methods on `AbstractExaModel{T,VT,E}` (ext:212-547; CPU forms at
+ * src/nlp.jl:1798-1978) would `ccall` on every solver iteration.  Names and argument
+ * order follow the only C-ABI precedent in the reference tree, the "cnlp ABI v0.1"
+ * exported by ExaModelsCompiler (`P_obj(id,x*,out*)`, `P_hess(id,x*,y*,obj_weight,
+ * vals*)`, ... /root/reference/ExaModelsCompiler/src/ExaModelsCompiler.jl:1564-1732),
+ * with a handle instead of an id, DEVICE pointers instead of host pointers, and a
+ * CUDA stream.
+ *
+ * Conventions (same as cnlp ABI v0.1, ExaModelsCompiler.jl:181-186):
+ *   - every function returns an int status, 0 on success; nothing throws across
+ *     the boundary; `exb_last_error()` gives the message of the last failure on the
+ *     calling thread;
+ *   - indices are 1-based; the Hessian is the lower triangle in COO form with
+ *     duplicates ("partially compressed", src/simdfunction.jl:78-100);
+ *   - outputs are fully overwritten (no caller pre-zero needed; the reference zero
+ *     fills, ext:317,343,521);
+ *   - work is enqueued on the caller's stream and NOT synchronised, except where a
+ *     scalar is returned to the host (`exb_obj`), mirroring the KA callbacks, which
+ *     never call `synchronize`;
+ *   - a handle is thread-compatible (one caller at a time); handles are independent.
+ *
+ * There is no CPU fallback: every evaluation entry point fails with EXB_ERR_CUDA if
+ * no sm_100 device / kernel module is available.
+ *
+ * --- §IR: the pattern IR (int64 little-endian word stream) ------------------
+ * The language-neutral image of `SIMDFunction` (src/simdfunction.jl:21-30) +
+ * `Objective / Constraint / ConstraintAugmentation` (src/nlp.jl:107-177), patterns in
+ * ADD ORDER.  Emitters: examodels.jl_b200/nlp.py (Python host) and the Julia shim of
+ * INTEGRATION.md.
+ *
+ *   header : MAGIC(0x0031425845 "EXB1") VERSION(1) nvar npar npatterns ndatabufs
+ *   pattern: kind(0 obj|1 con|2 aug) nitr itr_kind(0 range|1 AoS) range_start
+ *            databuf(-1 if range) stride_bytes
+ *            nfields { byte_offset type(0 i64|1 f64|2 i32|3 f32) }*nfields
+ *            o0 o1 o2            (-1: assign by the counter rules of nlp.jl:1474-1482,
+ *                                 1597-1611,1730-1738)
+ *            base                (aug: index of the base Constraint pattern, else -1)
+ *            nidx { idx_root }*nidx { dim }*nidx      (aug row = o0 + idxx(coord, dims),
+ *                                                      nlp.jl:1986-2001,2012-2015)
+ *            nnodes { tag a b payload }*nnodes  root
+ *            ncomp1 {comp1}*  ncomp2 {comp2}*   (optional; recomputed and cross-checked)
+ *   node tags: 0 CONST_I(payload) 1 CONST_F(payload=f64 bits) 2 DATA_SELF
+ *              3 DATA_FIELD(a=field) 4 VAR(a=index node) 5 PAR(a=index node)
+ *              6 NULL(payload=f64 bits) 7 OP1(a=child, payload=op) 8 OP2(a,b,payload=op)
+ *              9 VAL(payload)   -- Val{p} exponent (specialization.jl:199-202)
+ *   OP1 codes follow the order of src/functionlist.jl:6-60 (0 '+', 1 '-', 2 inv, ...),
+ *   OP2 codes the order of src/functionlist.jl:71-81 (+ - * / ^ atan hypot max min).
+ *   Children precede parents.
+ * ============================================================================= */
+#ifndef EXA_B200_H
+#define EXA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EXB_ABI_VERSION 1
+
+enum {
+  EXB_OK = 0,
+  EXB_ERR_HANDLE = 1,   /* invalid handle            (cnlp ABI: id invalid -> 1) */
+  EXB_ERR_INTERNAL = 2, /* caught exception          (cnlp ABI: exception  -> 2) */
+  EXB_ERR_IR = 3,       /* malformed / inconsistent IR */
+  EXB_ERR_COMPILE = 4,  /* nvcc failed or module could not be loaded */
+  EXB_ERR_CUDA = 5,     /* CUDA runtime error / no device */
+  EXB_ERR_ARG = 6
+};
+
+typedef struct exb_plan exb_plan;   /* host-only analysis of an IR (no GPU needed) */
+typedef struct exb_model exb_model; /* a model resident on one GPU */
+
+typedef struct exb_options {
+  int32_t device;      /* CUDA device ordinal; -1 = current device */
+  int32_t rank;        /* shard of every pattern's iterator this handle evaluates ... */
+  int32_t world;       /* ... out of `world` contiguous shards (1 = whole model) */
+  int32_t flags;       /* EXB_FLAG_* */
+  int64_t fuse_below;  /* patterns with fewer points share one launch; 0 = default */
+} exb_options;
+
+#define EXB_FLAG_NO_COMPILE 1 /* fail instead of invoking nvcc when the module is not cached */
+
+/* out[0..7] = nvar ncon nnzj nnzh nobj nnzg nconaug npar
+ * (NLPModelMeta fields of src/nlp.jl:765-798 plus the scratch sizes of ext:21-31) */
+#define EXB_NDIMS 8
+
+/* ---- analysis (replaces src/simdfunction.jl:66-100 + the counters of nlp.jl) ---- */
+int exb_plan_create(const void* ir, size_t ir_bytes, const exb_options* opt, exb_plan** out);
+int exb_plan_destroy(exb_plan* p);
+int exb_plan_dims(const exb_plan* p, int64_t* out8);
+int exb_plan_npatterns(const exb_plan* p);
+/* out[0..8] = kind nitr o0 o1 o2 o1step o2step len(comp1) len(comp2) */
+int exb_plan_pattern(const exb_plan* p, int k, int64_t* out9);
+/* which = 1: comp1 (Compressor of the gradient/Jacobian pass), 2: comp2 (Hessian) */
+int exb_plan_comp(const exb_plan* p, int k, int which, int64_t* out);
+/* generated CUDA C++ of the model's kernel module; *len excludes the NUL */
+int exb_plan_source(const exb_plan* p, const char** src, size_t* len);
+/* path of the compiled module for this plan (hash of source + flags) */
+int exb_plan_module_path(const exb_plan* p, char* buf, size_t buflen);
+/* run nvcc for this plan if the module is not cached (no GPU needed: cross-compiles) */
+int exb_plan_compile(exb_plan* p);
+
+/* ---- model lifetime (replaces build_extension, ext:33-191) ---------------- */
+/* `host_data[k]` = host pointer to AoS data buffer k (the iterator arrays, element
+ * stride as given in the IR); they are re-laid-out into device SoA columns and need
+ * not outlive the call. */
+int exb_create(const void* ir, size_t ir_bytes, const void* const* host_data, int n_data,
+               const exb_options* opt, exb_model** out);
+int exb_destroy(exb_model* m);
+int exb_dims(const exb_model* m, int64_t* out8);
+/* theta: DEVICE pointer to npar doubles (copied; set_value!, src/nlp.jl:1217-1287) */
+int exb_set_params(exb_model* m, const double* theta, void* stream);
+
+/* ---- callbacks: all pointers are DEVICE pointers, stream is a cudaStream_t ---- */
+/* obj (src/nlp.jl:1827-1839 | ext:253-271): *out_host written after a stream sync */
+int exb_obj(exb_model* m, const double* x, double* out_host, void* stream);
+/* same, result left on the device (no sync): *out_dev */
+int exb_obj_async(exb_model* m, const double* x, double* out_dev, void* stream);
+/* grad! (src/nlp.jl:1858-1868 | ext:310-336): g[nvar] */
+int exb_grad(exb_model* m, const double* x, double* g, void* stream);
+/* cons_nln! (src/nlp.jl:1841-1854 | ext:273-308): c[ncon] */
+int exb_cons(exb_model* m, const double* x, double* c, void* stream);
+/* jac_structure! (src/nlp.jl:1798-1807 | ext:212-226) */
+int exb_jac_structure64(exb_model* m, int64_t* rows, int64_t* cols, void* stream);
+int exb_jac_structure32(exb_model* m, int32_t* rows, int32_t* cols, void* stream);
+/* jac_coord! (src/nlp.jl:1870-1880 | ext:338-351): vals[nnzj] */
+int exb_jac(exb_model* m, const double* x, double* vals, void* stream);
+/* hess_structure! (src/nlp.jl:1809-1825 | ext:229-250): lower triangle */
+int exb_hess_structure64(exb_model* m, int64_t* rows, int64_t* cols, void* stream);
+int exb_hess_structure32(exb_model* m, int32_t* rows, int32_t* cols, void* stream);
+/* hess_coord! (src/nlp.jl:1906-1940 | ext:515-547): vals[nnzh];
+ * y == NULL is the objective-only form (src/nlp.jl:1906-1915) */
+int exb_hess(exb_model* m, const double* x, const double* y, double obj_weight, double* vals,
+             void* stream);
+
+/* ---- host-buffer shims: the WrapperNLPModel role (src/utils.jl:16-267) ------
+ * Same callbacks with HOST pointers; H2D / D2H copies go through pinned staging owned
+ * by the handle and are part of the call.  They synchronise before returning. */
+int exb_host_obj(exb_model* m, const double* x, double* out);
+int exb_host_grad(exb_model* m, const double* x, double* g);
+int exb_host_cons(exb_model* m, const double* x, double* c);
+int exb_host_jac(exb_model* m, const double* x, double* vals);
+int exb_host_hess(exb_model* m, const double* x, const double* y, double obj_weight, double* vals);
+int exb_host_jac_structure64(exb_model* m, int64_t* rows, int64_t* cols);
+int exb_host_hess_structure64(exb_model* m, int64_t* rows, int64_t* cols);
+
+/* ---- sharding / introspection ------------------------------------------- */
+/* For pattern k: out[0..5] = lo hi (0-based local point range of this rank)
+ * jac_lo jac_hi hess_lo hess_hi (0-based half-open slices of vals this rank writes) */
+int exb_shard(const exb_model* m, int k, int64_t* out6);
+/* out[0] = kernels launched since creation, out[1] = last callback launches,
+ * out[2] = device bytes owned by the handle, out[3] = 1 if module came from cache */
+int exb_stats(const exb_model* m, int64_t* out4);
+
+const char* exb_last_error(void);
+int exb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXA_B200_H */
