@@ -420,13 +420,14 @@ void free_model(exb_model* m) {
   delete m;
 }
 
-int ensure_host(exb_model* m, double** h, size_t* hn, double** d, size_t* dn, size_t n) {
+int ensure_host(exb_model* m, double** h, size_t* hn, double** d, size_t* dn, size_t nh, size_t n) {
   if (n == 0) n = 1;
-  if (*hn < n) {
+  if (nh > 0 && *hn < nh) {
+    n = n > nh ? n : nh;
     if (*h) cudaFreeHost(*h);
     *h = nullptr; *hn = 0;
-    CU_TRY(m, cudaMallocHost((void**)h, n * 8));
-    *hn = n;
+    CU_TRY(m, cudaMallocHost((void**)h, nh * 8));
+    *hn = nh;
   }
   if (*dn < n) {
     if (*d) cudaFree(*d);
@@ -630,24 +631,58 @@ static int host_stream(exb_model* m) {
   if (!m->hstream) CU_TRY(m, cudaStreamCreateWithFlags(&m->hstream, cudaStreamNonBlocking));
   return EXB_OK;
 }
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+// H2D of x (and y): straight from the caller's buffer when it is page-locked, else through pinned staging
 static int host_in(exb_model* m, const double* x, const double* y) {
   const exb::Plan& pl = m->plan->pl;
   int rc = host_stream(m); if (rc) return rc;
-  rc = ensure_host(m, &m->hx, &m->hx_n, &m->dx, &m->dx_n, (size_t)pl.m.nvar); if (rc) return rc;
-  memcpy(m->hx, x, (size_t)pl.m.nvar * 8);
-  CU_TRY(m, cudaMemcpyAsync(m->dx, m->hx, (size_t)pl.m.nvar * 8, cudaMemcpyHostToDevice, m->hstream));
+  const bool px = is_pinned(x);
+  rc = ensure_host(m, &m->hx, &m->hx_n, &m->dx, &m->dx_n, px ? 0 : (size_t)pl.m.nvar, (size_t)pl.m.nvar); if (rc) return rc;
+  if (!px) memcpy(m->hx, x, (size_t)pl.m.nvar * 8);
+  CU_TRY(m, cudaMemcpyAsync(m->dx, px ? x : m->hx, (size_t)pl.m.nvar * 8, cudaMemcpyHostToDevice, m->hstream));
   if (y) {
-    rc = ensure_host(m, &m->hy, &m->hy_n, &m->dy, &m->dy_n, (size_t)pl.ncon); if (rc) return rc;
-    memcpy(m->hy, y, (size_t)pl.ncon * 8);
-    CU_TRY(m, cudaMemcpyAsync(m->dy, m->hy, (size_t)pl.ncon * 8, cudaMemcpyHostToDevice, m->hstream));
+    const bool py = is_pinned(y);
+    rc = ensure_host(m, &m->hy, &m->hy_n, &m->dy, &m->dy_n, py ? 0 : (size_t)pl.ncon, (size_t)pl.ncon); if (rc) return rc;
+    if (!py) memcpy(m->hy, y, (size_t)pl.ncon * 8);
+    CU_TRY(m, cudaMemcpyAsync(m->dy, py ? y : m->hy, (size_t)pl.ncon * 8, cudaMemcpyHostToDevice, m->hstream));
   }
   return EXB_OK;
 }
-static int host_out(exb_model* m, double* out, size_t n) {
-  CU_TRY(m, cudaMemcpyAsync(m->hout, m->dout, n * 8, cudaMemcpyDeviceToHost, m->hstream));
+// D2H of out[lo, hi) slices (a sharded handle returns only what it wrote)
+static int host_out(exb_model* m, double* out, const std::vector<std::pair<long long, long long>>& sl) {
+  bool staged = false;
+  for (auto& s : sl) {
+    const size_t n = (size_t)(s.second - s.first);
+    if (n == 0) continue;
+    if (is_pinned(out + s.first)) {
+      CU_TRY(m, cudaMemcpyAsync(out + s.first, m->dout + s.first, n * 8, cudaMemcpyDeviceToHost, m->hstream));
+    } else {
+      CU_TRY(m, cudaMemcpyAsync(m->hout + s.first, m->dout + s.first, n * 8, cudaMemcpyDeviceToHost, m->hstream));
+      staged = true;
+    }
+  }
   CU_TRY(m, cudaStreamSynchronize(m->hstream));
-  memcpy(out, m->hout, n * 8);
+  if (staged)
+    for (auto& s : sl)
+      if (s.second > s.first && !is_pinned(out + s.first)) memcpy(out + s.first, m->hout + s.first, (size_t)(s.second - s.first) * 8);
   return EXB_OK;
+}
+static std::vector<std::pair<long long, long long>> whole(long long n) { return {{0LL, n}}; }
+static std::vector<std::pair<long long, long long>> slices(const exb_model* m, int which) {   // 1: jac, 2: hess
+  const exb::Plan& pl = m->plan->pl;
+  if (m->world == 1) return whole(which == 1 ? pl.nnzj : pl.nnzh);
+  std::vector<std::pair<long long, long long>> v;
+  for (size_t k = 0; k < pl.pats.size(); k++) {
+    const exb::PatternPlan& p = pl.pats[k];
+    if (which == 1 && p.ir.kind == exb::KIND_OBJ) continue;
+    const long long o = which == 1 ? p.o1 : p.o2, st = which == 1 ? p.o1step : p.o2step;
+    v.push_back({o + m->lo[k] * st, o + m->hi[k] * st});
+  }
+  return v;
 }
 int exb_host_obj(exb_model* m, const double* x, double* out) {
   EXB_BEGIN
@@ -656,30 +691,33 @@ int exb_host_obj(exb_model* m, const double* x, double* out) {
   return exb_obj(m, m->dx, out, m->hstream);
   EXB_END
 }
-#define EXB_HOST_VEC(NAME, N, CALL)                                                                   \
+#define EXB_HOST_VEC(N, SLICES, CALL)                                                                 \
   EXB_BEGIN                                                                                           \
   EXB_GUARD(m);                                                                                       \
   const exb::Plan& pl = m->plan->pl; (void)pl;                                                        \
   int rc = host_in(m, x, yy); if (rc) return rc;                                                      \
-  rc = ensure_host(m, &m->hout, &m->hout_n, &m->dout, &m->dout_n, (size_t)(N)); if (rc) return rc;    \
+  const std::vector<std::pair<long long, long long>> sl = SLICES;                                     \
+  bool all_pinned = true;                                                                             \
+  for (auto& s_ : sl) if (s_.second > s_.first && !is_pinned(out + s_.first)) all_pinned = false;     \
+  rc = ensure_host(m, &m->hout, &m->hout_n, &m->dout, &m->dout_n, all_pinned ? 0 : (size_t)(N), (size_t)(N)); if (rc) return rc; \
   rc = CALL; if (rc) return rc;                                                                       \
-  return host_out(m, out, (size_t)(N));                                                               \
+  return host_out(m, out, sl);                                                                        \
   EXB_END
 int exb_host_grad(exb_model* m, const double* x, double* out) {
   const double* yy = nullptr;
-  EXB_HOST_VEC(grad, pl.m.nvar, exb_grad(m, m->dx, m->dout, m->hstream))
+  EXB_HOST_VEC(pl.m.nvar, whole(pl.m.nvar), exb_grad(m, m->dx, m->dout, m->hstream))
 }
 int exb_host_cons(exb_model* m, const double* x, double* out) {
   const double* yy = nullptr;
-  EXB_HOST_VEC(cons, pl.ncon, exb_cons(m, m->dx, m->dout, m->hstream))
+  EXB_HOST_VEC(pl.ncon, whole(pl.ncon), exb_cons(m, m->dx, m->dout, m->hstream))
 }
 int exb_host_jac(exb_model* m, const double* x, double* out) {
   const double* yy = nullptr;
-  EXB_HOST_VEC(jac, pl.nnzj, exb_jac(m, m->dx, m->dout, m->hstream))
+  EXB_HOST_VEC(pl.nnzj, slices(m, 1), exb_jac(m, m->dx, m->dout, m->hstream))
 }
 int exb_host_hess(exb_model* m, const double* x, const double* y, double obj_weight, double* out) {
   const double* yy = y;
-  EXB_HOST_VEC(hess, pl.nnzh, exb_hess(m, m->dx, y ? m->dy : nullptr, obj_weight, m->dout, m->hstream))
+  EXB_HOST_VEC(pl.nnzh, slices(m, 2), exb_hess(m, m->dx, y ? m->dy : nullptr, obj_weight, m->dout, m->hstream))
 }
 static int host_structure(exb_model* m, int kn, long long n, int64_t* rows, int64_t* cols) {
   int rc = host_stream(m); if (rc) return rc;

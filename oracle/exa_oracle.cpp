@@ -85,6 +85,7 @@ struct Model {
   std::vector<std::pair<i64, i64>> gsparsity; std::vector<i64> gptr;
   std::string err;
   int nthreads;
+  int rank = 0, world = 1;   // test aid: evaluate only shard `rank` of `world` of every iterator
 };
 
 // ---- scalar helpers (Julia Base semantics used by src/functionlist.jl) --------------
@@ -629,14 +630,14 @@ void probe(Pattern& p) {
 bool parse(Model& m, const i64* w, size_t nw, const void* const* bufs, int nbufs) {
   size_t q = 0;
   auto rd = [&](i64& out) { if (q >= nw) return false; out = w[q++]; return true; };
-  i64 magic, ver, npat, nb;
+  i64 magic = 0, ver = 0, npat = 0, nb = 0;
   if (!rd(magic) || magic != 0x0031425845LL) { m.err = "bad IR magic"; return false; }
   if (!rd(ver) || ver != 1) { m.err = "bad IR version"; return false; }
   rd(m.nvar); rd(m.npar); rd(npat); rd(nb);
   if (nb > nbufs) { m.err = "IR references more data buffers than were passed"; return false; }
   m.pats.resize((size_t)npat);
   for (auto& p : m.pats) {
-    i64 v, nf, nidx, nn;
+    i64 v = 0, nf = 0, nidx = 0, nn = 0;
     rd(v); p.kind = (int)v; rd(p.nitr); rd(v); p.itr_kind = (int)v; rd(p.range_start);
     rd(v); p.databuf = (int)v; rd(p.stride); rd(nf);
     p.fields.resize((size_t)nf);
@@ -692,20 +693,26 @@ i64 offset0(const Ctx& c) {
 
 int nthreads_of(const Model& m) { return m.nthreads > 0 ? m.nthreads : 1; }
 
+inline void shard_of(const Model& m, const Pattern& p, i64& lo, i64& hi) {
+  lo = p.nitr * m.rank / m.world; hi = p.nitr * (m.rank + 1) / m.world;
+}
+
 template <class F>
 void for_points(const Model& m, const Pattern& p, const double* X, F body) {
   int nt = nthreads_of(m);
-  if (nt <= 1 || p.nitr < 1024) {
+  i64 s_lo, s_hi; shard_of(m, p, s_lo, s_hi);
+  const i64 n = s_hi - s_lo;
+  if (nt <= 1 || n < 1024) {
     Work w; w.size(p.t.size());
     Ctx c; c.p = &p; c.X = X; c.TH = m.theta.data(); c.w = &w;
-    for (i64 k = 0; k < p.nitr; k++) { point(c, k); body(c); }
+    for (i64 k = s_lo; k < s_hi; k++) { point(c, k); body(c); }
     return;
   }
   // static partition of the data points over host threads: the shape of
   // KernelAbstractions.CPU() under `julia -t N` (docs/src/gpu.jl:2-5,48)
   std::vector<std::thread> th;
   for (int r = 0; r < nt; r++) {
-    i64 lo = p.nitr * r / nt, hi = p.nitr * (r + 1) / nt;
+    i64 lo = s_lo + n * r / nt, hi = s_lo + n * (r + 1) / nt;
     th.emplace_back([&, lo, hi]() {
       Work w; w.size(p.t.size());
       Ctx c; c.p = &p; c.X = X; c.TH = m.theta.data(); c.w = &w;
@@ -713,6 +720,15 @@ void for_points(const Model& m, const Pattern& p, const double* X, F body) {
     });
   }
   for (auto& t : th) t.join();
+}
+
+// sequential visit of the (sharded) points of one pattern
+template <class F>
+void seq_points(const Model& m, const Pattern& p, const double* X, F body) {
+  i64 lo, hi; shard_of(m, p, lo, hi);
+  Work w; w.size(p.t.size());
+  Ctx c; c.p = &p; c.X = X; c.TH = m.theta.data(); c.w = &w;
+  for (i64 k = lo; k < hi; k++) { point(c, k); body(c); }
 }
 
 }  // namespace
@@ -731,6 +747,7 @@ void* ora_create(const void* ir, size_t ir_bytes, const void* const* bufs, int n
 const char* ora_error(void* h) { return ((Model*)h)->err.c_str(); }
 void ora_destroy(void* h) { delete (Model*)h; }
 void ora_set_threads(void* h, int n) { ((Model*)h)->nthreads = n; }
+void ora_set_shard(void* h, int rank, int world) { ((Model*)h)->rank = rank; ((Model*)h)->world = world; }
 int ora_max_threads() { unsigned n = std::thread::hardware_concurrency(); return n ? (int)n : 1; }
 void ora_set_params(void* h, const double* th) { Model* m = (Model*)h; m->theta.assign(th, th + m->npar); }
 
@@ -760,11 +777,9 @@ double ora_obj(void* h, const double* x) {
   for (auto& p : m->pats) {
     if (p.kind != KIND_OBJ) continue;
     if (nthreads_of(*m) <= 1) {
-      Work w; w.size(p.t.size());
-      Ctx c; c.p = &p; c.X = x; c.TH = m->theta.data(); c.w = &w;
-      for (i64 k = 0; k < p.nitr; k++) { point(c, k); s += eval0(c, p.root); }
+      seq_points(*m, p, x, [&](Ctx& c) { s += eval0(c, c.p->root); });
     } else {   // KA shape: objbuffer + sum (ext:253-271)
-      std::vector<double> buf((size_t)p.nitr);
+      std::vector<double> buf((size_t)p.nitr, 0.0);
       for_points(*m, p, x, [&](Ctx& c) { buf[(size_t)c.k] = eval0(c, c.p->root); });
       for (double v : buf) s += v;
     }
@@ -780,9 +795,7 @@ void ora_cons(void* h, const double* x, double* g) {
     if (p.kind == KIND_OBJ) continue;
     if (p.kind == KIND_CON) for_points(*m, p, x, [&](Ctx& c) { g[offset0(c) - 1] += eval0(c, c.p->root); });
     else {   // augmentation rows collide across points: sequential (CPU path is sequential, nlp.jl:1849-1851)
-      Work w; w.size(p.t.size());
-      Ctx c; c.p = &p; c.X = x; c.TH = m->theta.data(); c.w = &w;
-      for (i64 k = 0; k < p.nitr; k++) { point(c, k); g[offset0(c) - 1] += eval0(c, p.root); }
+      seq_points(*m, p, x, [&](Ctx& c) { g[offset0(c) - 1] += eval0(c, c.p->root); });
     }
   }
 }
@@ -793,12 +806,8 @@ void ora_grad(void* h, const double* x, double* g) {
   std::fill(g, g + m->nvar, 0.0);
   for (auto& p : m->pats) {
     if (p.kind != KIND_OBJ) continue;
-    Work w; w.size(p.t.size());
-    Ctx c; c.p = &p; c.X = x; c.TH = m->theta.data(); c.w = &w;
     Sink s; std::memset(&s, 0, sizeof s); s.mode = M_DENSE; s.y = g;
-    for (i64 k = 0; k < p.nitr; k++) {
-      point(c, k); fwd(c, p.root, 1); int cnt = 0; rpass1(c, p.root, s, cnt, 1.0);
-    }
+    seq_points(*m, p, x, [&](Ctx& c) { fwd(c, c.p->root, 1); int cnt = 0; rpass1(c, c.p->root, s, cnt, 1.0); });
   }
 }
 

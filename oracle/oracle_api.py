@@ -75,6 +75,10 @@ class Oracle:
     def set_threads(self, n):
         lib().ora_set_threads(self.h, int(n))
 
+    def set_shard(self, rank, world):
+        """Test aid: evaluate only shard `rank` of `world` of every pattern's iterator."""
+        lib().ora_set_shard(self.h, int(rank), int(world))
+
     @staticmethod
     def max_threads():
         return int(lib().ora_max_threads())

@@ -1,0 +1,245 @@
+"""Pins the CPU oracle (oracle/exa_oracle.cpp) to everything the reference tree fixes for this path:
+hand-derived slot layouts (tests/golden/known_answers.json), the closed-form `cons` values of
+test/NLPTest/conaug_test.jl, and derivative tables against finite differences as in
+test/ADTest/ADTest.jl:298-374.  CPU only."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import examodels_jl_b200 as E
+from examodels_jl_b200 import graph as G
+from examodels_jl_b200 import models as M
+from oracle.oracle_api import Oracle, bi, uni
+
+KA = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "known_answers.json")))
+
+
+def _check_pattern(o, k, exp):
+    info = o.pattern_info(k)
+    assert (info["o1step"], info["o2step"]) == (exp["o1step"], exp["o2step"])
+    assert o.comp(k, 1).tolist() == exp["comp1"]
+    assert o.comp(k, 2).tolist() == exp["comp2"]
+
+
+def test_lv_layout_known_answers():
+    N = 100
+    o = Oracle.from_core(M.luksan_vlcek(N, order="bench"))
+    t = KA["lv_totals_N100"]
+    assert (o.nvar, o.ncon, o.nnzj, o.nnzh) == (t["nvar"], t["ncon"], t["nnzj"], t["nnzh"])
+    _check_pattern(o, 0, KA["lv_constraint"])
+    _check_pattern(o, 1, KA["lv_objective"])
+    jr, jc = o.jac_structure()
+    hr, hc = o.hess_structure()
+    for i in range(1, N - 1):  # constraint point i (1-based), slots in order (i+1, i+2, i)
+        assert jr[3 * (i - 1): 3 * i].tolist() == [i] * 3
+        assert jc[3 * (i - 1): 3 * i].tolist() == [i + d for d in KA["lv_constraint"]["jac_cols_offsets"]]
+        exp = [(i + a, i + b) for a, b in KA["lv_constraint"]["hess_pairs_offsets"]]
+        assert list(zip(hr[6 * (i - 1): 6 * i].tolist(), hc[6 * (i - 1): 6 * i].tolist())) == exp
+    base = 6 * (N - 2)  # bench order: constraint slots first
+    for q, i in enumerate(range(2, N + 1)):
+        exp = [(i + a, i + b) for a, b in KA["lv_objective_hess_pairs_offsets"]]
+        assert list(zip(hr[base + 3 * q: base + 3 * q + 3].tolist(), hc[base + 3 * q: base + 3 * q + 3].tolist())) == exp
+    # guide order: objective first
+    o2 = Oracle.from_core(M.luksan_vlcek(N, order="guide"))
+    assert o2.pattern_info(0)["o2"] == 0 and o2.pattern_info(1)["o2"] == 3 * (N - 1)
+    assert (np.asarray(o2.hess_structure()[0]) >= np.asarray(o2.hess_structure()[1])).all()  # lower triangle
+
+
+@pytest.mark.parametrize("N", [3, 20])
+def test_lv_aug_variant(N):
+    o = Oracle.from_core(M.luksan_vlcek_aug(N, 1))
+    assert [o.pattern_info(0)[k] for k in ("o1step", "o2step")] == KA["lv_aug"]["con1"]
+    assert [o.pattern_info(1)[k] for k in ("o1step", "o2step")] == KA["lv_aug"]["con2"]
+    assert o.nnzj == 5 * (N - 2) and o.nnzh == 10 * N - 17 and o.nconaug == N - 2
+    # base + augmentation must equal the single-pattern LV constraint
+    ref = Oracle.from_core(M.luksan_vlcek(N))
+    x = M.lv_x0(N) + 0.01 * np.random.default_rng(0).uniform(-1, 1, N)
+    np.testing.assert_allclose(o.cons(x), ref.cons(x), rtol=1e-13)
+    np.testing.assert_allclose(o.grad(x), ref.grad(x), rtol=1e-13)
+    assert abs(o.obj(x) - ref.obj(x)) <= 1e-12 * abs(ref.obj(x))
+
+
+def test_opf_layout_known_answers():
+    o = Oracle.from_core(M.ac_power(M.synthetic_power_data(30, 41, 6, seed=5)))
+    steps = [[o.pattern_info(k)["o1step"], o.pattern_info(k)["o2step"]] for k in range(o.npatterns())]
+    assert steps == KA["opf_steps"]
+    _check_pattern(o, 2, KA["opf_flow"])
+    assert o.pattern_info(2)["ncomp1"] == 10 and o.pattern_info(2)["ncomp2"] == 21  # JuMPTest.jl:404-405
+    assert o.nvar == 2 * 30 + 2 * 6 + 4 * 41
+    assert o.ncon == 1 + 7 * 41 + 2 * 30
+
+
+# ---- closed-form constraint values: test/NLPTest/conaug_test.jl -----------------------------
+def _cons(core, x):
+    return Oracle.from_core(core).cons(np.asarray(x, dtype=np.float64))
+
+
+def test_conaug_2d_integer_dims():   # conaug_test.jl:73-94
+    N, Mm = 3, 4
+    c = E.ExaCore()
+    x = c.add_var(N, Mm)
+    g = c.add_con(dims=(N, Mm), lcon=-np.inf, ucon=0.0)
+    itr = [(i, j) for j in range(1, Mm + 1) for i in range(1, N)]
+    c.add_con_aug(lambda d: g[d[1], d[2]] + (x[d[1], d[2]] - x[d[1] + 1, d[2]]), itr)
+    o = Oracle.from_core(c)
+    assert o.ncon == N * Mm and o.nnzj == len(itr) * 2
+    gv = o.cons(np.arange(1, N * Mm + 1, dtype=np.float64))
+    for j in range(1, Mm + 1):
+        for i in range(1, N + 1):
+            k = (j - 1) * N + i
+            assert gv[k - 1] == (float(k) - float(k + 1) if i < N else 0.0)
+
+
+def test_conaug_2d_range_dims_nonunit_start():   # conaug_test.jl:96-123
+    N, Mm = 3, 4
+    r1, r2 = range(1, N + 1), range(2, Mm + 2)
+    c = E.ExaCore()
+    x = c.add_var(N, Mm + 1)
+    g = c.add_con(dims=(r1, r2), lcon=-np.inf, ucon=0.0)
+    itr = [(i, j) for j in r2 for i in range(1, N)]
+    c.add_con_aug(lambda d: g[d[1], d[2]] + (x[d[1], d[2]] - x[d[1] + 1, d[2]]), itr)
+    o = Oracle.from_core(c)
+    assert o.ncon == N * Mm and o.nnzj == len(itr) * 2
+    gv = o.cons(np.arange(1, N * (Mm + 1) + 1, dtype=np.float64))
+    for jc in range(1, Mm + 1):
+        for i in range(1, N + 1):
+            assert gv[(jc - 1) * N + i - 1] == (-1.0 if i < N else 0.0)
+
+
+def test_conaug_3d():   # conaug_test.jl:125-143
+    N, Mm, K = 2, 3, 4
+    c = E.ExaCore()
+    x = c.add_var(N * Mm * K)
+    g = c.add_con(dims=(N, Mm, K))
+    itr = [(i, j, k) for k in range(1, K + 1) for j in range(1, Mm + 1) for i in range(1, N + 1)]
+    c.add_con_aug(lambda d: g[d[1], d[2], d[3]] + x[(d[3] - 1) * (N * Mm) + (d[2] - 1) * N + d[1]] * 2, itr)
+    o = Oracle.from_core(c)
+    assert o.ncon == N * Mm * K and o.nnzj == len(itr)
+    assert np.all(o.cons(np.ones(N * Mm * K)) == 2.0)
+
+
+def test_conaug_multiple_augmentations():   # conaug_test.jl:176-213
+    N, Mm = 4, 5
+    fwd = [(i, j) for j in range(1, Mm + 1) for i in range(1, N)]
+    bwd = [(i, j) for j in range(1, Mm + 1) for i in range(2, N + 1)]
+    c = E.ExaCore()
+    x = c.add_var(N, Mm)
+    g = c.add_con(dims=(N, Mm), lcon=-np.inf, ucon=np.inf)
+    c.add_con_aug(lambda d: g[d[1], d[2]] + (x[d[1], d[2]] - x[d[1] + 1, d[2]]), fwd)
+    c.add_con_aug(lambda d: g[d[1], d[2]] + (x[d[1] - 1, d[2]] - x[d[1], d[2]]), bwd)
+    o = Oracle.from_core(c)
+    assert o.ncon == N * Mm and o.nnzj == (len(fwd) + len(bwd)) * 2
+    gv = o.cons(np.arange(1, N * Mm + 1, dtype=np.float64))
+    for j in range(1, Mm + 1):
+        for i in range(1, N + 1):
+            xv = (j - 1) * N
+            exp = -1.0 if i in (1, N) else float(xv + i - 1) - float(xv + i + 1)
+            assert gv[(j - 1) * N + i - 1] == exp
+
+
+def test_conaug_1d_sugar_matches_explicit():   # conaug_test.jl:49-70
+    N = 6
+    c1 = E.ExaCore(); x1 = c1.add_var(N + 1)
+    g1 = c1.add_con(lambda i: x1[i] + x1[i + 1], range(1, N + 1), lcon=-1.0, ucon=1.0)
+    c1.add_con_aug(g1, lambda i: (i, -(x1[i] + x1[i + 1])), range(1, N + 1))
+    c2 = E.ExaCore(); x2 = c2.add_var(N + 1)
+    g2 = c2.add_con(dims=(N,), lcon=-1.0, ucon=1.0)
+    c2.add_con_aug(lambda i: g2[i] + (x2[i] + x2[i + 1]), range(1, N + 1))
+    c2.add_con_aug(lambda i: g2[i] + (-(x2[i] + x2[i + 1])), range(1, N + 1))
+    x0 = np.random.default_rng(3).uniform(size=N + 1)
+    np.testing.assert_allclose(_cons(c1, x0), 0.0, atol=1e-15)
+    np.testing.assert_allclose(_cons(c2, x0), 0.0, atol=1e-15)
+
+
+# ---- derivative tables vs finite differences: test/ADTest/ADTest.jl:298-342 -----------------------
+_DOMAIN = {"acosh": 1.7, "acoth": 1.7, "asin": 0.3, "acos": 0.3, "atanh": 0.3}
+
+
+@pytest.mark.parametrize("name", G.UNIVARIATE)
+def test_univariate_table_vs_fd(name):
+    op = G.OP1_CODE[name]
+    x = _DOMAIN.get(name, 0.7)
+    h = 1e-5
+    f, d, dd = uni(op, x)
+    fp, dp, _ = uni(op, x + h)
+    fm, dm, _ = uni(op, x - h)
+    assert math.isfinite(f)
+    np.testing.assert_allclose(d, (fp - fm) / (2 * h), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(dd, (dp - dm) / (2 * h), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", G.BIVARIATE)
+def test_bivariate_table_vs_fd(name):
+    op = G.OP2_CODE[name]
+    a, b, h = 0.7, 1.3, 1e-5
+    f, y1, y2, h11, h12, h22 = bi(op, a, b)
+    g = lambda u, v: bi(op, u, v)
+    np.testing.assert_allclose(y1, (g(a + h, b)[0] - g(a - h, b)[0]) / (2 * h), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(y2, (g(a, b + h)[0] - g(a, b - h)[0]) / (2 * h), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(h11, (g(a + h, b)[1] - g(a - h, b)[1]) / (2 * h), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(h12, (g(a, b + h)[1] - g(a, b - h)[1]) / (2 * h), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(h22, (g(a, b + h)[2] - g(a, b - h)[2]) / (2 * h), rtol=1e-4, atol=1e-6)
+
+
+def test_integer_power_table():
+    for n in (2, 3, 5, -1, -2):
+        f, y1, _, h11, _, _ = bi(G.OP2_CODE["^"], 0.7, float(n), e2_is_int=True)
+        np.testing.assert_allclose([f, y1, h11], [0.7 ** n, n * 0.7 ** (n - 1), n * (n - 1) * 0.7 ** (n - 2)], rtol=1e-14)
+
+
+# ---- whole-callback consistency: COO derivatives vs finite differences of the primal callbacks ----
+def _dense(n, m, rows, cols, vals):
+    A = np.zeros((n, m))
+    np.add.at(A, (np.asarray(rows) - 1, np.asarray(cols) - 1), vals)
+    return A
+
+
+@pytest.mark.parametrize("build", [lambda: M.luksan_vlcek(8), lambda: M.luksan_vlcek_aug(7, 2),
+                                   lambda: M.ac_power(M.synthetic_power_data(5, 6, 2, seed=1)),
+                                   lambda: M.goddard_rocket(4), lambda: M.pattern_family(5, 32)])
+def test_callbacks_vs_finite_differences(build):
+    core = build()
+    o = Oracle.from_core(core)
+    rng = np.random.default_rng(7)
+    x = core.meta()["x0"] + 0.05 * rng.uniform(-1, 1, o.nvar)
+    y = rng.standard_normal(o.ncon)
+    h = 1e-6
+    eye = np.eye(o.nvar)
+    gfd = np.array([(o.obj(x + h * e) - o.obj(x - h * e)) / (2 * h) for e in eye])
+    np.testing.assert_allclose(o.grad(x), gfd, rtol=2e-5, atol=2e-5 * max(1.0, np.abs(gfd).max()))
+    jr, jc = o.jac_structure()
+    J = _dense(o.ncon, o.nvar, jr, jc, o.jac_coord(x))
+    Jfd = np.array([(o.cons(x + h * e) - o.cons(x - h * e)) / (2 * h) for e in eye]).T
+    np.testing.assert_allclose(J, Jfd, rtol=2e-5, atol=2e-5 * max(1.0, np.abs(Jfd).max()))
+    hr, hc = o.hess_structure()
+    assert (hr >= hc).all()
+    L = _dense(o.nvar, o.nvar, hr, hc, o.hess_coord(x, y, 0.7))
+    H = L + np.tril(L, -1).T
+
+    def glag(z):
+        Jz = _dense(o.ncon, o.nvar, jr, jc, o.jac_coord(z))
+        return 0.7 * o.grad(z) + Jz.T @ y
+    Hfd = np.array([(glag(x + h * e) - glag(x - h * e)) / (2 * h) for e in eye])
+    scale = max(1.0, np.abs(Hfd).max())
+    np.testing.assert_allclose(H, Hfd, rtol=1e-4, atol=1e-5 * scale)
+    # sparse gradient slots sum to the dense gradient; matrix-free products agree with the COO forms
+    v = rng.standard_normal(o.nvar)
+    w = rng.standard_normal(o.ncon)
+    np.testing.assert_allclose(o.jprod(x, v), J @ v, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(o.jtprod(x, w), J.T @ w, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(o.hprod(x, y, v, 0.7), H @ v, rtol=1e-11, atol=1e-11 * scale)
+
+
+def test_threaded_oracle_matches_sequential():
+    core = M.luksan_vlcek(5000)
+    o = Oracle.from_core(core)
+    x = core.meta()["x0"]
+    y = np.ones(o.ncon)
+    a = o.hess_coord(x, y, 1.0).copy()
+    j = o.jac_coord(x).copy()
+    o.set_threads(4)
+    assert np.array_equal(o.hess_coord(x, y, 1.0), a)
+    assert np.array_equal(o.jac_coord(x), j)

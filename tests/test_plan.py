@@ -1,0 +1,111 @@
+"""CPU-side checks of the product's host logic: the plan (probe, counters, generated source)
+against the oracle, the C-ABI surface, IR validation, and failing loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import examodels_jl_b200 as E
+from examodels_jl_b200 import models as M
+from examodels_jl_b200 import backend as B
+from oracle.oracle_api import Oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+MODELS = {
+    "lv_bench": lambda: M.luksan_vlcek(50, order="bench"),
+    "lv_guide": lambda: M.luksan_vlcek(50, order="guide"),
+    "lv_aug": lambda: M.luksan_vlcek_aug(9, 3),
+    "opf": lambda: M.ac_power(M.synthetic_power_data(30, 41, 6, seed=5)),
+    "rocket": lambda: M.goddard_rocket(10),
+    "family": lambda: M.pattern_family(10, 32),
+}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    E.build_library()
+
+
+@pytest.mark.parametrize("name", list(MODELS))
+def test_plan_matches_oracle(name):
+    core = MODELS[name]()
+    p, o = E.Plan(core), Oracle.from_core(core)
+    for a in ("nvar", "ncon", "nnzj", "nnzh", "nobj", "nnzg", "nconaug", "npar"):
+        assert getattr(p, a) == getattr(o, a), a
+    assert p.npatterns() == o.npatterns()
+    for k in range(p.npatterns()):
+        assert p.pattern_info(k) == o.pattern_info(k)
+        assert np.array_equal(p.comp(k, 1), o.comp(k, 1))
+        assert np.array_equal(p.comp(k, 2), o.comp(k, 2))
+
+
+def test_generated_source_is_model_size_independent():
+    a, b = E.Plan(M.luksan_vlcek(100)), E.Plan(M.luksan_vlcek(10_000))
+    assert a.source() == b.source() and a.module_path() == b.module_path()
+    src = a.source()
+    for kern in ("exb_hess_g0", "exb_jac_g0", "exb_sgrad_g0", "exb_cons_g0", "exb_obj_g0", "exb_hstruct64_g0"):
+        assert f'extern "C" __global__ void __launch_bounds__(EXB_BLOCK) {kern}' in src
+    assert "sincos" in src and "struct P0" in src and "struct P1" in src
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "exa_b200.h")).read()
+    decl = set(re.findall(r"\b(exb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(decl) >= 30
+    lib = B.lib()
+    for s in decl:
+        assert hasattr(lib, s), f"{s} declared in include/exa_b200.h but not exported"
+    assert lib.exb_abi_version() == 1
+
+
+def test_malformed_ir_is_rejected():
+    lib = B.lib()
+    h = C.c_void_p()
+    bad = b"\0" * 64
+    assert lib.exb_plan_create(bad, C.c_size_t(len(bad)), None, C.byref(h)) == 3
+    assert b"magic" in lib.exb_last_error()
+    ir, _ = M.luksan_vlcek(10).to_ir()
+    assert lib.exb_plan_create(ir[:-24], C.c_size_t(len(ir) - 24), None, C.byref(h)) == 3
+
+
+def test_no_silent_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(E.ExbError):
+        E.ExaModel(M.luksan_vlcek(10))
+    # the raw ABI refuses as well
+    lib = B.lib()
+    ir, bufs = M.luksan_vlcek(10).to_ir()
+    h = C.c_void_p()
+    rc = lib.exb_create(ir, C.c_size_t(len(ir)), None, 0, None, C.byref(h))
+    assert rc == 5 and not h.value
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "examodels.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".hpp", ".h")) and f != "exb_embed.cpp":
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle_api" not in txt and "exa_oracle" not in txt and "libexa_oracle" not in txt, f
+
+
+def test_front_end_tree_shapes():
+    from examodels_jl_b200 import graph as G
+    c = E.ExaCore()
+    x = c.add_var(5)
+    d = G.DataSource()
+    assert isinstance(x[d] ** 2, G.Node1) and (x[d] ** 2).op == "abs2"          # specialization.jl:198
+    p3 = x[d] ** 3
+    assert isinstance(p3, G.Node2) and p3.op == "^" and isinstance(p3.inner2, G.Val)   # :199
+    assert (x[d] ** 1) is not None and isinstance(x[d] ** 1, G.Var)
+    e = 3 * x[d] ** 3                                                              # 3*(x^3)
+    assert isinstance(e, G.Node2) and e.op == "*" and e.inner1 == 3
+    s = x[d] + x[d + 1] + x[d + 2]                                                 # left fold
+    assert s.inner1.op == "+" and isinstance(s.inner2, G.Var)
+    assert x[d] == x[d] and x[d + 1] != x[d]                                       # === on index expressions
+    assert x[3].i == 3 and isinstance(x[d].i, G.Node2)                             # nlp.jl:908,922
