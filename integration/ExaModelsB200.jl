@@ -1,0 +1,162 @@
+# ExaModelsB200.jl — the reference-side binding of libexa_b200.so (include/exa_b200.h).
+#
+# UNVERIFIED: there is no Julia toolchain in the build image or on the GPU box, so this file has
+# never been executed.  It is the stub a maintainer would add as `ext/ExaModelsB200.jl`, written
+# against ExaModels v0.12.0: the extension point is `build_extension(c::ExaCore{T,VT,B}; prod)`
+# (src/nlp.jl:898; KernelAbstractions method at ext/ExaModelsKernelAbstractions.jl:33-191) and the
+# callback methods dispatch on the model's `E` parameter (`AbstractExaModel{T,VT,E}`, src/nlp.jl:702;
+# KA methods ext:212-547).  Arrays are CUDA.jl `CuVector{Float64}`; every callback is one `ccall`.
+module ExaModelsB200
+
+import ExaModels, NLPModels
+import ExaModels: Var, ParameterNode, DataSource, DataIndexed, Node1, Node2, Constant, Null,
+    SIMDFunction, Objective, Constraint, ConstraintAugmentation, ExaCore, AbstractExaModel
+using CUDA
+
+const LIB = get(ENV, "EXB_LIB", "libexa_b200.so")
+
+struct B200Backend            # stored in ExaCore{T,VT,B}.backend
+    device::Int
+    rank::Int
+    world::Int
+end
+B200Backend(; device = 0, rank = 0, world = 1) = B200Backend(device, rank, world)
+ExaModels.convert_array(v, ::B200Backend) = CuArray(v)          # src/templates.jl:2-3
+ExaModels.default_T(::B200Backend) = Float64
+
+mutable struct B200Extension  # stored in ExaModel.ext
+    handle::Ptr{Cvoid}
+    keep::Vector{Any}         # iterator arrays referenced by the IR during exb_create
+end
+
+check(rc) = rc == 0 || error("libexa_b200: ", unsafe_string(ccall((:exb_last_error, LIB), Cstring, ())))
+
+# ---- IR emitter: walks the TYPE + fields of each pattern's tree (SURVEY.md Appendix A) -------------
+const OP1 = Dict(f => i - 1 for (i, f) in enumerate(first.(ExaModels._UNIVARIATES)))   # src/functionlist.jl:6-60
+const OP2 = Dict(f => i - 1 for (i, f) in enumerate(first.(ExaModels._BIVARIATES)))    # src/functionlist.jl:71-81
+const T_CONST_I, T_CONST_F, T_DATA_SELF, T_DATA_FIELD, T_VAR, T_PAR, T_NULL, T_OP1, T_OP2, T_VAL = 0:9
+
+mutable struct Emitter
+    rows::Vector{NTuple{4,Int64}}
+    fields::Vector{Tuple{Int64,Int64}}      # (byte offset, type 0 i64 | 1 f64 | 2 i32 | 3 f32)
+    eltype::Type
+    isrange::Bool
+end
+push_row!(e, r) = (push!(e.rows, r); length(e.rows) - 1)
+f64bits(v) = reinterpret(Int64, Float64(v))
+ftype(::Type{Int64}) = 0; ftype(::Type{Float64}) = 1; ftype(::Type{Int32}) = 2; ftype(::Type{Float32}) = 3
+
+emit!(e, v::Integer) = push_row!(e, (T_CONST_I, 0, 0, Int64(v)))
+emit!(e, v::Real) = push_row!(e, (T_CONST_F, 0, 0, f64bits(v)))
+emit!(e, ::Val{V}) where {V} = push_row!(e, (T_VAL, 0, 0, Int64(V)))
+emit!(e, ::Constant{V}) where {V} = emit!(e, V)
+emit!(e, n::Null) = push_row!(e, (T_NULL, 0, 0, f64bits(n.value === nothing ? 0.0 : n.value)))
+emit!(e, n::Var) = push_row!(e, (T_VAR, emit!(e, n.i), 0, 0))
+emit!(e, n::ParameterNode) = push_row!(e, (T_PAR, emit!(e, n.i), 0, 0))
+emit!(e, n::Node1{F}) where {F} = push_row!(e, (T_OP1, emit!(e, n.inner), 0, OP1[Symbol(F.instance)]))
+function emit!(e, n::Node2{F}) where {F}
+    a = emit!(e, n.inner1); b = emit!(e, n.inner2)
+    push_row!(e, (T_OP2, a, b, OP2[Symbol(F.instance)]))
+end
+function emit!(e, n::Union{DataSource,DataIndexed})
+    e.isrange && return push_row!(e, (T_DATA_SELF, 0, 0, 0))
+    off, T = field_path(e.eltype, n)
+    k = findfirst(==((off, ftype(T))), e.fields)
+    k === nothing && (push!(e.fields, (off, ftype(T))); k = length(e.fields))
+    push_row!(e, (T_DATA_FIELD, k - 1, 0, 0))
+end
+field_path(T, ::DataSource) = (0, T)
+function field_path(T, n::DataIndexed{I,J}) where {I,J}     # J: Symbol or position (src/graph.jl:194-199)
+    off, S = field_path(T, n.inner)
+    k = J isa Symbol ? Base.fieldindex(S, J) : J
+    (off + fieldoffset(S, k), fieldtype(S, k))
+end
+
+function emit_pattern!(words, bufs, p, kind, base_index)
+    sf = p.f
+    isrange = p.itr isa UnitRange
+    e = Emitter(NTuple{4,Int64}[], Tuple{Int64,Int64}[], eltype(p.itr), isrange)
+    tree = kind == 2 ? sf.f.second : sf.f                    # augmentation: f.f :: Pair(idx, expr)
+    root = emit!(e, tree)
+    idx = kind == 2 ? (sf.f.first isa Tuple ? collect(sf.f.first) : [sf.f.first]) : []
+    idx_roots = [emit!(e, i) for i in idx]
+    append!(words, (kind, length(p.itr)))
+    if isrange
+        append!(words, (0, first(p.itr), -1, 0))
+    else
+        host = Array(p.itr); push!(bufs, host)
+        append!(words, (1, 0, length(bufs) - 1, sizeof(eltype(host))))
+    end
+    push!(words, length(e.fields)); foreach(f -> append!(words, f), e.fields)
+    append!(words, (kind == 2 ? -1 : sf.o0, sf.o1, sf.o2, base_index, length(idx_roots)))
+    append!(words, idx_roots)
+    append!(words, kind == 2 ? collect(Int64, p.dims)[1:length(idx_roots)] : Int64[])
+    push!(words, length(e.rows)); foreach(r -> append!(words, r), e.rows)
+    push!(words, root)
+    push!(words, length(sf.comp1.inner)); append!(words, sf.comp1.inner)   # cross-checked by the probe
+    push!(words, length(sf.comp2.inner)); append!(words, sf.comp2.inner)
+end
+
+function ExaModels.build_extension(c::ExaCore{T,VT,B}; prod = false, kwargs...) where {T,VT,B<:B200Backend}
+    prod && error("prod = true (jprod/jtprod/hprod) is not provided by the B200 backend yet")
+    # patterns in ADD ORDER: both lists are stored newest-first (src/nlp.jl:536); the shared nnzh
+    # counter (f.o2) orders objectives against constraints
+    pats = Any[]
+    for o in reverse(collect(c.obj)); push!(pats, (o, 0)); end
+    for k in reverse(collect(c.cons)); push!(pats, (k, k isa ConstraintAugmentation ? 2 : 1)); end
+    sort!(pats; by = t -> (t[1].f.o2, t[1].f.o1), alg = MergeSort)
+    words = Int64[0x0031425845, 1, c.nvar, c.npar, length(pats), 0]
+    bufs = Any[]
+    for (p, kind) in pats
+        base = kind == 2 ? findfirst(q -> q[2] == 1 && q[1].f.o0 == p.f.o0, pats) - 1 : -1
+        emit_pattern!(words, bufs, p, kind, base)
+    end
+    words[6] = length(bufs)
+    opt = Ref((Int32(c.backend.device), Int32(c.backend.rank), Int32(c.backend.world), Int32(0), Int64(0)))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    ptrs = Ptr{Cvoid}[pointer(b) for b in bufs]
+    GC.@preserve bufs check(ccall((:exb_create, LIB), Cint,
+        (Ptr{Int64}, Csize_t, Ptr{Ptr{Cvoid}}, Cint, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}),
+        words, 8 * length(words), ptrs, length(ptrs), opt, h))
+    ext = B200Extension(h[], bufs)
+    finalizer(e -> ccall((:exb_destroy, LIB), Cint, (Ptr{Cvoid},), e.handle), ext)
+    c.npar > 0 && check(ccall((:exb_set_params, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float64}, Ptr{Cvoid}), h[], c.θ, stream().handle))
+    ext
+end
+
+# ---- callbacks: same signatures / return conventions as src/nlp.jl:1798-1940 -------------------------
+const M{T,VT} = AbstractExaModel{T,VT,B200Extension}
+st() = stream().handle
+
+function NLPModels.obj(m::M, x::AbstractVector)
+    out = Ref{Float64}(0)
+    check(ccall((:exb_obj, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float64}, Ptr{Float64}, Ptr{Cvoid}), m.ext.handle, x, out, st()))
+    out[]
+end
+function NLPModels.grad!(m::M, x::AbstractVector, g::AbstractVector)
+    check(ccall((:exb_grad, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}), m.ext.handle, x, g, st())); g
+end
+function NLPModels.cons_nln!(m::M, x::AbstractVector, c::AbstractVector)
+    check(ccall((:exb_cons, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}), m.ext.handle, x, c, st())); c
+end
+function NLPModels.jac_coord!(m::M, x::AbstractVector, vals::AbstractVector)
+    check(ccall((:exb_jac, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}), m.ext.handle, x, vals, st())); vals
+end
+function NLPModels.hess_coord!(m::M, x::AbstractVector, y::AbstractVector, vals::AbstractVector; obj_weight = one(eltype(x)))
+    check(ccall((:exb_hess, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Cdouble, CuPtr{Float64}, Ptr{Cvoid}),
+        m.ext.handle, x, y, obj_weight, vals, st())); vals
+end
+function NLPModels.hess_coord!(m::M, x::AbstractVector, vals::AbstractVector; obj_weight = one(eltype(x)))   # nlp.jl:1906-1915
+    check(ccall((:exb_hess, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Cdouble, CuPtr{Float64}, Ptr{Cvoid}),
+        m.ext.handle, x, CU_NULL, obj_weight, vals, st())); vals
+end
+for (name, sym64, sym32) in ((:jac_structure!, :exb_jac_structure64, :exb_jac_structure32),
+                             (:hess_structure!, :exb_hess_structure64, :exb_hess_structure32))
+    @eval function NLPModels.$name(m::M, rows::CuVector{I}, cols::CuVector{I}) where {I<:Union{Int64,Int32}}
+        sym = I === Int64 ? $(QuoteNode(sym64)) : $(QuoteNode(sym32))
+        check(ccall((sym, LIB), Cint, (Ptr{Cvoid}, CuPtr{I}, CuPtr{I}, Ptr{Cvoid}), m.ext.handle, rows, cols, st()))
+        rows, cols
+    end
+end
+
+end # module
