@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <sstream>
 #include <string>
@@ -58,6 +59,7 @@ struct Plan {
   std::string error;
   // pattern lists per kernel (indices into pats), fixed at generation time
   std::vector<int> k_hess, k_jac, k_sgrad, k_cons, k_obj, k_aug;
+  int block = 128, minb = 16;  // launch shape of the generated kernels (tuning knobs: EXB_TUNE_BLOCK / EXB_TUNE_MINB)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -652,12 +654,14 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes) {
     if (p.ir.kind == KIND_AUG) pl.k_aug.push_back((int)k);
   }
   // module source
+  if (const char* e = getenv("EXB_TUNE_BLOCK")) { int b = atoi(e); if (b == 64 || b == 128 || b == 256 || b == 512) pl.block = b; }
+  if (const char* e = getenv("EXB_TUNE_MINB")) { int b = atoi(e); if (b >= 1 && b <= 32) pl.minb = b; }
   std::ostringstream o;
   o << "// generated by exb_plan.hpp -- one struct per pattern, kernels per callback\n";
   for (size_t k = 0; k < pl.pats.size(); k++) o << gen_pattern(pl.pats[k], (int)k);
   auto kern = [&](const char* name, const char* body, const std::vector<int>& v, const char* targ) {
     if (v.empty()) return;
-    o << "extern \"C\" __global__ void __launch_bounds__(EXB_BLOCK) " << name << "(const ExbGroup g, const ExbCall c) { "
+    o << "extern \"C\" __global__ void __launch_bounds__(EXB_BLOCK, EXB_MINB) " << name << "(const ExbGroup g, const ExbCall c) { "
       << body << "<" << targ << plist(v) << ">(g, c); }\n";
   };
   kern("exb_hess_g0", "exb_hess_body", pl.k_hess, "");

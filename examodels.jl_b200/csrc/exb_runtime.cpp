@@ -111,11 +111,18 @@ const char* KNAME[KN_COUNT] = {"exb_hess_g0", "exb_jac_g0", "exb_sgrad_g0", "exb
 
 }  // namespace
 
+// One kernel module is compiled per LAUNCH-SHAPE VARIANT (same generated code, different
+// __launch_bounds__ min-blocks => different register budget: 32 / 40 / natural).  Which variant is
+// fastest depends on the pattern (LV: 32 registers, +25%; AC-OPF: 40; Goddard rocket: natural), so the
+// runtime measures each kernel once on the device at its first call and remembers the winner
+// (exb_<hash>.tune next to the modules).
+struct Variant { int minb; std::string source, hash, cubin_path, cu_path; };
 struct exb_plan {
   exb::Plan pl;
-  std::string full_source;
-  std::string hash;
-  std::string cubin_path, cu_path;
+  std::vector<Variant> var;
+  std::string full_source;            // variant 0, for exb_plan_source
+  std::string hash;                   // variant-independent hash (tune file name)
+  std::string cubin_path, tune_path;  // variant 0 module path
   bool from_cache = false;
   const std::vector<int>& list(int kn) const {
     switch (kn) {
@@ -131,8 +138,10 @@ struct exb_plan {
 
 namespace {
 
-struct Launch {          // one generated kernel of the module, ready to launch
-  CUfunction fn = nullptr;
+struct Launch {          // one generated kernel, ready to launch
+  CUfunction fn = nullptr;            // the variant in use
+  std::vector<CUfunction> cand;       // one per compiled variant
+  int best = -1;                      // index into cand once tuned
   ExbGroup g{};          // device pointers
   unsigned nblocks = 0;
   unsigned smem = 0;
@@ -146,13 +155,25 @@ int make_plan(const void* ir, size_t bytes, exb_plan** out) {
     delete p;
     return fail(EXB_ERR_IR, e);
   }
-  p->full_source = std::string(exb_device_header_text) + "\n" + p->pl.source;
-  char buf[32];
-  snprintf(buf, sizeof buf, "%016llx", (unsigned long long)fnv1a(NVCC_FLAGS_CLEAN, fnv1a(p->full_source)));
-  p->hash = buf;
+  std::vector<int> minbs = {16, 12, 1};
+  if (getenv("EXB_TUNE_MINB")) minbs = {p->pl.minb};
   std::string d = cache_dir();
-  p->cubin_path = d + "/exb_" + p->hash + ".cubin";
-  p->cu_path = d + "/exb_" + p->hash + ".cu";
+  char buf[32];
+  snprintf(buf, sizeof buf, "%016llx", (unsigned long long)fnv1a(NVCC_FLAGS_CLEAN, fnv1a(std::string(exb_device_header_text) + p->pl.source + std::to_string(p->pl.block))));
+  p->hash = buf;
+  for (int mb : minbs) {
+    Variant v; v.minb = mb;
+    v.source = "#define EXB_BLOCK " + std::to_string(p->pl.block) + "\n#define EXB_MINB " + std::to_string(mb) + "\n" +
+               std::string(exb_device_header_text) + "\n" + p->pl.source;
+    snprintf(buf, sizeof buf, "%016llx", (unsigned long long)fnv1a(NVCC_FLAGS_CLEAN, fnv1a(v.source)));
+    v.hash = buf;
+    v.cubin_path = d + "/exb_" + v.hash + ".cubin";
+    v.cu_path = d + "/exb_" + v.hash + ".cu";
+    p->var.push_back(v);
+  }
+  p->full_source = p->var[0].source;
+  p->cubin_path = p->var[0].cubin_path;
+  p->tune_path = d + "/exb_" + p->hash + ".tune";
   *out = p;
   return EXB_OK;
 }
@@ -160,31 +181,37 @@ int make_plan(const void* ir, size_t bytes, exb_plan** out) {
 bool file_exists(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 && st.st_size > 0; }
 
 int compile_plan(exb_plan* p, bool allow_compile) {
-  if (file_exists(p->cubin_path)) { p->from_cache = true; return EXB_OK; }
+  bool all = true;
+  for (auto& v : p->var) all = all && file_exists(v.cubin_path);
+  if (all) { p->from_cache = true; return EXB_OK; }
   if (!allow_compile) return fail(EXB_ERR_COMPILE, "kernel module " + p->cubin_path + " is not cached and EXB_FLAG_NO_COMPILE is set");
-  // serialise concurrent builders of the same module (ranks of one job, parallel tests)
+  // serialise concurrent builders of the same model (ranks of one job, parallel tests)
   std::string lock = p->cubin_path + ".lock";
   int fd = open(lock.c_str(), O_CREAT | O_RDWR, 0666);
   if (fd >= 0) flock(fd, LOCK_EX);
   int rc = EXB_OK;
-  if (!file_exists(p->cubin_path)) {
-    {
-      std::ofstream f(p->cu_path);
-      f << p->full_source;
-    }
-    std::string tmp = p->cubin_path + ".tmp" + std::to_string((long)getpid());
-    std::string log = p->cubin_path + ".log";
-    std::string cmd = nvcc_path() + " " + NVCC_FLAGS_CLEAN + " -o " + tmp + " " + p->cu_path + " > " + log + " 2>&1";
+  std::string cmd;   // the variants compile concurrently: one shell, background jobs, wait
+  std::vector<const Variant*> todo;
+  for (auto& v : p->var) {
+    if (file_exists(v.cubin_path)) continue;
+    { std::ofstream f(v.cu_path); f << v.source; }
+    std::string tmp = v.cubin_path + ".tmp" + std::to_string((long)getpid());
+    cmd += "( " + nvcc_path() + " " + NVCC_FLAGS_CLEAN + " -o " + tmp + " " + v.cu_path + " > " + v.cubin_path + ".log 2>&1 && mv " + tmp + " " +
+           v.cubin_path + " ) & ";
+    todo.push_back(&v);
+  }
+  if (!todo.empty()) {
+    cmd += "wait";
     int st = system(cmd.c_str());
-    if (st != 0 || !file_exists(tmp)) {
-      std::ifstream lf(log);
+    (void)st;
+    for (const Variant* v : todo) {
+      if (file_exists(v->cubin_path)) continue;
+      std::ifstream lf(v->cubin_path + ".log");
       std::stringstream ss; ss << lf.rdbuf();
       std::string msg = ss.str();
       if (msg.size() > 4000) msg = msg.substr(0, 4000);
-      rc = fail(EXB_ERR_COMPILE, "nvcc failed (" + cmd + "): " + msg);
-      unlink(tmp.c_str());
-    } else {
-      rename(tmp.c_str(), p->cubin_path.c_str());
+      rc = fail(EXB_ERR_COMPILE, "nvcc failed for " + v->cu_path + ": " + msg);
+      break;
     }
   } else {
     p->from_cache = true;
@@ -198,7 +225,7 @@ int compile_plan(exb_plan* p, bool allow_compile) {
 struct exb_model {
   exb_plan* plan = nullptr;
   int device = 0, rank = 0, world = 1;
-  CUmodule mod = nullptr;
+  std::vector<CUmodule> mods;
   Launch k[KN_COUNT];
   std::vector<void*> dev;      // everything cudaMalloc'ed by the handle
   size_t dev_bytes = 0;
@@ -235,16 +262,53 @@ int dmalloc(exb_model* m, void** p, size_t bytes) {
   return EXB_OK;
 }
 
-int launch(exb_model* m, int kn, const ExbCall& c, cudaStream_t st) {
+int launch_fn(exb_model* m, int kn, CUfunction fn, const ExbCall& c, cudaStream_t st) {
   Launch& L = m->k[kn];
-  if (!L.fn || L.nblocks == 0) return EXB_OK;
   ExbGroup g = L.g;
   ExbCall cc = c;
   void* params[2] = {&g, &cc};
-  CUresult r = g_drv.LaunchKernel(L.fn, L.nblocks, 1, 1, EXB_BLOCK, 1, 1, L.smem, (CUstream)st, params, nullptr);
+  CUresult r = g_drv.LaunchKernel(fn, L.nblocks, 1, 1, (unsigned)m->plan->pl.block, 1, 1, L.smem, (CUstream)st, params, nullptr);
   if (r != CUDA_SUCCESS) return fail(EXB_ERR_CUDA, std::string("launch of ") + KNAME[kn] + ": " + cu_err(r));
   m->launches++; m->last_launches++;
   return EXB_OK;
+}
+
+// First call of a tunable kernel: run every variant on the caller's own buffers (each one fully
+// defines the output, so the result is valid whichever ran last), time them with events and keep
+// the fastest.  This one call synchronises the stream; later calls do not.
+int tune(exb_model* m, int kn, const ExbCall& c, cudaStream_t st) {
+  Launch& L = m->k[kn];
+  cudaEvent_t e0, e1;
+  CU_TRY(m, cudaEventCreate(&e0)); CU_TRY(m, cudaEventCreate(&e1));
+  int rc = EXB_OK; float best_ms = 0; int best = 0;
+  for (size_t v = 0; v < L.cand.size() && !rc; v++) {
+    rc = launch_fn(m, kn, L.cand[v], c, st);                       // warm-up (module load, caches)
+    float ms = 1e30f;
+    for (int rep = 0; rep < 2 && !rc; rep++) {
+      cudaEventRecord(e0, st);
+      rc = launch_fn(m, kn, L.cand[v], c, st);
+      cudaEventRecord(e1, st);
+      if (cudaEventSynchronize(e1) != cudaSuccess) rc = fail(EXB_ERR_CUDA, "kernel failed while tuning");
+      float t = 0; cudaEventElapsedTime(&t, e0, e1);
+      if (t < ms) ms = t;
+    }
+    if (v == 0 || ms < best_ms) { best_ms = ms; best = (int)v; }
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (rc) return rc;
+  L.best = best; L.fn = L.cand[(size_t)best];
+  if (m->rank == 0 && best_ms >= 0.03f) {   // remember, unless the launch was too short to rank variants (append; last entry wins)
+    std::ofstream tf(m->plan->tune_path, std::ios::app);
+    tf << KNAME[kn] << " " << m->plan->var[(size_t)best].minb << "\n";
+  }
+  return EXB_OK;
+}
+
+int launch(exb_model* m, int kn, const ExbCall& c, cudaStream_t st) {
+  Launch& L = m->k[kn];
+  if (!L.fn || L.nblocks == 0) return EXB_OK;
+  if (L.best < 0) return tune(m, kn, c, st);
+  return launch_fn(m, kn, L.fn, c, st);
 }
 
 // Re-lay-out one AoS field as a device column (int fields narrowed to int32 when they fit).
@@ -299,14 +363,27 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
     if (prop.major != 10) return fail(EXB_ERR_CUDA, "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + "; this evaluator targets sm_100a (B200) only");
   }
   // module
-  std::vector<char> image;
-  {
-    std::ifstream f(P->cubin_path, std::ios::binary);
+  CUresult r = CUDA_SUCCESS;
+  for (auto& v : P->var) {
+    std::vector<char> image;
+    std::ifstream f(v.cubin_path, std::ios::binary);
     image.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
-    if (image.empty()) return fail(EXB_ERR_COMPILE, "cannot read " + P->cubin_path);
+    if (image.empty()) return fail(EXB_ERR_COMPILE, "cannot read " + v.cubin_path);
+    CUmodule mod = nullptr;
+    r = g_drv.ModuleLoadData(&mod, image.data());
+    if (r != CUDA_SUCCESS) return fail(EXB_ERR_COMPILE, "cuModuleLoadData(" + v.cubin_path + "): " + cu_err(r));
+    m->mods.push_back(mod);
   }
-  CUresult r = g_drv.ModuleLoadData(&m->mod, image.data());
-  if (r != CUDA_SUCCESS) return fail(EXB_ERR_COMPILE, "cuModuleLoadData(" + P->cubin_path + "): " + cu_err(r));
+  // a previous run's tuning result for this model's kernels: "<kernel> <minb>" lines
+  std::vector<int> tuned(KN_COUNT, -1);
+  {
+    std::ifstream tf(P->tune_path);
+    std::string name; int mb;
+    while (tf >> name >> mb)
+      for (int kn = 0; kn < KN_COUNT; kn++)
+        if (name == KNAME[kn])
+          for (size_t vi = 0; vi < P->var.size(); vi++) if (P->var[vi].minb == mb) tuned[kn] = (int)vi;
+  }
 
   // per-pattern arguments
   const size_t np = pl.pats.size();
@@ -338,34 +415,52 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
     const std::vector<int>& lst = P->list(kn);
     if (lst.empty()) continue;
     Launch& L = m->k[kn];
-    r = g_drv.ModuleGetFunction(&L.fn, m->mod, KNAME[kn]);
-    if (r != CUDA_SUCCESS) return fail(EXB_ERR_COMPILE, std::string("kernel ") + KNAME[kn] + " missing from module: " + cu_err(r));
+    for (CUmodule mod : m->mods) {
+      CUfunction fn = nullptr;
+      r = g_drv.ModuleGetFunction(&fn, mod, KNAME[kn]);
+      if (r != CUDA_SUCCESS) return fail(EXB_ERR_COMPILE, std::string("kernel ") + KNAME[kn] + " missing from module: " + cu_err(r));
+      L.cand.push_back(fn);
+    }
+    const bool tunable = kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD || kn == KN_CONS || kn == KN_OBJ;
+    L.best = (!tunable || L.cand.size() == 1) ? 0 : tuned[kn];
+    L.fn = L.cand[L.best >= 0 ? (size_t)L.best : 0];
+    const long long BLK = P->pl.block;
     std::vector<ExbPatArgs> args(lst.size());
-    std::vector<int> blk_end(lst.size());
-    long long tot = 0; int maxns = 1;
+    std::vector<long long> nb(lst.size());
+    long long tot = 0, maxnb = 0; int maxns = 1;
     for (size_t q = 0; q < lst.size(); q++) {
       args[q] = pa[(size_t)lst[q]];
-      tot += (args[q].n + EXB_BLOCK - 1) / EXB_BLOCK;
-      if (tot > 2147483647LL) return fail(EXB_ERR_ARG, "too many blocks");
-      blk_end[q] = (int)tot;
+      nb[q] = (args[q].n + BLK - 1) / BLK;
+      tot += nb[q]; if (nb[q] > maxnb) maxnb = nb[q];
       const exb::PatternPlan& p = pl.pats[(size_t)lst[q]];
       int ns = (kn == KN_HESS) ? p.o2step : (kn == KN_JAC || kn == KN_SGRAD) ? p.o1step : 1;
       if (ns <= EXB_TILE_MAX_NS && ns > maxns) maxns = ns;
     }
-    void *d_args = nullptr, *d_blk = nullptr;
+    if (tot == 0) continue;   // nothing local to evaluate (e.g. a shard with no points)
+    // chunked round-robin interleave of the patterns' block ranges (see ExbGroup)
+    int shift = 0;
+    while ((tot >> shift) > 4096 && shift < 9) shift++;
+    const long long csz = 1LL << shift;
+    std::vector<ExbChunk> chunks;
+    for (long long r = 0; r * csz < maxnb; r++)
+      for (size_t q = 0; q < lst.size(); q++)
+        if (r * csz < nb[q]) chunks.push_back(ExbChunk{(int)q, (int)(r * csz)});
+    if ((long long)chunks.size() * csz > 2147483647LL) return fail(EXB_ERR_ARG, "too many blocks");
+    void *d_args = nullptr, *d_chunk = nullptr;
     int rc = dmalloc(m, &d_args, args.size() * sizeof(ExbPatArgs)); if (rc) return rc;
-    rc = dmalloc(m, &d_blk, blk_end.size() * sizeof(int)); if (rc) return rc;
+    rc = dmalloc(m, &d_chunk, chunks.size() * sizeof(ExbChunk)); if (rc) return rc;
     CU_TRY(m, cudaMemcpy(d_args, args.data(), args.size() * sizeof(ExbPatArgs), cudaMemcpyHostToDevice));
-    CU_TRY(m, cudaMemcpy(d_blk, blk_end.data(), blk_end.size() * sizeof(int), cudaMemcpyHostToDevice));
-    L.g.pat = (const ExbPatArgs*)d_args; L.g.blk_end = (const int*)d_blk; L.g.np = (int)lst.size();
-    L.nblocks = (unsigned)tot;
-    L.smem = (kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD) ? (maxns > 1 ? (unsigned)(EXB_BLOCK * maxns * 8) : 16u) : 0u;
+    CU_TRY(m, cudaMemcpy(d_chunk, chunks.data(), chunks.size() * sizeof(ExbChunk), cudaMemcpyHostToDevice));
+    L.g.pat = (const ExbPatArgs*)d_args; L.g.chunk = (const ExbChunk*)d_chunk; L.g.np = (int)lst.size(); L.g.shift = shift;
+    L.nblocks = (unsigned)(chunks.size() * csz);
+    L.smem = (kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD) ? (maxns > 1 ? (unsigned)(BLK * maxns * 8) : 16u) : 0u;
   }
   // scratch owned by the handle (ext:21-31,180-190)
   int rc;
   rc = dmalloc(m, (void**)&m->d_theta, (size_t)pl.m.npar * 8); if (rc) return rc;
   CU_TRY(m, cudaMemset(m->d_theta, 0, (size_t)(pl.m.npar ? pl.m.npar : 1) * 8));
   rc = dmalloc(m, (void**)&m->d_objpart, (size_t)(m->k[KN_OBJ].nblocks + 1) * 8); if (rc) return rc;
+  CU_TRY(m, cudaMemset(m->d_objpart, 0, (size_t)(m->k[KN_OBJ].nblocks + 1) * 8));   // padding blocks never write
   rc = dmalloc(m, (void**)&m->d_obj, 8); if (rc) return rc;
   rc = dmalloc(m, (void**)&m->d_gradbuf, (size_t)pl.nnzg * 8); if (rc) return rc;
   rc = dmalloc(m, (void**)&m->d_conbuf, (size_t)pl.nconaug * 8); if (rc) return rc;
@@ -408,7 +503,7 @@ void free_model(exb_model* m) {
   if (!m) return;
   DeviceGuard dg(m->device);
   for (void* p : m->dev) cudaFree(p);
-  if (m->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(m->mod);
+  for (CUmodule mod : m->mods) if (mod && g_drv.ModuleUnload) g_drv.ModuleUnload(mod);
   if (m->hx) cudaFreeHost(m->hx);
   if (m->hy) cudaFreeHost(m->hy);
   if (m->hout) cudaFreeHost(m->hout);

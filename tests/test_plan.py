@@ -47,7 +47,7 @@ def test_generated_source_is_model_size_independent():
     assert a.source() == b.source() and a.module_path() == b.module_path()
     src = a.source()
     for kern in ("exb_hess_g0", "exb_jac_g0", "exb_sgrad_g0", "exb_cons_g0", "exb_obj_g0", "exb_hstruct64_g0"):
-        assert f'extern "C" __global__ void __launch_bounds__(EXB_BLOCK) {kern}' in src
+        assert f'extern "C" __global__ void __launch_bounds__(EXB_BLOCK, EXB_MINB) {kern}' in src
     assert "sincos" in src and "struct P0" in src and "struct P1" in src
 
 
