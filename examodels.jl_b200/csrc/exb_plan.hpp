@@ -36,6 +36,7 @@ enum { FX_NONE, FX_FIRST, FX_SECOND };
 static const int EXB_MAXF_HOST = 16;  // must equal EXB_MAXF in exb_device.cuh
 static const int EXB_MAXD_HOST = 4;
 static const int EXB_TILE_MAX_NS_HOST = 20;
+static const int EXB_CPAT_MAX = 256;  // patterns whose arguments fit the module's constant bank (224 B each)
 
 struct NodeInfo { int kind = K_REAL; int fx = FX_NONE; bool is_int = false; };
 
@@ -522,7 +523,7 @@ inline std::string gen_pattern(const PatternPlan& p, int index) {
   const int a1 = ns1 > 0 ? ns1 : 1, a2 = ns2 > 0 ? ns2 : 1;
   const std::string A = "const ExbPatArgs& pa, const long long kg";
   o << "struct P" << index << " {\n";
-  o << "  static constexpr int KIND = " << p.ir.kind << ", NS1 = " << ns1 << ", NS2 = " << ns2 << ";\n";
+  o << "  static constexpr int INDEX = " << index << ", KIND = " << p.ir.kind << ", NS1 = " << ns1 << ", NS2 = " << ns2 << ";\n";
   {  // row (offset0, nlp.jl:1980-2001; idxx :2012-2015)
     Body B; Gen g(p, B, 0);
     std::vector<std::string> tail;

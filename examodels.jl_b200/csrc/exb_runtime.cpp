@@ -75,6 +75,7 @@ struct Drv {
   CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
   CUresult (*ModuleUnload)(CUmodule) = nullptr;
   CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*) = nullptr;
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
   CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
@@ -94,7 +95,7 @@ bool entry(const char* name, F& f) {
 bool load_driver() {
   std::call_once(g_drv_once, [] {
     g_drv.ok = entry("cuModuleLoadData", g_drv.ModuleLoadData) && entry("cuModuleUnload", g_drv.ModuleUnload) &&
-               entry("cuModuleGetFunction", g_drv.ModuleGetFunction) && entry("cuLaunchKernel", g_drv.LaunchKernel) &&
+               entry("cuModuleGetFunction", g_drv.ModuleGetFunction) && entry("cuModuleGetGlobal", g_drv.ModuleGetGlobal) && entry("cuLaunchKernel", g_drv.LaunchKernel) &&
                entry("cuFuncGetAttribute", g_drv.FuncGetAttribute) && entry("cuGetErrorString", g_drv.GetErrorString);
   });
   return g_drv.ok;
@@ -164,6 +165,7 @@ int make_plan(const void* ir, size_t bytes, exb_plan** out) {
   for (int mb : minbs) {
     Variant v; v.minb = mb;
     v.source = "#define EXB_BLOCK " + std::to_string(p->pl.block) + "\n#define EXB_MINB " + std::to_string(mb) + "\n" +
+               ((int)p->pl.pats.size() <= exb::EXB_CPAT_MAX && !p->pl.pats.empty() ? "#define EXB_NPAT " + std::to_string(p->pl.pats.size()) + "\n" : std::string()) +
                std::string(exb_device_header_text) + "\n" + p->pl.source;
     snprintf(buf, sizeof buf, "%016llx", (unsigned long long)fnv1a(NVCC_FLAGS_CLEAN, fnv1a(v.source)));
     v.hash = buf;
@@ -408,6 +410,15 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
         if (rc) return rc;
         if (is32) a.i32mask |= (1LL << f);
       }
+    }
+  }
+  // per-pattern arguments into each module's constant bank (see EXB_PAT in exb_device.cuh)
+  if ((int)np <= exb::EXB_CPAT_MAX && np > 0) {
+    for (CUmodule mod : m->mods) {
+      CUdeviceptr dp = 0; size_t bytes = 0;
+      r = g_drv.ModuleGetGlobal(&dp, &bytes, mod, "exb_cpat");
+      if (r != CUDA_SUCCESS || bytes != np * sizeof(ExbPatArgs)) return fail(EXB_ERR_COMPILE, "exb_cpat missing from module or of the wrong size");
+      CU_TRY(m, cudaMemcpy((void*)dp, pa.data(), bytes, cudaMemcpyHostToDevice));
     }
   }
   // kernels
