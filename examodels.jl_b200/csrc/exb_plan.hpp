@@ -35,7 +35,7 @@ enum { FX_NONE, FX_FIRST, FX_SECOND };
 
 static const int EXB_MAXF_HOST = 16;  // must equal EXB_MAXF in exb_device.cuh
 static const int EXB_MAXD_HOST = 4;
-static const int EXB_TILE_MAX_NS_HOST = 20;
+static const int EXB_TILE_MAX_NS_HOST = 96;
 static const int EXB_CPAT_MAX = 256;  // patterns whose arguments fit the module's constant bank (224 B each)
 
 struct NodeInfo { int kind = K_REAL; int fx = FX_NONE; bool is_int = false; };

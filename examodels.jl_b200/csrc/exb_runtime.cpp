@@ -78,6 +78,7 @@ struct Drv {
   CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*) = nullptr;
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
   CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
   bool ok = false;
 };
@@ -96,7 +97,7 @@ bool load_driver() {
   std::call_once(g_drv_once, [] {
     g_drv.ok = entry("cuModuleLoadData", g_drv.ModuleLoadData) && entry("cuModuleUnload", g_drv.ModuleUnload) &&
                entry("cuModuleGetFunction", g_drv.ModuleGetFunction) && entry("cuModuleGetGlobal", g_drv.ModuleGetGlobal) && entry("cuLaunchKernel", g_drv.LaunchKernel) &&
-               entry("cuFuncGetAttribute", g_drv.FuncGetAttribute) && entry("cuGetErrorString", g_drv.GetErrorString);
+               entry("cuFuncGetAttribute", g_drv.FuncGetAttribute) && entry("cuFuncSetAttribute", g_drv.FuncSetAttribute) && entry("cuGetErrorString", g_drv.GetErrorString);
   });
   return g_drv.ok;
 }
@@ -465,6 +466,11 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
     L.g.pat = (const ExbPatArgs*)d_args; L.g.chunk = (const ExbChunk*)d_chunk; L.g.np = (int)lst.size(); L.g.shift = shift;
     L.nblocks = (unsigned)(chunks.size() * csz);
     L.smem = (kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD) ? (maxns > 1 ? (unsigned)(BLK * maxns * 8) : 16u) : 0u;
+    if (L.smem > 48u * 1024u)   // tiles of patterns with many slots per point: opt in to large dynamic shared memory
+      for (CUfunction fn : L.cand) {
+        r = g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)L.smem);
+        if (r != CUDA_SUCCESS) return fail(EXB_ERR_CUDA, std::string("cuFuncSetAttribute(max dynamic smem): ") + cu_err(r));
+      }
   }
   // scratch owned by the handle (ext:21-31,180-190)
   int rc;
