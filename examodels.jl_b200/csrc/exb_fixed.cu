@@ -16,17 +16,29 @@
 namespace {
 
 // one thread per distinct target: y[target[t]] (+)= sum_{l in [ptr[t], ptr[t+1])} buf[slot[l]]
-template <bool ACC>
-__global__ void __launch_bounds__(256) k_compress(const double* __restrict__ buf, const long long* __restrict__ ptr,
-                                                  const long long* __restrict__ slot, const long long* __restrict__ target,
+// IDX = int when every index fits 32 bits (halves the index traffic), else long long.
+// target == nullptr means "every row/variable 1..nt is a target, in order" (dense case).
+template <bool ACC, typename IDX>
+__global__ void __launch_bounds__(256) k_compress(const double* __restrict__ buf, const IDX* __restrict__ ptr,
+                                                  const IDX* __restrict__ slot, const IDX* __restrict__ target,
                                                   long long nt, double* __restrict__ y) {
   const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
   if (t >= nt) return;
   const long long lo = __ldg(ptr + t), hi = __ldg(ptr + t + 1);
   double s = 0.0;
   for (long long l = lo; l < hi; l++) s += __ldg(buf + __ldg(slot + l));
-  const long long k = __ldg(target + t) - 1;
+  const long long k = target ? (long long)__ldg(target + t) - 1 : t;
   if (ACC) y[k] += s; else y[k] = s;
+}
+
+__global__ void k_narrow(const long long* __restrict__ in, int* __restrict__ out, long long n) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t < n) out[t] = (int)in[t];
+}
+// flag[0] = 1 iff target[t] == t + 1 for all t
+__global__ void k_is_iota(const long long* __restrict__ target, long long n, int* flag) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t < n && target[t] != t + 1) *flag = 0;
 }
 
 // deterministic sum of n partials into out[0]: fixed per-thread strided order + fixed tree
@@ -57,12 +69,50 @@ __global__ void k_iota_ll(long long* p, long long n) {
 
 }  // namespace
 
-cudaError_t exb_fx_compress(const double* buf, const long long* ptr, const long long* slot, const long long* target,
+cudaError_t exb_fx_compress(const double* buf, const void* ptr, const void* slot, const void* target, int idx32,
                             long long nt, double* y, int accumulate, cudaStream_t st) {
   if (nt <= 0) return cudaSuccess;
   const unsigned grid = (unsigned)((nt + 255) / 256);
-  if (accumulate) k_compress<true><<<grid, 256, 0, st>>>(buf, ptr, slot, target, nt, y);
-  else k_compress<false><<<grid, 256, 0, st>>>(buf, ptr, slot, target, nt, y);
+  if (idx32) {
+    if (accumulate) k_compress<true, int><<<grid, 256, 0, st>>>(buf, (const int*)ptr, (const int*)slot, (const int*)target, nt, y);
+    else k_compress<false, int><<<grid, 256, 0, st>>>(buf, (const int*)ptr, (const int*)slot, (const int*)target, nt, y);
+  } else {
+    if (accumulate) k_compress<true, long long><<<grid, 256, 0, st>>>(buf, (const long long*)ptr, (const long long*)slot, (const long long*)target, nt, y);
+    else k_compress<false, long long><<<grid, 256, 0, st>>>(buf, (const long long*)ptr, (const long long*)slot, (const long long*)target, nt, y);
+  }
+  return cudaGetLastError();
+}
+
+// In-place post-processing of a sort_runs result: drop `target` when it is 1..nruns (returns *dense = 1),
+// and narrow the three arrays to int32 when everything fits (returns *idx32 = 1; arrays are re-allocated).
+cudaError_t exb_fx_pack_runs(void** slot, void** target, void** ptr, long long nslots, long long nruns, long long max_index,
+                             int* idx32, int* dense, cudaStream_t st) {
+  *idx32 = 0; *dense = 0;
+  if (nruns <= 0) return cudaSuccess;
+  cudaError_t e;
+  int* flag = nullptr; int h = 1;
+  if ((e = cudaMalloc(&flag, 4)) != cudaSuccess) return e;
+  cudaMemcpyAsync(flag, &h, 4, cudaMemcpyHostToDevice, st);
+  k_is_iota<<<(unsigned)((nruns + 255) / 256), 256, 0, st>>>((const long long*)*target, nruns, flag);
+  cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, st);
+  e = cudaStreamSynchronize(st);
+  cudaFree(flag);
+  if (e != cudaSuccess) return e;
+  if (h) { cudaFree(*target); *target = nullptr; *dense = 1; }
+  if (max_index < 2147483647LL && nslots < 2147483647LL) {
+    void** arr[3] = {slot, target, ptr};
+    long long len[3] = {nslots, nruns, nruns + 1};
+    for (int k = 0; k < 3; k++) {
+      if (!*arr[k]) continue;
+      int* out = nullptr;
+      if ((e = cudaMalloc(&out, (size_t)(len[k] ? len[k] : 1) * 4)) != cudaSuccess) return e;
+      if (len[k] > 0) k_narrow<<<(unsigned)((len[k] + 255) / 256), 256, 0, st>>>((const long long*)*arr[k], out, len[k]);
+      if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+      cudaFree(*arr[k]);
+      *arr[k] = out;
+    }
+    *idx32 = 1;
+  }
   return cudaGetLastError();
 }
 
@@ -81,8 +131,8 @@ cudaError_t exb_fx_fill(long long* p, long long n, long long v, cudaStream_t st)
 // slot number as payload, then run-length encode.  Outputs are freshly cudaMalloc'ed arrays sized to the
 // number of owned runs: *slot_out[n_owned], *target_out[nruns], *ptr_out[nruns + 1].
 cudaError_t exb_fx_sort_runs(const long long* keys, long long n, long long** slot_out, long long** target_out,
-                             long long** ptr_out, long long* nruns_out, cudaStream_t st) {
-  *slot_out = *target_out = *ptr_out = nullptr; *nruns_out = 0;
+                             long long** ptr_out, long long* nruns_out, long long* nslots_out, cudaStream_t st) {
+  *slot_out = *target_out = *ptr_out = nullptr; *nruns_out = 0; *nslots_out = 0;
   if (n <= 0) return cudaSuccess;
   cudaError_t e;
   long long *vals_in = nullptr, *keys_s = nullptr, *vals_s = nullptr, *uniq = nullptr, *cnt = nullptr, *d_nruns = nullptr;
@@ -115,6 +165,7 @@ cudaError_t exb_fx_sort_runs(const long long* keys, long long n, long long** slo
       long long nowned = 0;
       EXB_FX_TRY(cudaMemcpyAsync(&nowned, cnt + nruns, 8, cudaMemcpyDeviceToHost, st));
       EXB_FX_TRY(cudaStreamSynchronize(st));
+      *nslots_out = nowned;
       EXB_FX_TRY(cudaMalloc(slot_out, (nowned ? nowned : 1) * 8));
       EXB_FX_TRY(cudaMalloc(target_out, nruns * 8));
       EXB_FX_TRY(cudaMalloc(ptr_out, (nruns + 1) * 8));

@@ -48,6 +48,7 @@ struct PatternPlan {
   i64 o0 = 0, o1 = 0, o2 = 0;  // 0-based bases (SIMDFunction offsets)
   i64 oa = 0;                  // aug: first conbuffer slot (ConstraintAugmentation.oa)
   i64 ob = 0;                  // obj: first objbuffer slot
+  int ppt0 = 1, ppt1 = 1, ppt2 = 1;   // points per thread in the value / first-order / second-order kernels
   std::vector<int> leaf1;      // representative Var IR node per first-order slot
   std::vector<std::pair<int, int>> leaf2;
 };
@@ -517,7 +518,22 @@ inline void emit_fn(std::ostringstream& o, const std::string& sig, const Body& B
   o << "  }\n";
 }
 
-inline std::string gen_pattern(const PatternPlan& p, int index) {
+// Points per thread: cheap bodies are dominated by the per-block prologue / tile-store epilogue, so they get
+// several points per thread (also more loads in flight per thread); heavy bodies keep one.
+inline int body_weight(const Body& B) {
+  int w = 0;
+  for (auto& l : B.lines) w += (l.find("exb_uni<") != std::string::npos || l.find("exb_bi<") != std::string::npos ||
+                                l.find("exb_pow_") != std::string::npos || l.find("exb_f1<") != std::string::npos ||
+                                l.find("exb_f2<") != std::string::npos) ? 30 : 1;
+  return w;
+}
+inline int ppt_for(int weight, int ns) {
+  int p = weight <= 60 ? 4 : weight <= 150 ? 2 : 1;
+  while (p > 1 && p * ns > 16) p >>= 1;   // slots live in registers
+  return p;
+}
+
+inline std::string gen_pattern(PatternPlan& p, int index) {
   std::ostringstream o;
   const int ns1 = p.o1step, ns2 = p.o2step;
   const int a1 = ns1 > 0 ? ns1 : 1, a2 = ns2 > 0 ? ns2 : 1;
@@ -547,6 +563,7 @@ inline std::string gen_pattern(const PatternPlan& p, int index) {
     Body B; Gen g(p, B, 0);
     NV& r = g.fwd(p.ir.root);
     emit_fn(o, "double val(" + A + ", const double* __restrict__ x, const double* __restrict__ th)", B, {"return " + r.x.s + ";"});
+    p.ppt0 = ppt_for(body_weight(B), 1);
   }
   {  // d1
     Body B; Gen g(p, B, 1);
@@ -558,6 +575,7 @@ inline std::string gen_pattern(const PatternPlan& p, int index) {
       for (int j = 0; j < ns1; j++) tail.push_back("s[" + std::to_string(j) + "] = " + g.slot[(size_t)j].s + ";");
     }
     emit_fn(o, "void d1(" + A + ", const double* __restrict__ x, const double* __restrict__ th, double (&s)[" + std::to_string(a1) + "])", B, tail);
+    p.ppt1 = ppt_for(body_weight(B), a1);
   }
   {  // d2
     Body B; Gen g(p, B, 2);
@@ -569,6 +587,7 @@ inline std::string gen_pattern(const PatternPlan& p, int index) {
       for (int j = 0; j < ns2; j++) tail.push_back("s[" + std::to_string(j) + "] = " + g.slot[(size_t)j].s + ";");
     }
     emit_fn(o, "void d2(" + A + ", const double* __restrict__ x, const double* __restrict__ th, const double a0, double (&s)[" + std::to_string(a2) + "])", B, tail);
+    p.ppt2 = ppt_for(body_weight(B), a2);
   }
   {  // s1: variable index per first-order slot (jacobian.jl:69-83)
     Body B; Gen g(p, B, 0);
@@ -589,6 +608,7 @@ inline std::string gen_pattern(const PatternPlan& p, int index) {
     }
     emit_fn(o, "void s2(" + A + ", long long (&r)[" + std::to_string(a2) + "], long long (&c)[" + std::to_string(a2) + "])", B, tail);
   }
+  o << "  static constexpr int PPT0 = " << p.ppt0 << ", PPT1 = " << p.ppt1 << ", PPT2 = " << p.ppt2 << ";\n";
   o << "};\n";
   return o.str();
 }

@@ -18,6 +18,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -236,8 +237,8 @@ struct exb_model {
   double* d_objpart = nullptr; double* d_obj = nullptr;
   double* d_gradbuf = nullptr; double* d_conbuf = nullptr;
   // sorted (target, slot) lists: grad (ext:39-46) and constraint augmentation (ext:48-53)
-  long long *g_slot = nullptr, *g_target = nullptr, *g_ptr = nullptr, g_runs = 0;
-  long long *a_slot = nullptr, *a_target = nullptr, *a_ptr = nullptr, a_runs = 0;
+  void *g_slot = nullptr, *g_target = nullptr, *g_ptr = nullptr; long long g_runs = 0; int g_i32 = 0, g_dense = 0;
+  void *a_slot = nullptr, *a_target = nullptr, *a_ptr = nullptr; long long a_runs = 0; int a_i32 = 0, a_dense = 0;
   std::vector<long long> lo, hi;   // local point range per pattern
   // host shims
   cudaStream_t hstream = nullptr;
@@ -442,11 +443,13 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
     long long tot = 0, maxnb = 0; int maxns = 1;
     for (size_t q = 0; q < lst.size(); q++) {
       args[q] = pa[(size_t)lst[q]];
-      nb[q] = (args[q].n + BLK - 1) / BLK;
-      tot += nb[q]; if (nb[q] > maxnb) maxnb = nb[q];
       const exb::PatternPlan& p = pl.pats[(size_t)lst[q]];
-      int ns = (kn == KN_HESS) ? p.o2step : (kn == KN_JAC || kn == KN_SGRAD) ? p.o1step : 1;
-      if (ns <= EXB_TILE_MAX_NS && ns > maxns) maxns = ns;
+      const bool k2 = kn == KN_HESS, k1 = kn == KN_JAC || kn == KN_SGRAD, k0 = kn == KN_CONS || kn == KN_OBJ;
+      const int ppt = k2 ? p.ppt2 : k1 ? p.ppt1 : k0 ? p.ppt0 : 1;
+      nb[q] = (args[q].n + BLK * ppt - 1) / (BLK * ppt);
+      tot += nb[q]; if (nb[q] > maxnb) maxnb = nb[q];
+      int ns = k2 ? p.o2step : k1 ? p.o1step : 1;
+      if (ns <= EXB_TILE_MAX_NS && ns * ppt > maxns) maxns = ns * ppt;   // tile words per thread
     }
     if (tot == 0) continue;   // nothing local to evaluate (e.g. a shard with no points)
     // chunked round-robin interleave of the patterns' block ranges (see ExbGroup)
@@ -454,9 +457,14 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
     while ((tot >> shift) > 4096 && shift < 9) shift++;
     const long long csz = 1LL << shift;
     std::vector<ExbChunk> chunks;
-    for (long long r = 0; r * csz < maxnb; r++)
-      for (size_t q = 0; q < lst.size(); q++)
-        if (r * csz < nb[q]) chunks.push_back(ExbChunk{(int)q, (int)(r * csz)});
+    if (lst.size() <= 4) {   // few patterns: interleave them so shared parts of x are streamed from HBM once
+      for (long long r = 0; r * csz < maxnb; r++)
+        for (size_t q = 0; q < lst.size(); q++)
+          if (r * csz < nb[q]) chunks.push_back(ExbChunk{(int)q, (int)(r * csz)});
+    } else {                 // many patterns: one after the other, so an SM runs one pattern's code at a time
+      for (size_t q = 0; q < lst.size(); q++)   // (interleaving 32 patterns thrashes the instruction cache: 3x slower)
+        for (long long r = 0; r * csz < nb[q]; r++) chunks.push_back(ExbChunk{(int)q, (int)(r * csz)});
+    }
     if ((long long)chunks.size() * csz > 2147483647LL) return fail(EXB_ERR_ARG, "too many blocks");
     void *d_args = nullptr, *d_chunk = nullptr;
     int rc = dmalloc(m, &d_args, args.size() * sizeof(ExbPatArgs)); if (rc) return rc;
@@ -489,7 +497,9 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
     ExbCall c{}; c.cols = keys; c.rows = nullptr;
     int lrc = e == cudaSuccess ? launch(m, KN_GSTRUCT64, c, 0) : fail(EXB_ERR_CUDA, cudaGetErrorString(e));
     if (!lrc) {
-      e = exb_fx_sort_runs(keys, pl.nnzg, &m->g_slot, &m->g_target, &m->g_ptr, &m->g_runs, 0);
+      long long ns = 0;
+      e = exb_fx_sort_runs(keys, pl.nnzg, (long long**)&m->g_slot, (long long**)&m->g_target, (long long**)&m->g_ptr, &m->g_runs, &ns, 0);
+      if (e == cudaSuccess) e = exb_fx_pack_runs(&m->g_slot, &m->g_target, &m->g_ptr, ns, m->g_runs, std::max(pl.nnzg, pl.m.nvar), &m->g_i32, &m->g_dense, 0);
       if (e != cudaSuccess) lrc = fail(EXB_ERR_CUDA, std::string("gradient sparsity sort: ") + cudaGetErrorString(e));
     }
     cudaFree(keys);
@@ -504,7 +514,9 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
     ExbCall c{}; c.rows = keys;
     int lrc = e == cudaSuccess ? launch(m, KN_AUGROW, c, 0) : fail(EXB_ERR_CUDA, cudaGetErrorString(e));
     if (!lrc) {
-      e = exb_fx_sort_runs(keys, pl.nconaug, &m->a_slot, &m->a_target, &m->a_ptr, &m->a_runs, 0);
+      long long ns = 0;
+      e = exb_fx_sort_runs(keys, pl.nconaug, (long long**)&m->a_slot, (long long**)&m->a_target, (long long**)&m->a_ptr, &m->a_runs, &ns, 0);
+      if (e == cudaSuccess) e = exb_fx_pack_runs(&m->a_slot, &m->a_target, &m->a_ptr, ns, m->a_runs, std::max(pl.nconaug, pl.ncon), &m->a_i32, &m->a_dense, 0);
       if (e != cudaSuccess) lrc = fail(EXB_ERR_CUDA, std::string("augmentation sparsity sort: ") + cudaGetErrorString(e));
     }
     cudaFree(keys);
@@ -682,8 +694,9 @@ int exb_grad(exb_model* m, const double* x, double* g, void* stream) {
   const exb::Plan& pl = m->plan->pl;
   ExbCall c{}; c.x = x; c.th = m->d_theta; c.out = m->d_gradbuf;
   int rc = launch(m, KN_SGRAD, c, st); if (rc) return rc;                        // kerg, ext:669-679
-  CU_TRY(m, cudaMemsetAsync(g, 0, (size_t)pl.m.nvar * 8, st));                   // fill!(g, 0), ext:317
-  CU_TRY(m, exb_fx_compress(m->d_gradbuf, m->g_ptr, m->g_slot, m->g_target, m->g_runs, g, 0, st));   // ext:691-697
+  // fill!(g, 0) (ext:317) is only needed when some variable has no objective term; otherwise every g[v] is assigned
+  if (!(m->g_dense && m->g_runs == pl.m.nvar)) CU_TRY(m, cudaMemsetAsync(g, 0, (size_t)pl.m.nvar * 8, st));
+  CU_TRY(m, exb_fx_compress(m->d_gradbuf, m->g_ptr, m->g_slot, m->g_target, m->g_i32, m->g_runs, g, 0, st));   // ext:691-697
   if (m->g_runs > 0) { m->launches++; m->last_launches++; }
   return EXB_OK;
   EXB_END
@@ -698,7 +711,7 @@ int exb_cons(exb_model* m, const double* x, double* cvals, void* stream) {
   if (m->world > 1) CU_TRY(m, cudaMemsetAsync(cvals, 0, (size_t)pl.ncon * 8, st));
   ExbCall c{}; c.x = x; c.th = m->d_theta; c.out = cvals; c.out2 = m->d_conbuf;
   int rc = launch(m, KN_CONS, c, st); if (rc) return rc;                         // kerf + kerf2, ext:681-688
-  CU_TRY(m, exb_fx_compress(m->d_conbuf, m->a_ptr, m->a_slot, m->a_target, m->a_runs, cvals, 1, st));   // ext:691-697
+  CU_TRY(m, exb_fx_compress(m->d_conbuf, m->a_ptr, m->a_slot, m->a_target, m->a_i32, m->a_runs, cvals, 1, st));   // ext:691-697
   if (m->a_runs > 0) { m->launches++; m->last_launches++; }
   return EXB_OK;
   EXB_END
