@@ -36,7 +36,9 @@ _SYMBOLS = """exb_plan_create exb_plan_destroy exb_plan_dims exb_plan_npatterns 
 exb_plan_source exb_plan_module_path exb_plan_compile exb_create exb_destroy exb_dims exb_set_params exb_obj
 exb_obj_async exb_grad exb_cons exb_jac_structure64 exb_jac_structure32 exb_jac exb_hess_structure64
 exb_hess_structure32 exb_hess exb_host_obj exb_host_grad exb_host_cons exb_host_jac exb_host_hess
-exb_host_jac_structure64 exb_host_hess_structure64 exb_shard exb_stats exb_last_error exb_abi_version""".split()
+exb_host_jac_structure64 exb_host_hess_structure64 exb_shard exb_stats exb_last_error exb_abi_version
+exb_jprod exb_jtprod exb_hprod exb_compressed_dims exb_jac_structure_compressed64 exb_hess_structure_compressed64
+exb_jac_compressed exb_hess_compressed""".split()
 
 
 class ExbError(RuntimeError):
@@ -271,6 +273,25 @@ class ExaModel:
     def hess_structure(self, rows, cols):
         return self._structure("hess", self.nnzh, rows, cols)
 
+    # -- matrix-free products (src/nlp.jl:1882-1978 | ext:353-511) ---------------------------
+    def jprod_nln(self, x, v, Jv):
+        _check(lib().exb_jprod(self.h, self._dev(x, self.nvar), self._dev(v, self.nvar), self._dev(Jv, self.ncon), self._stream()))
+        return Jv
+
+    def jtprod_nln(self, x, v, Jtv):
+        _check(lib().exb_jtprod(self.h, self._dev(x, self.nvar), self._dev(v, self.ncon), self._dev(Jtv, self.nvar), self._stream()))
+        return Jtv
+
+    def hprod(self, x, y, v, Hv, obj_weight=1.0):
+        yp = None if y is None else self._dev(y, self.ncon)
+        _check(lib().exb_hprod(self.h, self._dev(x, self.nvar), yp, self._dev(v, self.nvar), C.c_double(float(obj_weight)),
+                               self._dev(Hv, self.nvar), self._stream()))
+        return Hv
+
+    def compressed(self):
+        """`CompressedNLPModel(m)` (src/utils.jl:425-579): the same model with duplicate COO entries summed."""
+        return CompressedExaModel(self)
+
     # -- sharding / introspection ------------------------------------------------------
     def shard(self, k):
         o = np.zeros(6, dtype=np.int64)
@@ -281,3 +302,37 @@ class ExaModel:
         o = np.zeros(4, dtype=np.int64)
         _check(lib().exb_stats(self.h, _np_ptr(o)))
         return dict(zip(("launches", "last_launches", "device_bytes", "module_cached"), (int(v) for v in o)))
+
+
+class CompressedExaModel:
+    """Duplicate-free COO view of an `ExaModel`: unique (row, col) coordinates in the reference's order
+    (sorted by (col, row), src/utils.jl:478-487,509-510), duplicate values summed (`_compress!`, :564-571)."""
+
+    def __init__(self, inner):
+        self.inner = inner
+        nj, nh = C.c_int64(), C.c_int64()
+        _check(lib().exb_compressed_dims(inner.h, C.byref(nj), C.byref(nh)))
+        self.nvar, self.ncon, self.nnzj, self.nnzh = inner.nvar, inner.ncon, int(nj.value), int(nh.value)
+        for a in ("obj", "grad", "cons_nln", "cons", "new"):
+            setattr(self, a, getattr(inner, a))
+
+    def jac_structure(self, rows, cols):
+        i = self.inner
+        _check(lib().exb_jac_structure_compressed64(i.h, i._dev(rows, self.nnzj, rows.dtype), i._dev(cols, self.nnzj, cols.dtype), i._stream()))
+        return rows, cols
+
+    def hess_structure(self, rows, cols):
+        i = self.inner
+        _check(lib().exb_hess_structure_compressed64(i.h, i._dev(rows, self.nnzh, rows.dtype), i._dev(cols, self.nnzh, cols.dtype), i._stream()))
+        return rows, cols
+
+    def jac_coord(self, x, vals):
+        i = self.inner
+        _check(lib().exb_jac_compressed(i.h, i._dev(x, self.nvar), i._dev(vals, self.nnzj), i._stream()))
+        return vals
+
+    def hess_coord(self, x, y, vals, obj_weight=1.0):
+        i = self.inner
+        yp = None if y is None else i._dev(y, self.ncon)
+        _check(lib().exb_hess_compressed(i.h, i._dev(x, self.nvar), yp, C.c_double(float(obj_weight)), i._dev(vals, self.nnzh), i._stream()))
+        return vals

@@ -41,6 +41,39 @@ __global__ void k_is_iota(const long long* __restrict__ target, long long n, int
   if (t < n && target[t] != t + 1) *flag = 0;
 }
 
+// SpMV over a pre-sorted COO structure (kerspmv / kerspmv2 / kersyspmv / kersyspmv2, ext:482-511):
+// one thread per distinct target index; y[target] (+)= sum_l buf[slot[l]] * v[other[l]].
+// SKIPDIAG drops entries whose other index equals the target (strict-triangle pass of the symmetric product).
+template <bool ACC, bool SKIPDIAG, typename IDX>
+__global__ void __launch_bounds__(256) k_spmv(const double* __restrict__ buf, const IDX* __restrict__ ptr, const IDX* __restrict__ slot,
+                                              const IDX* __restrict__ other, const IDX* __restrict__ target, long long nt,
+                                              const double* __restrict__ v, double* __restrict__ y) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= nt) return;
+  const long long lo = __ldg(ptr + t), hi = __ldg(ptr + t + 1);
+  const long long tg = target ? (long long)__ldg(target + t) : t + 1;
+  double s = 0.0;
+  for (long long l = lo; l < hi; l++) {
+    const long long o = __ldg(other + l);
+    if (SKIPDIAG && o == tg) continue;
+    s += __ldg(buf + __ldg(slot + l)) * __ldg(v + (o - 1));
+  }
+  if (ACC) y[tg - 1] += s; else y[tg - 1] = s;
+}
+template <typename IDX>
+__global__ void k_gather(const long long* __restrict__ src, const IDX* __restrict__ slot, IDX* __restrict__ out, long long n) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t < n) out[t] = (IDX)src[slot[t]];
+}
+__global__ void k_make_keys(const long long* __restrict__ major, const long long* __restrict__ minor, long long mult, long long* keys, long long n) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t < n) keys[t] = major[t] * mult + minor[t];
+}
+__global__ void k_decode_keys(const long long* __restrict__ keys, long long mult, long long* major, long long* minor, long long n) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t < n) { major[t] = keys[t] / mult; minor[t] = keys[t] % mult; }
+}
+
 // deterministic sum of n partials into out[0]: fixed per-thread strided order + fixed tree
 __global__ void __launch_bounds__(1024) k_sum(const double* __restrict__ part, long long n, double* __restrict__ out) {
   __shared__ double sm[32];
@@ -90,7 +123,9 @@ cudaError_t exb_fx_pack_runs(void** slot, void** target, void** ptr, long long n
   *idx32 = 0; *dense = 0;
   if (nruns <= 0) return cudaSuccess;
   cudaError_t e;
+  if (!*target) { *dense = 1; }
   int* flag = nullptr; int h = 1;
+  if (*target) {
   if ((e = cudaMalloc(&flag, 4)) != cudaSuccess) return e;
   cudaMemcpyAsync(flag, &h, 4, cudaMemcpyHostToDevice, st);
   k_is_iota<<<(unsigned)((nruns + 255) / 256), 256, 0, st>>>((const long long*)*target, nruns, flag);
@@ -99,6 +134,7 @@ cudaError_t exb_fx_pack_runs(void** slot, void** target, void** ptr, long long n
   cudaFree(flag);
   if (e != cudaSuccess) return e;
   if (h) { cudaFree(*target); *target = nullptr; *dense = 1; }
+  }
   if (max_index < 2147483647LL && nslots < 2147483647LL) {
     void** arr[3] = {slot, target, ptr};
     long long len[3] = {nslots, nruns, nruns + 1};
@@ -113,6 +149,40 @@ cudaError_t exb_fx_pack_runs(void** slot, void** target, void** ptr, long long n
     }
     *idx32 = 1;
   }
+  return cudaGetLastError();
+}
+
+cudaError_t exb_fx_spmv(const double* buf, const void* ptr, const void* slot, const void* other, const void* target, int idx32,
+                        long long nt, const double* v, double* y, int accumulate, int skipdiag, cudaStream_t st) {
+  if (nt <= 0) return cudaSuccess;
+  const unsigned grid = (unsigned)((nt + 255) / 256);
+#define EXB_SPMV(A, S, T) k_spmv<A, S, T><<<grid, 256, 0, st>>>(buf, (const T*)ptr, (const T*)slot, (const T*)other, (const T*)target, nt, v, y)
+  if (idx32) {
+    if (accumulate) { if (skipdiag) EXB_SPMV(true, true, int); else EXB_SPMV(true, false, int); }
+    else { if (skipdiag) EXB_SPMV(false, true, int); else EXB_SPMV(false, false, int); }
+  } else {
+    if (accumulate) { if (skipdiag) EXB_SPMV(true, true, long long); else EXB_SPMV(true, false, long long); }
+    else { if (skipdiag) EXB_SPMV(false, true, long long); else EXB_SPMV(false, false, long long); }
+  }
+#undef EXB_SPMV
+  return cudaGetLastError();
+}
+// out[l] = src[slot[l]] for the sorted positions l (the "other" index of each sorted COO entry)
+cudaError_t exb_fx_gather(const long long* src, const void* slot, int idx32, void* out, long long n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (idx32) k_gather<int><<<grid, 256, 0, st>>>(src, (const int*)slot, (int*)out, n);
+  else k_gather<long long><<<grid, 256, 0, st>>>(src, (const long long*)slot, (long long*)out, n);
+  return cudaGetLastError();
+}
+cudaError_t exb_fx_make_keys(const long long* major, const long long* minor, long long mult, long long* keys, long long n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  k_make_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(major, minor, mult, keys, n);
+  return cudaGetLastError();
+}
+cudaError_t exb_fx_decode_keys(const long long* keys, long long mult, long long* major, long long* minor, long long n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  k_decode_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, mult, major, minor, n);
   return cudaGetLastError();
 }
 

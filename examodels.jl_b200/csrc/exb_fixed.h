@@ -12,3 +12,8 @@ cudaError_t exb_fx_sum(const double* part, long long n, double* out, cudaStream_
 cudaError_t exb_fx_fill(long long* p, long long n, long long v, cudaStream_t st);
 cudaError_t exb_fx_sort_runs(const long long* keys, long long n, long long** slot_out, long long** target_out,
                              long long** ptr_out, long long* nruns_out, long long* nslots_out, cudaStream_t st);
+cudaError_t exb_fx_spmv(const double* buf, const void* ptr, const void* slot, const void* other, const void* target, int idx32,
+                        long long nt, const double* v, double* y, int accumulate, int skipdiag, cudaStream_t st);
+cudaError_t exb_fx_gather(const long long* src, const void* slot, int idx32, void* out, long long n, cudaStream_t st);
+cudaError_t exb_fx_make_keys(const long long* major, const long long* minor, long long mult, long long* keys, long long n, cudaStream_t st);
+cudaError_t exb_fx_decode_keys(const long long* keys, long long mult, long long* major, long long* minor, long long n, cudaStream_t st);

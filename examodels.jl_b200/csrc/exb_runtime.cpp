@@ -239,6 +239,12 @@ struct exb_model {
   // sorted (target, slot) lists: grad (ext:39-46) and constraint augmentation (ext:48-53)
   void *g_slot = nullptr, *g_target = nullptr, *g_ptr = nullptr; long long g_runs = 0; int g_i32 = 0, g_dense = 0;
   void *a_slot = nullptr, *a_target = nullptr, *a_ptr = nullptr; long long a_runs = 0; int a_i32 = 0, a_dense = 0;
+  // sorted structure for the matrix-free products (ext:56-175) and the duplicate-free COO (utils.jl:425-579)
+  struct Sorted { void *slot = nullptr, *other = nullptr, *target = nullptr, *ptr = nullptr; long long runs = 0, nslots = 0; int i32 = 0, dense = 0;
+                  long long *urows = nullptr, *ucols = nullptr; };
+  Sorted jrow, jcol, hrow, hcol, jcmp, hcmp;
+  bool prod_ready = false, cmp_ready = false;
+  double *d_jacbuf = nullptr, *d_hessbuf = nullptr;
   std::vector<long long> lo, hi;   // local point range per pattern
   // host shims
   cudaStream_t hstream = nullptr;
@@ -750,6 +756,182 @@ int exb_hess_structure64(exb_model* m, int64_t* rows, int64_t* cols, void* strea
 int exb_hess_structure32(exb_model* m, int32_t* rows, int32_t* cols, void* stream) {
   EXB_BEGIN EXB_GUARD(m); return structure(m, KN_HSTRUCT32, rows, cols, stream); EXB_END
 }
+
+}  // extern "C" (callbacks)
+
+// ---- sorted-structure features -----------------------------------------------------------------------
+namespace {
+
+int track(exb_model* m, void* p) { if (p) m->dev.push_back(p); return 0; }
+
+// keys (1-based, device, length n) -> Sorted list; `other_src` (optional): per-slot "other" index gathered into sorted order
+int build_sorted(exb_model* m, const long long* keys, long long n, long long max_index, const long long* other_src,
+                 bool keep_unique_keys, long long key_mult, exb_model::Sorted& S) {
+  long long *slot = nullptr, *target = nullptr, *ptr = nullptr;
+  cudaError_t e = exb_fx_sort_runs(keys, n, &slot, &target, &ptr, &S.runs, &S.nslots, 0);
+  if (e != cudaSuccess) return fail(EXB_ERR_CUDA, std::string("structure sort: ") + cudaGetErrorString(e));
+  if (keep_unique_keys && S.runs > 0) {   // decode the unique (col, row) keys into coordinate arrays
+    CU_TRY(m, cudaMalloc((void**)&S.urows, (size_t)S.runs * 8)); CU_TRY(m, cudaMalloc((void**)&S.ucols, (size_t)S.runs * 8));
+    CU_TRY(m, exb_fx_decode_keys(target, key_mult, S.ucols, S.urows, S.runs, 0));
+    CU_TRY(m, cudaStreamSynchronize(0));
+    track(m, S.urows); track(m, S.ucols);
+    cudaFree(target); target = nullptr;   // values land at position t: dense targets
+  }
+  S.slot = slot; S.target = target; S.ptr = ptr;
+  e = exb_fx_pack_runs(&S.slot, &S.target, &S.ptr, S.nslots, S.runs, std::max(max_index, n), &S.i32, &S.dense, 0);
+  if (e != cudaSuccess) return fail(EXB_ERR_CUDA, std::string("structure pack: ") + cudaGetErrorString(e));
+  if (other_src && S.nslots > 0) {
+    CU_TRY(m, cudaMalloc(&S.other, (size_t)S.nslots * (S.i32 ? 4 : 8)));
+    CU_TRY(m, exb_fx_gather(other_src, S.slot, S.i32, S.other, S.nslots, 0));
+    CU_TRY(m, cudaStreamSynchronize(0));
+  }
+  track(m, S.slot); track(m, S.target); track(m, S.ptr); track(m, S.other);
+  return EXB_OK;
+}
+
+int structure_raw(exb_model* m, int kn, void* rows, void* cols, cudaStream_t st);   // defined below
+
+int ensure_buffers(exb_model* m) {
+  const exb::Plan& pl = m->plan->pl;
+  if (!m->d_jacbuf) { int rc = dmalloc(m, (void**)&m->d_jacbuf, (size_t)pl.nnzj * 8); if (rc) return rc; }
+  if (!m->d_hessbuf) { int rc = dmalloc(m, (void**)&m->d_hessbuf, (size_t)pl.nnzh * 8); if (rc) return rc; }
+  return EXB_OK;
+}
+
+// which: 1 = products (row- and column-sorted), 2 = compressed (sorted by (col, row))
+int ensure_sorted(exb_model* m, int which) {
+  if (m->world != 1) return fail(EXB_ERR_ARG, "matrix-free products / compressed COO are not available on sharded handles");
+  if ((which == 1 && m->prod_ready) || (which == 2 && m->cmp_ready)) return EXB_OK;
+  const exb::Plan& pl = m->plan->pl;
+  int rc = ensure_buffers(m); if (rc) return rc;
+  for (int pass = 0; pass < 2; pass++) {   // 0: Jacobian, 1: Hessian
+    const long long n = pass == 0 ? pl.nnzj : pl.nnzh;
+    const long long nrow = pass == 0 ? pl.ncon : pl.m.nvar, ncol = pl.m.nvar;
+    if (n == 0) continue;
+    long long *rows = nullptr, *cols = nullptr, *keys = nullptr;
+    CU_TRY(m, cudaMalloc((void**)&rows, (size_t)n * 8));
+    cudaError_t e1 = cudaMalloc((void**)&cols, (size_t)n * 8), e2 = cudaMalloc((void**)&keys, (size_t)n * 8);
+    rc = (e1 != cudaSuccess || e2 != cudaSuccess) ? fail(EXB_ERR_CUDA, "out of device memory building the sorted structure") : EXB_OK;
+    if (!rc) rc = structure_raw(m, pass == 0 ? KN_JSTRUCT64 : KN_HSTRUCT64, rows, cols, 0);
+    if (!rc && cudaStreamSynchronize(0) != cudaSuccess) rc = fail(EXB_ERR_CUDA, "structure kernel failed");
+    if (!rc && which == 1) {
+      rc = build_sorted(m, rows, n, std::max(nrow, ncol), cols, false, 0, pass == 0 ? m->jrow : m->hrow);
+      if (!rc) rc = build_sorted(m, cols, n, std::max(nrow, ncol), rows, false, 0, pass == 0 ? m->jcol : m->hcol);
+    }
+    if (!rc && which == 2) {
+      const long long mult = nrow + 1;   // key = col * (nrow + 1) + row: sorted by (col, row) like the reference's ((j, i), k) tuples
+      if ((double)(ncol + 1) * (double)mult > 9.0e18) rc = fail(EXB_ERR_ARG, "model too large for 64-bit (col, row) keys");
+      if (!rc) {
+        cudaError_t e = exb_fx_make_keys(cols, rows, mult, keys, n, 0);
+        if (e != cudaSuccess) rc = fail(EXB_ERR_CUDA, cudaGetErrorString(e));
+      }
+      if (!rc) rc = build_sorted(m, keys, n, n, nullptr, true, mult, pass == 0 ? m->jcmp : m->hcmp);
+    }
+    cudaFree(rows); cudaFree(cols); cudaFree(keys);
+    if (rc) return rc;
+  }
+  if (which == 1) m->prod_ready = true; else m->cmp_ready = true;
+  return EXB_OK;
+}
+
+int spmv(exb_model* m, const exb_model::Sorted& S, const double* buf, const double* v, double* y, int acc, int skipdiag, cudaStream_t st) {
+  CU_TRY(m, exb_fx_spmv(buf, S.ptr, S.slot, S.other, S.target, S.i32, S.runs, v, y, acc, skipdiag, st));
+  if (S.runs > 0) { m->launches++; m->last_launches++; }
+  return EXB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int exb_jprod(exb_model* m, const double* x, const double* v, double* Jv, void* stream) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  int rc = ensure_sorted(m, 1); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = exb_jac(m, x, m->d_jacbuf, stream); if (rc) return rc;
+  CU_TRY(m, cudaMemsetAsync(Jv, 0, (size_t)m->plan->pl.ncon * 8, st));
+  return spmv(m, m->jrow, m->d_jacbuf, v, Jv, 0, 0, st);                 // kerspmv, ext:482-488
+  EXB_END
+}
+int exb_jtprod(exb_model* m, const double* x, const double* v, double* Jtv, void* stream) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  int rc = ensure_sorted(m, 1); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = exb_jac(m, x, m->d_jacbuf, stream); if (rc) return rc;
+  CU_TRY(m, cudaMemsetAsync(Jtv, 0, (size_t)m->plan->pl.m.nvar * 8, st));
+  return spmv(m, m->jcol, m->d_jacbuf, v, Jtv, 0, 0, st);                // kerspmv2, ext:489-495
+  EXB_END
+}
+int exb_hprod(exb_model* m, const double* x, const double* y, const double* v, double obj_weight, double* Hv, void* stream) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  int rc = ensure_sorted(m, 1); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = exb_hess(m, x, y, obj_weight, m->d_hessbuf, stream); if (rc) return rc;
+  CU_TRY(m, cudaMemsetAsync(Hv, 0, (size_t)m->plan->pl.m.nvar * 8, st));
+  rc = spmv(m, m->hrow, m->d_hessbuf, v, Hv, 0, 0, st); if (rc) return rc;   // lower triangle incl. diagonal (kersyspmv, ext:496-503)
+  return spmv(m, m->hcol, m->d_hessbuf, v, Hv, 1, 1, st);                    // transpose of the strict lower part (kersyspmv2, ext:504-511)
+  EXB_END
+}
+
+int exb_compressed_dims(exb_model* m, int64_t* nj, int64_t* nh) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  int rc = ensure_sorted(m, 2); if (rc) return rc;
+  if (nj) *nj = m->jcmp.runs;
+  if (nh) *nh = m->hcmp.runs;
+  return EXB_OK;
+  EXB_END
+}
+static int cmp_structure(exb_model* m, const exb_model::Sorted& S, int64_t* rows, int64_t* cols, void* stream) {
+  if (!rows || !cols) return fail(EXB_ERR_ARG, "null rows / cols");
+  if (S.runs > 0) {
+    CU_TRY(m, cudaMemcpyAsync(rows, S.urows, (size_t)S.runs * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    CU_TRY(m, cudaMemcpyAsync(cols, S.ucols, (size_t)S.runs * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  }
+  return EXB_OK;
+}
+int exb_jac_structure_compressed64(exb_model* m, int64_t* rows, int64_t* cols, void* stream) {
+  EXB_BEGIN EXB_GUARD(m); int rc = ensure_sorted(m, 2); if (rc) return rc; return cmp_structure(m, m->jcmp, rows, cols, stream); EXB_END
+}
+int exb_hess_structure_compressed64(exb_model* m, int64_t* rows, int64_t* cols, void* stream) {
+  EXB_BEGIN EXB_GUARD(m); int rc = ensure_sorted(m, 2); if (rc) return rc; return cmp_structure(m, m->hcmp, rows, cols, stream); EXB_END
+}
+int exb_jac_compressed(exb_model* m, const double* x, double* vals, void* stream) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  int rc = ensure_sorted(m, 2); if (rc) return rc;
+  rc = exb_jac(m, x, m->d_jacbuf, stream); if (rc) return rc;
+  const exb_model::Sorted& S = m->jcmp;
+  CU_TRY(m, exb_fx_compress(m->d_jacbuf, S.ptr, S.slot, S.target, S.i32, S.runs, vals, 0, (cudaStream_t)stream));   // ker_compress!, ext:1295-1303
+  if (S.runs > 0) { m->launches++; m->last_launches++; }
+  return EXB_OK;
+  EXB_END
+}
+int exb_hess_compressed(exb_model* m, const double* x, const double* y, double obj_weight, double* vals, void* stream) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  int rc = ensure_sorted(m, 2); if (rc) return rc;
+  rc = exb_hess(m, x, y, obj_weight, m->d_hessbuf, stream); if (rc) return rc;
+  const exb_model::Sorted& S = m->hcmp;
+  CU_TRY(m, exb_fx_compress(m->d_hessbuf, S.ptr, S.slot, S.target, S.i32, S.runs, vals, 0, (cudaStream_t)stream));
+  if (S.runs > 0) { m->launches++; m->last_launches++; }
+  return EXB_OK;
+  EXB_END
+}
+
+}  // extern "C"
+
+namespace {
+int structure_raw(exb_model* m, int kn, void* rows, void* cols, cudaStream_t st) {
+  ExbCall c{}; c.rows = rows; c.cols = cols;
+  return launch(m, kn, c, st);
+}
+}  // namespace
+
+extern "C" {
 
 // ---- host-buffer shims (the WrapperNLPModel role, src/utils.jl:16-267) -----------------------
 static int host_stream(exb_model* m) {

@@ -143,6 +143,25 @@ int exb_hess_structure32(exb_model* m, int32_t* rows, int32_t* cols, void* strea
 int exb_hess(exb_model* m, const double* x, const double* y, double obj_weight, double* vals,
              void* stream);
 
+/* ---- matrix-free products: jprod_nln! / jtprod_nln! / hprod! (src/nlp.jl:1882-1978; device form
+ * ext/ExaModelsKernelAbstractions.jl:353-511, `ExaModel(c; prod = true)`): the COO values are evaluated
+ * into a buffer owned by the handle and multiplied through row- / column-sorted copies of the structure
+ * (built on first use, ext:56-175).  Deterministic (no atomics).  Not available on sharded handles. */
+int exb_jprod(exb_model* m, const double* x, const double* v, double* Jv, void* stream);    /* Jv[ncon]  */
+int exb_jtprod(exb_model* m, const double* x, const double* v, double* Jtv, void* stream);  /* Jtv[nvar] */
+int exb_hprod(exb_model* m, const double* x, const double* y, const double* v, double obj_weight, double* Hv,
+              void* stream);                                                                 /* Hv[nvar]  */
+
+/* ---- duplicate-free COO: the CompressedNLPModel role (src/utils.jl:425-579 | ext:1290-1319) ----
+ * Unique (row, col) coordinates in the reference's order (sorted by (col, row)); values of duplicates are
+ * summed in ascending slot order.  Built on first use.  Not available on sharded handles. */
+int exb_compressed_dims(exb_model* m, int64_t* nnzj_unique, int64_t* nnzh_unique);
+int exb_jac_structure_compressed64(exb_model* m, int64_t* rows, int64_t* cols, void* stream);
+int exb_hess_structure_compressed64(exb_model* m, int64_t* rows, int64_t* cols, void* stream);
+int exb_jac_compressed(exb_model* m, const double* x, double* vals, void* stream);
+int exb_hess_compressed(exb_model* m, const double* x, const double* y, double obj_weight, double* vals,
+                        void* stream);
+
 /* ---- host-buffer shims: the WrapperNLPModel role (src/utils.jl:16-267) ------
  * Same callbacks with HOST pointers; H2D / D2H copies go through pinned staging owned
  * by the handle and are part of the call.  They synchronise before returning. */
