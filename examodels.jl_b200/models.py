@@ -240,3 +240,48 @@ def pattern_family(n=1_000_000, npat=32, seed=3):
         else:
             c.add_obj(body, d)
     return c
+
+
+# ---------------------------------------------------------------------------
+# small coverage models (parameters; every registered operator)
+# ---------------------------------------------------------------------------
+def parametric(n=200, seed=4):
+    """Parameters θ in objectives and constraints (add_par, src/nlp.jl:1177-1215; test/NLPTest/feature_test.jl:100-126)."""
+    rng = np.random.default_rng(seed)
+    c = ExaCore()
+    x = c.add_var(n, start=rng.uniform(0.5, 1.5, n))
+    th = c.add_par(n, value=rng.uniform(1.0, 2.0, n))
+    w = c.add_par(range(2, 5), value=[10.0, 20.0, 30.0])
+    c.add_obj(lambda i: th[i] * (x[i] - w[2]) ** 2 + exp(th[i] * x[i]), range(1, n + 1))
+    c.add_con(lambda i: th[i] * x[i] * x[i + 1] - w[3] * sin(x[i] / th[i + 1]), range(1, n))
+    c.add_con(lambda j: w[j] * x[1] + x[j] ** 3, range(2, 5))
+    return c
+
+
+def all_ops(n=64, part=0, seed=6):
+    """One constraint pattern per registered univariate operator (src/functionlist.jl:6-60) applied to an
+    argument inside its domain, and one per bivariate operator (:71-81) in its node-node, node-Real and
+    Real-node forms: the operator coverage matrix of test/ADTest/ADTest.jl."""
+    rng = np.random.default_rng(seed)
+    c = ExaCore()
+    x = c.add_var(n + 1, start=rng.uniform(0.3, 0.7, n + 1))
+    d = np.zeros(n, dtype=np.dtype([("i", "i8"), ("a", "f8")]))
+    d["i"] = np.arange(1, n + 1)
+    d["a"] = rng.uniform(1.1, 1.9, n)
+    big = {"acosh", "acoth"}                      # need |arg| > 1
+    # three parts keep each generated module small (compile time grows quickly with the pattern count)
+    uni = G.UNIVARIATE[:26] if part == 0 else G.UNIVARIATE[26:] if part == 1 else []
+    for name in uni:
+        f = (lambda z, nm=name: G._op1(nm, z))
+        if name in big:
+            c.add_con(lambda p, f=f: f(p.a + x[p.i] * x[p.i + 1]) * x[p.i], d)
+        else:
+            c.add_con(lambda p, f=f: f(x[p.i] * x[p.i + 1]) * x[p.i] + p.a, d)
+    for name in (G.BIVARIATE if part == 2 else []):
+        f = (lambda u, v, nm=name: G._op2(nm, u, v))
+        c.add_con(lambda p, f=f: f(x[p.i] + 0.5, x[p.i + 1] * p.a) * x[p.i], d)       # node, node
+        c.add_con(lambda p, f=f: f(x[p.i] * x[p.i + 1] + 0.5, p.a) * x[p.i + 1], d)   # node, Real
+        c.add_con(lambda p, f=f: f(p.a, x[p.i] * x[p.i + 1] + 0.5) * x[p.i + 1], d)   # Real, node
+    c.add_con(lambda p: (x[p.i] * p.a) ** 5 + G.pow_runtime(x[p.i + 1] + 1.0, p.i) / (1.0 + x[p.i] ** 2), d)  # Val and Int-data exponents
+    c.add_obj(lambda p: sqrt(1.0 + x[p.i] ** 2) * log(p.a + x[p.i + 1]), d)
+    return c

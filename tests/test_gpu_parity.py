@@ -27,6 +27,10 @@ def _models():
         "opf_300": lambda: M.ac_power(M.synthetic_power_data(300, 420, 70, seed=2)),
         "rocket_50": lambda: M.goddard_rocket(50),
         "family_1000": lambda: M.pattern_family(1000, 32),
+        "params": lambda: M.parametric(200),
+        "all_ops_0": lambda: M.all_ops(64, 0),
+        "all_ops_1": lambda: M.all_ops(64, 1),
+        "all_ops_2": lambda: M.all_ops(64, 2),
     }
 
 

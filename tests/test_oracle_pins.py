@@ -243,3 +243,22 @@ def test_threaded_oracle_matches_sequential():
     o.set_threads(4)
     assert np.array_equal(o.hess_coord(x, y, 1.0), a)
     assert np.array_equal(o.jac_coord(x), j)
+
+
+# ---- parameters: test/NLPTest/feature_test.jl:100-126 -------------------------------------------
+def _par_models():
+    c1 = E.ExaCore()
+    x = c1.add_var(5)
+    th = c1.add_par(range(2, 5), value=[10.0, 20.0, 30.0])
+    c1.add_con(lambda j: th[j] * x[1], range(2, 5))
+    c2 = E.ExaCore()
+    x2 = c2.add_var(12)
+    th2 = c2.add_par(3, range(2, 6), value=np.arange(1.0, 13.0).reshape(3, 4, order="F"))
+    c2.add_con(lambda d: th2[d[1], d[2]] * x2[1], [(1, 2), (2, 3), (3, 4)])
+    return c1, c2
+
+
+def test_add_par_values():
+    c1, c2 = _par_models()
+    np.testing.assert_allclose(Oracle.from_core(c1).cons(np.ones(5)), [10.0, 20.0, 30.0])
+    np.testing.assert_allclose(Oracle.from_core(c2).cons(np.ones(12)), [1.0, 5.0, 9.0])
