@@ -90,3 +90,28 @@ def test_callbacks_match_oracle(exa, torch_, name):
     assert abs(m.obj(x) - ref_obj) <= 1e-10 * max(abs(ref_obj), 1.0)
     st = m.stats()
     assert st["launches"] > 0
+
+
+def test_cuda_graph_full_eval_matches_eager(exa, torch_):
+    """obj + grad! + cons! + jac_coord! + hess_coord! captured in one CUDA graph give the eager results,
+    also after x / y are updated in place."""
+    from examodels_jl_b200 import models as M
+    torch = torch_
+    core = M.ac_power(M.synthetic_power_data(300, 420, 70, seed=2))
+    m = exa.ExaModel(core)
+    x, y = inputs(core)
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    od, g, c, j, h = m.new(1), m.new(m.nvar), m.new(m.ncon), m.new(m.nnzj), m.new(m.nnzh)
+    gr = m.capture_full_eval(dx, dy, od, g, c, j, h, obj_weight=0.5)
+    for seed in (3, 4):
+        x2, y2 = inputs(core, seed)
+        dx.copy_(torch.from_numpy(x2)); dy.copy_(torch.from_numpy(y2))
+        for t in (od, g, c, j, h):
+            t.fill_(float("nan"))
+        gr.replay()
+        torch.cuda.synchronize()
+        assert od.item() == m.obj(dx)
+        assert torch.equal(g, m.grad(dx, m.new(m.nvar)))
+        assert torch.equal(c, m.cons_nln(dx, m.new(m.ncon)))
+        assert torch.equal(j, m.jac_coord(dx, m.new(m.nnzj)))
+        assert torch.equal(h, m.hess_coord(dx, dy, m.new(m.nnzh), obj_weight=0.5))
