@@ -61,6 +61,7 @@ struct Plan {
   std::string error;
   // pattern lists per kernel (indices into pats), fixed at generation time
   std::vector<int> k_hess, k_jac, k_sgrad, k_cons, k_obj, k_aug;
+  bool idx32 = false;          // every index (variables, points, slots) fits 31 bits: address arithmetic in 32 bits
   int block = 128, minb = 16;  // launch shape of the generated kernels (tuning knobs: EXB_TUNE_BLOCK / EXB_TUNE_MINB)
 };
 
@@ -226,10 +227,10 @@ struct Gen {
       case T_CONST_F: { double v; std::memcpy(&v, &q.payload, 8); r.lit = true; r.x = K(v); r.rs = dlit(v); } break;
       case T_DATA_SELF: r.rs = B.tmp("long long", "pa.start + kg"); break;
       case T_DATA_FIELD:
-        if (r.is_int) r.rs = B.tmp("long long", "exb_ld_i(pa, " + std::to_string(q.a) + ", kg)");
-        else r.rs = B.tmp("double", "exb_ld_f(pa, " + std::to_string(q.a) + ", kg)");
+        if (r.is_int) r.rs = B.tmp("long long", "exb_ld_i(pa, " + std::to_string(q.a) + ", EXB_IX(kg))");
+        else r.rs = B.tmp("double", "exb_ld_f(pa, " + std::to_string(q.a) + ", EXB_IX(kg))");
         break;
-      case T_PAR: { NV& ix = real((int)q.a); r.rs = B.tmp("double", "__ldg(th + (" + ix.rs + " - 1))"); } break;  // graph.jl:310-311
+      case T_PAR: { NV& ix = real((int)q.a); r.rs = B.tmp("double", "__ldg(th + EXB_IX(" + ix.rs + " - 1))"); } break;  // graph.jl:310-311
       case T_OP1: {
         NV& a = real((int)q.a);
         int op = (int)q.payload;
@@ -279,7 +280,7 @@ struct Gen {
     if (in.kind == K_VAR) {
       NV& ix = real((int)q.a);
       r.idx = ix.rs;
-      r.x = Sym(B.tmp("double", "__ldg(x + (" + ix.rs + " - 1))"));
+      r.x = Sym(B.tmp("double", "__ldg(x + EXB_IX(" + ix.rs + " - 1))"));
       return r;
     }
     if (q.tag == T_OP1) {
@@ -382,7 +383,7 @@ struct Gen {
     if (adj.c && adj.v == 0) return;
     Ex v;
     if (ir_equal(p.ir, (int)N(a).a, (int)N(b).a)) v = B.mul(K(2), adj);     // i == j structurally
-    else v = Sym(B.tmp("double", "exb_twice_if_eq(" + nv[(size_t)a].idx + ", " + nv[(size_t)b].idx + ", " + adj.s + ")"));
+    else v = Sym(B.tmp("double", "exb_twice_if_eq(EXB_IX(" + nv[(size_t)a].idx + "), EXB_IX(" + nv[(size_t)b].idx + "), " + adj.s + ")"));
     slot[(size_t)j] = B.add(slot[(size_t)j], v);
   }
 
@@ -675,6 +676,12 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes) {
     if (p.ir.kind == KIND_AUG) pl.k_aug.push_back((int)k);
   }
   // module source
+  {
+    i64 mx = std::max(std::max(pl.m.nvar, pl.m.npar), std::max(std::max(pl.nnzh, pl.nnzj), std::max(pl.nnzg, pl.ncon)));
+    for (auto& p : pl.pats) mx = std::max(mx, p.ir.nitr + (p.ir.range_start > 0 ? p.ir.range_start : 0));
+    // measured on LV N=1e7 (scripts/ab.py): 32-bit address chains are NOT faster (0.166 vs 0.162 ms), so this stays opt-in
+    pl.idx32 = mx < 2000000000LL && getenv("EXB_TUNE_IDX32") != nullptr;
+  }
   if (const char* e = getenv("EXB_TUNE_BLOCK")) { int b = atoi(e); if (b == 64 || b == 128 || b == 256 || b == 512) pl.block = b; }
   if (const char* e = getenv("EXB_TUNE_MINB")) { int b = atoi(e); if (b >= 1 && b <= 32) pl.minb = b; }
   std::ostringstream o;

@@ -167,6 +167,7 @@ int make_plan(const void* ir, size_t bytes, exb_plan** out) {
   for (int mb : minbs) {
     Variant v; v.minb = mb;
     v.source = "#define EXB_BLOCK " + std::to_string(p->pl.block) + "\n#define EXB_MINB " + std::to_string(mb) + "\n" +
+               (p->pl.idx32 ? "#define EXB_IDX32 1\n" : "") +
                ((int)p->pl.pats.size() <= exb::EXB_CPAT_MAX && !p->pl.pats.empty() ? "#define EXB_NPAT " + std::to_string(p->pl.pats.size()) + "\n" : std::string()) +
                std::string(exb_device_header_text) + "\n" + p->pl.source;
     snprintf(buf, sizeof buf, "%016llx", (unsigned long long)fnv1a(NVCC_FLAGS_CLEAN, fnv1a(v.source)));
