@@ -318,7 +318,11 @@ int tune(exb_model* m, int kn, const ExbCall& c, cudaStream_t st) {
 int launch(exb_model* m, int kn, const ExbCall& c, cudaStream_t st) {
   Launch& L = m->k[kn];
   if (!L.fn || L.nblocks == 0) return EXB_OK;
-  if (L.best < 0) return tune(m, kn, c, st);
+  if (L.best < 0) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+    if (cs == cudaStreamCaptureStatusNone) return tune(m, kn, c, st);   // timing needs a stream sync: not while capturing a graph
+  }
   return launch_fn(m, kn, L.fn, c, st);
 }
 
