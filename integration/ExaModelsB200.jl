@@ -98,7 +98,7 @@ function emit_pattern!(words, bufs, p, kind, base_index)
 end
 
 function ExaModels.build_extension(c::ExaCore{T,VT,B}; prod = false, kwargs...) where {T,VT,B<:B200Backend}
-    prod && error("prod = true (jprod/jtprod/hprod) is not provided by the B200 backend yet")
+    # `prod` needs no work here: the sorted structure behind exb_jprod / exb_jtprod / exb_hprod is built on first use
     # patterns in ADD ORDER: both lists are stored newest-first (src/nlp.jl:536); the shared nnzh
     # counter (f.o2) orders objectives against constraints
     pats = Any[]
@@ -149,6 +149,16 @@ end
 function NLPModels.hess_coord!(m::M, x::AbstractVector, vals::AbstractVector; obj_weight = one(eltype(x)))   # nlp.jl:1906-1915
     check(ccall((:exb_hess, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Cdouble, CuPtr{Float64}, Ptr{Cvoid}),
         m.ext.handle, x, CU_NULL, obj_weight, vals, st())); vals
+end
+function NLPModels.jprod_nln!(m::M, x::AbstractVector, v::AbstractVector, Jv::AbstractVector)      # nlp.jl:1882-1897 | ext:353-420
+    check(ccall((:exb_jprod, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}), m.ext.handle, x, v, Jv, st())); Jv
+end
+function NLPModels.jtprod_nln!(m::M, x::AbstractVector, v::AbstractVector, Jtv::AbstractVector)    # nlp.jl:1899-1904 | ext:421-440
+    check(ccall((:exb_jtprod, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}), m.ext.handle, x, v, Jtv, st())); Jtv
+end
+function NLPModels.hprod!(m::M, x::AbstractVector, y::AbstractVector, v::AbstractVector, Hv::AbstractVector; obj_weight = one(eltype(x)))   # nlp.jl:1942-1978 | ext:441-481
+    check(ccall((:exb_hprod, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cdouble, CuPtr{Float64}, Ptr{Cvoid}),
+        m.ext.handle, x, y, v, obj_weight, Hv, st())); Hv
 end
 for (name, sym64, sym32) in ((:jac_structure!, :exb_jac_structure64, :exb_jac_structure32),
                              (:hess_structure!, :exb_hess_structure64, :exb_hess_structure32))
