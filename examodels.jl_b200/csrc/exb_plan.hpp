@@ -529,7 +529,9 @@ inline int body_weight(const Body& B) {
   return w;
 }
 inline int ppt_for(int weight, int ns) {
-  int p = weight <= 60 ? 4 : weight <= 150 ? 2 : 1;
+  static const int w4 = getenv("EXB_TUNE_PPT_W4") ? atoi(getenv("EXB_TUNE_PPT_W4")) : 60;    // dev knobs
+  static const int w2 = getenv("EXB_TUNE_PPT_W2") ? atoi(getenv("EXB_TUNE_PPT_W2")) : 150;
+  int p = weight <= w4 ? 4 : weight <= w2 ? 2 : 1;
   while (p > 1 && p * ns > 16) p >>= 1;   // slots live in registers
   return p;
 }

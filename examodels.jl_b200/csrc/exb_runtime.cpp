@@ -746,6 +746,9 @@ int exb_hess(exb_model* m, const double* x, const double* y, double obj_weight, 
 
 static int structure(exb_model* m, int kn, void* rows, void* cols, void* stream) {
   ExbCall c{}; c.rows = rows; c.cols = cols;
+  const exb::Plan& pl = m->plan->pl;
+  const long long n = (kn == KN_JSTRUCT64 || kn == KN_JSTRUCT32) ? pl.nnzj : pl.nnzh;
+  if (n == 0) return EXB_OK;   // nothing to write (e.g. a model without constraints): null outputs are fine
   if (!rows || !cols) return fail(EXB_ERR_ARG, "null rows / cols");
   return launch(m, kn, c, (cudaStream_t)stream);
 }

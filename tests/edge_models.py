@@ -1,0 +1,77 @@
+"""Edge-case models shared by the CPU (oracle) and GPU (parity) tests."""
+import numpy as np
+
+import examodels_jl_b200 as E
+from examodels_jl_b200.graph import cos, exp, sin
+
+
+def only_objective():
+    c = E.ExaCore(); x = c.add_var(9, start=np.linspace(0.1, 0.9, 9))
+    c.add_obj(lambda i: (x[i] - x[i + 1]) ** 2 * exp(x[i]), range(1, 9))
+    return c
+
+
+def only_constraints():
+    c = E.ExaCore(); x = c.add_var(9, start=np.linspace(0.1, 0.9, 9))
+    c.add_con(lambda i: sin(x[i]) * x[i + 1], range(1, 9))
+    return c
+
+
+def empty_patterns():
+    """Zero-length iterators mixed with non-empty ones (a range of length 0 and an empty array)."""
+    c = E.ExaCore(); x = c.add_var(6, start=np.linspace(0.2, 0.7, 6))
+    c.add_con(lambda i: x[i] ** 3, range(1, 1))
+    c.add_obj(lambda i: x[i] * x[i + 1], range(1, 6))
+    c.add_con(lambda d: d.a * x[d.i] ** 2, np.zeros(0, dtype=np.dtype([("i", "i8"), ("a", "f8")])))
+    c.add_con(lambda i: x[i] * exp(x[i + 1]), range(2, 5))
+    c.add_obj(lambda i: x[i] ** 2, range(3, 3))
+    return c
+
+
+def single_points_and_constants():
+    """One-row patterns, a fixed-index variable shared by every point, a constant body and Null rows."""
+    c = E.ExaCore(); x = c.add_var(7, start=np.linspace(0.3, 0.9, 7)); t = c.add_var(1, start=0.5)
+    c.add_obj(x[7] * t[1])
+    c.add_con(x[1] - 1.0)
+    c.add_con(lambda i: t[1] * (x[i] + x[i + 1]) ** 2, range(1, 7))
+    c.add_con(lambda i: 3.5, range(1, 4))
+    g = c.add_con(dims=(4,))
+    c.add_con_aug(lambda i: g[i] + x[i] * x[i + 3], range(1, 5))
+    return c
+
+
+def self_loops():
+    """AC-OPF-like cross terms whose two variable indices coincide numerically for some points: the slots stay
+    distinct (dedupe is symbolic) and the cross slot gets 2*adj (src/hessian.jl:261-266)."""
+    rng = np.random.default_rng(8)
+    n = 40
+    d = np.zeros(n, dtype=np.dtype([("f", "i8"), ("t", "i8"), ("g", "f8")]))
+    d["f"] = rng.integers(1, 11, n); d["t"] = rng.integers(1, 11, n)
+    d["t"][::3] = d["f"][::3]                      # every third branch is a self loop
+    d["g"] = rng.uniform(0.5, 2.0, n)
+    c = E.ExaCore(); v = c.add_var(10, start=rng.uniform(0.9, 1.1, 10)); a = c.add_var(10, start=rng.uniform(-0.2, 0.2, 10))
+    c.add_con(lambda b: b.g * (v[b.f] * v[b.t] * cos(a[b.f] - a[b.t])), d)
+    c.add_obj(lambda b: (v[b.f] - v[b.t]) ** 2 + v[b.f] * v[b.t], d)
+    return c
+
+
+def field_types():
+    """int32 / float32 / int64 / float64 fields, an Int field used as a VALUE beyond 2^31, and a nested struct."""
+    rng = np.random.default_rng(9)
+    n = 33
+    inner = np.dtype([("k", "i4"), ("w", "f4")])
+    dt = np.dtype([("i", "i8"), ("big", "i8"), ("p", inner), ("a", "f8")])
+    d = np.zeros(n, dtype=dt)
+    d["i"] = np.arange(1, n + 1)
+    d["big"] = 3_000_000_000 + np.arange(n)
+    d["p"]["k"] = rng.integers(1, n + 1, n)
+    d["p"]["w"] = rng.uniform(0.5, 1.5, n).astype(np.float32)
+    d["a"] = rng.uniform(0.5, 1.5, n)
+    c = E.ExaCore(); x = c.add_var(n + 1, start=rng.uniform(0.5, 1.0, n + 1))
+    c.add_con(lambda q: q.p.w * x[q.i] * x[q.p.k] + q.big * 1e-9 * x[q.i + 1] ** 2, d)
+    c.add_obj(lambda q: q.a * sin(x[q.p.k]) + q.i * x[q.i], d)
+    return c
+
+
+EDGE = {"only_objective": only_objective, "only_constraints": only_constraints, "empty_patterns": empty_patterns,
+        "single_points_and_constants": single_points_and_constants, "self_loops": self_loops, "field_types": field_types}
