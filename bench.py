@@ -103,16 +103,16 @@ def run_reference(args):
     from examodels_jl_b200 import models as M
     OA.build()
     threads = OA.Oracle.max_threads()
-    # bounded sample of the LV N=10^7 workload: calibrate, then size a step to ~1 s
+    # bounded sample of the LV N=10^7 workload: calibrate, then size a step so that the W + K steps take ~2 minutes
     rate, _ = cpu_hess_rate(200_000, threads)
-    n = int(min(N_PER_GPU, max(200_000, rate / 9.0 * 1.0)))
+    per_step_s = min(1.0, 120.0 / (args.steps + args.warmup))
+    n = int(min(N_PER_GPU, max(20_000, rate / 9.0 * per_step_s)))
     core = M.luksan_vlcek(n)
     ora = OA.Oracle.from_core(core)
     ora.set_threads(threads)
     x, y = lv_inputs(ora.nvar, ora.ncon)
     out = np.zeros(ora.nnzh)
-    # the CPU arm's step is ~1 s: cap the counts so that the run ends within a few minutes whatever K / W were asked
-    steps, warmup = min(args.steps, 30), min(args.warmup, 3)
+    steps, warmup = args.steps, args.warmup
     for _ in range(warmup):
         ora.hess_coord(x, y, 1.0, out)
     t0 = time.perf_counter()
