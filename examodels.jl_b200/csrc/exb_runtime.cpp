@@ -469,9 +469,21 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
     const long long csz = 1LL << shift;
     std::vector<ExbChunk> chunks;
     if (lst.size() <= 4) {   // few patterns: interleave them so shared parts of x are streamed from HBM once
-      for (long long r = 0; r * csz < maxnb; r++)
-        for (size_t q = 0; q < lst.size(); q++)
-          if (r * csz < nb[q]) chunks.push_back(ExbChunk{(int)q, (int)(r * csz)});
+      // proportional merge: always take the pattern that is least far through its own range, so patterns with
+      // different points-per-block still walk x side by side
+      std::vector<long long> nch(lst.size()), at(lst.size(), 0);
+      long long left = 0;
+      for (size_t q = 0; q < lst.size(); q++) { nch[q] = (nb[q] + csz - 1) / csz; left += nch[q]; }
+      while (left-- > 0) {
+        size_t best = 0; double bf = 2.0;
+        for (size_t q = 0; q < lst.size(); q++) {
+          if (at[q] >= nch[q]) continue;
+          const double f = ((double)at[q] + 0.5) / (double)nch[q];
+          if (f < bf) { bf = f; best = q; }
+        }
+        chunks.push_back(ExbChunk{(int)best, (int)(at[best] * csz)});
+        at[best]++;
+      }
     } else {                 // many patterns: one after the other, so an SM runs one pattern's code at a time
       for (size_t q = 0; q < lst.size(); q++)   // (interleaving 32 patterns thrashes the instruction cache: 3x slower)
         for (long long r = 0; r * csz < nb[q]; r++) chunks.push_back(ExbChunk{(int)q, (int)(r * csz)});
