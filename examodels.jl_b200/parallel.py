@@ -73,13 +73,20 @@ class ShardedExaModel:
     def _replicate(self, vals, which):
         if not self.gather or self.world == 1:
             return vals
-        works = []
+        jobs = []
         for r in range(self.world):
             src = self.dist.get_global_rank(self.group, r) if self.group is not None else r
-            for lo, hi in self.slices(which, r):
-                works.append(self.dist.broadcast(vals[lo:hi], src=src, group=self.group, async_op=True))
-        for w in works:
-            w.wait()
+            jobs += [(vals[lo:hi], src) for lo, hi in self.slices(which, r)]
+        try:      # one NCCL group launch for all (pattern, owner) broadcasts instead of one launch each
+            from torch.distributed.distributed_c10d import _coalescing_manager
+            with _coalescing_manager(group=self.group, device=vals.device, async_ops=True) as cm:
+                for t, src in jobs:
+                    self.dist.broadcast(t, src=src, group=self.group)
+            cm.wait()
+        except Exception:
+            works = [self.dist.broadcast(t, src=src, group=self.group, async_op=True) for t, src in jobs]
+            for w in works:
+                w.wait()
         return vals
 
     def jac_coord(self, x, vals):

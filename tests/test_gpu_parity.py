@@ -115,3 +115,31 @@ def test_cuda_graph_full_eval_matches_eager(exa, torch_):
         assert torch.equal(c, m.cons_nln(dx, m.new(m.ncon)))
         assert torch.equal(j, m.jac_coord(dx, m.new(m.nnzj)))
         assert torch.equal(h, m.hess_coord(dx, dy, m.new(m.nnzh), obj_weight=0.5))
+
+
+def test_plain_c_host_through_the_abi(exa, tmp_path):
+    """The boundary is usable without Python: a C program (tests/c_host_example.c) linked against libexa_b200.so
+    builds LV N=5000 from an IR file and evaluates hess_coord! / obj with host buffers."""
+    import os
+    import subprocess
+    from examodels_jl_b200 import models as M
+    from oracle.oracle_api import Oracle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "examodels.jl_b200", "csrc")
+    exe = str(tmp_path / "c_host_example")
+    subprocess.check_call(["gcc", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "c_host_example.c"),
+                           "-o", exe, "-L", csrc, "-lexa_b200", "-Wl,-rpath," + csrc])
+    core = M.luksan_vlcek(5000)
+    ir, bufs = core.to_ir()
+    assert not bufs
+    x, y = inputs(core)
+    (tmp_path / "m.ir").write_bytes(ir); x.tofile(tmp_path / "x.bin"); y.tofile(tmp_path / "y.bin")
+    out = subprocess.check_output([exe, str(tmp_path / "m.ir"), str(tmp_path / "x.bin"), str(tmp_path / "y.bin"), "0.5"], text=True)
+    nnzh, s, w, obj = out.split()
+    ora = Oracle.from_core(core)
+    h = ora.hess_coord(x, y, 0.5)
+    wts = (np.arange(h.size) % 97) + 1.0
+    assert int(nnzh) == ora.nnzh
+    scale = np.abs(h).sum()
+    assert abs(float(s) - h.sum()) <= 1e-10 * scale and abs(float(w) - (h * wts).sum()) <= 1e-10 * (np.abs(h) * wts).sum()
+    assert abs(float(obj) - ora.obj(x)) <= 1e-10 * abs(ora.obj(x))
