@@ -38,7 +38,7 @@ exb_obj_async exb_grad exb_cons exb_jac_structure64 exb_jac_structure32 exb_jac 
 exb_hess_structure32 exb_hess exb_host_obj exb_host_grad exb_host_cons exb_host_jac exb_host_hess
 exb_host_jac_structure64 exb_host_hess_structure64 exb_shard exb_stats exb_last_error exb_abi_version
 exb_jprod exb_jtprod exb_hprod exb_compressed_dims exb_jac_structure_compressed64 exb_hess_structure_compressed64
-exb_jac_compressed exb_hess_compressed""".split()
+exb_jac_compressed exb_hess_compressed exb_set_timing exb_timings""".split()
 
 
 class ExbError(RuntimeError):
@@ -331,6 +331,16 @@ class ExaModel:
         o = np.zeros(6, dtype=np.int64)
         _check(lib().exb_shard(self.h, k, _np_ptr(o)))
         return dict(zip(("lo", "hi", "jac_lo", "jac_hi", "hess_lo", "hess_hi"), (int(v) for v in o)))
+
+    def set_timing(self, on=True):
+        """Per-callback device timing (the `TimedNLPModel` role, src/utils.jl:271-408)."""
+        _check(lib().exb_set_timing(self.h, 1 if on else 0))
+
+    def timings(self, reset=False):
+        ms, calls = np.zeros(8), np.zeros(8, dtype=np.int64)
+        _check(lib().exb_timings(self.h, _np_ptr(ms), _np_ptr(calls), 1 if reset else 0))
+        names = ("obj", "grad", "cons", "jac", "hess", "jprod", "jtprod", "hprod")
+        return {n: {"ms": float(m), "calls": int(c)} for n, m, c in zip(names, ms, calls)}
 
     def stats(self):
         o = np.zeros(4, dtype=np.int64)

@@ -252,6 +252,12 @@ struct exb_model {
   double *hx = nullptr, *hy = nullptr, *hout = nullptr; size_t hx_n = 0, hy_n = 0, hout_n = 0;
   double *dx = nullptr, *dy = nullptr, *dout = nullptr; size_t dx_n = 0, dy_n = 0, dout_n = 0;
   long long launches = 0, last_launches = 0;
+  // per-callback device timing (the TimedNLPModel role, src/utils.jl:271-408): CUDA events around each callback
+  bool timing = false;
+  struct Pending { int cb; cudaEvent_t e0, e1; };
+  std::vector<Pending> pending;
+  double cb_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long cb_calls[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -563,6 +569,7 @@ void free_model(exb_model* m) {
   if (m->dy) cudaFree(m->dy);
   if (m->dout) cudaFree(m->dout);
   if (m->hstream) cudaStreamDestroy(m->hstream);
+  for (auto& p : m->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
   delete m->plan;
   delete m;
 }
@@ -587,6 +594,20 @@ int ensure_host(exb_model* m, double** h, size_t* hn, double** d, size_t* dn, si
 
 }  // namespace
 
+enum { CB_OBJ = 0, CB_GRAD, CB_CONS, CB_JAC, CB_HESS, CB_JPROD, CB_JTPROD, CB_HPROD };
+struct TimeScope {   // records an event pair on the caller's stream when timing is on (never synchronises)
+  exb_model* m; int cb; cudaStream_t st; cudaEvent_t e0 = nullptr;
+  TimeScope(exb_model* m_, int cb_, void* st_) : m(m_), cb(cb_), st((cudaStream_t)st_) {
+    if (m && m->timing && cudaEventCreate(&e0) == cudaSuccess) cudaEventRecord(e0, st); else e0 = nullptr;
+  }
+  ~TimeScope() {
+    if (!e0) return;
+    cudaEvent_t e1 = nullptr;
+    if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); return; }
+    cudaEventRecord(e1, st);
+    m->pending.push_back({cb, e0, e1});
+  }
+};
 #define EXB_GUARD(m) if (!(m) || !(m)->plan) return fail(EXB_ERR_HANDLE, "invalid handle"); DeviceGuard dg_((m)->device); (m)->last_launches = 0
 #define EXB_BEGIN try {
 #define EXB_END } catch (const std::exception& e) { return fail(EXB_ERR_INTERNAL, e.what()); } catch (...) { return fail(EXB_ERR_INTERNAL, "unknown exception"); }
@@ -691,6 +712,7 @@ int exb_set_params(exb_model* m, const double* theta, void* stream) {
 int exb_obj_async(exb_model* m, const double* x, double* out_dev, void* stream) {
   EXB_BEGIN
   EXB_GUARD(m);
+  TimeScope ts_(m, CB_OBJ, stream);
   cudaStream_t st = (cudaStream_t)stream;
   ExbCall c{}; c.x = x; c.th = m->d_theta; c.out2 = m->d_objpart;
   int rc = launch(m, KN_OBJ, c, st); if (rc) return rc;
@@ -713,6 +735,7 @@ int exb_obj(exb_model* m, const double* x, double* out_host, void* stream) {
 int exb_grad(exb_model* m, const double* x, double* g, void* stream) {
   EXB_BEGIN
   EXB_GUARD(m);
+  TimeScope ts_(m, CB_GRAD, stream);
   cudaStream_t st = (cudaStream_t)stream;
   const exb::Plan& pl = m->plan->pl;
   ExbCall c{}; c.x = x; c.th = m->d_theta; c.out = m->d_gradbuf;
@@ -728,6 +751,7 @@ int exb_grad(exb_model* m, const double* x, double* g, void* stream) {
 int exb_cons(exb_model* m, const double* x, double* cvals, void* stream) {
   EXB_BEGIN
   EXB_GUARD(m);
+  TimeScope ts_(m, CB_CONS, stream);
   cudaStream_t st = (cudaStream_t)stream;
   const exb::Plan& pl = m->plan->pl;
   // a sharded handle owns only part of the base rows: zero the rest so that ranks can be summed
@@ -743,6 +767,7 @@ int exb_cons(exb_model* m, const double* x, double* cvals, void* stream) {
 int exb_jac(exb_model* m, const double* x, double* vals, void* stream) {
   EXB_BEGIN
   EXB_GUARD(m);
+  TimeScope ts_(m, CB_JAC, stream);
   ExbCall c{}; c.x = x; c.th = m->d_theta; c.out = vals;
   return launch(m, KN_JAC, c, (cudaStream_t)stream);
   EXB_END
@@ -751,6 +776,7 @@ int exb_jac(exb_model* m, const double* x, double* vals, void* stream) {
 int exb_hess(exb_model* m, const double* x, const double* y, double obj_weight, double* vals, void* stream) {
   EXB_BEGIN
   EXB_GUARD(m);
+  TimeScope ts_(m, CB_HESS, stream);
   ExbCall c{}; c.x = x; c.y = y; c.th = m->d_theta; c.sigma = obj_weight; c.out = vals;
   return launch(m, KN_HESS, c, (cudaStream_t)stream);
   EXB_END
@@ -867,6 +893,7 @@ extern "C" {
 int exb_jprod(exb_model* m, const double* x, const double* v, double* Jv, void* stream) {
   EXB_BEGIN
   EXB_GUARD(m);
+  TimeScope ts_(m, CB_JPROD, stream);
   int rc = ensure_sorted(m, 1); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   rc = exb_jac(m, x, m->d_jacbuf, stream); if (rc) return rc;
@@ -877,6 +904,7 @@ int exb_jprod(exb_model* m, const double* x, const double* v, double* Jv, void* 
 int exb_jtprod(exb_model* m, const double* x, const double* v, double* Jtv, void* stream) {
   EXB_BEGIN
   EXB_GUARD(m);
+  TimeScope ts_(m, CB_JTPROD, stream);
   int rc = ensure_sorted(m, 1); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   rc = exb_jac(m, x, m->d_jacbuf, stream); if (rc) return rc;
@@ -887,6 +915,7 @@ int exb_jtprod(exb_model* m, const double* x, const double* v, double* Jtv, void
 int exb_hprod(exb_model* m, const double* x, const double* y, const double* v, double obj_weight, double* Hv, void* stream) {
   EXB_BEGIN
   EXB_GUARD(m);
+  TimeScope ts_(m, CB_HPROD, stream);
   int rc = ensure_sorted(m, 1); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   rc = exb_hess(m, x, y, obj_weight, m->d_hessbuf, stream); if (rc) return rc;
@@ -1078,6 +1107,32 @@ int exb_shard(const exb_model* m, int k, int64_t* o) {
   o[2] = in_jac ? p.o1 + o[0] * p.o1step : 0; o[3] = in_jac ? p.o1 + o[1] * p.o1step : 0;
   o[4] = p.o2 + o[0] * p.o2step; o[5] = p.o2 + o[1] * p.o2step;
   return EXB_OK;
+}
+int exb_set_timing(exb_model* m, int on) {
+  if (!m) return fail(EXB_ERR_HANDLE, "invalid handle");
+  m->timing = on != 0;
+  return EXB_OK;
+}
+// ms8 / calls8: accumulated device milliseconds and call counts for obj grad cons jac hess jprod jtprod hprod
+int exb_timings(exb_model* m, double* ms8, int64_t* calls8, int reset) {
+  EXB_BEGIN
+  if (!m) return fail(EXB_ERR_HANDLE, "invalid handle");
+  DeviceGuard dg(m->device);
+  for (auto& p : m->pending) {
+    float t = 0;
+    if (cudaEventSynchronize(p.e1) == cudaSuccess && cudaEventElapsedTime(&t, p.e0, p.e1) == cudaSuccess) {
+      m->cb_ms[p.cb] += t; m->cb_calls[p.cb]++;
+    } else cudaGetLastError();
+    cudaEventDestroy(p.e0); cudaEventDestroy(p.e1);
+  }
+  m->pending.clear();
+  for (int k = 0; k < 8; k++) {
+    if (ms8) ms8[k] = m->cb_ms[k];
+    if (calls8) calls8[k] = m->cb_calls[k];
+    if (reset) { m->cb_ms[k] = 0; m->cb_calls[k] = 0; }
+  }
+  return EXB_OK;
+  EXB_END
 }
 int exb_stats(const exb_model* m, int64_t* o) {
   if (!m || !o) return fail(EXB_ERR_HANDLE, "invalid handle");

@@ -181,6 +181,12 @@ int exb_shard(const exb_model* m, int k, int64_t* out6);
  * out[2] = device bytes owned by the handle, out[3] = 1 if module came from cache */
 int exb_stats(const exb_model* m, int64_t* out4);
 
+/* Per-callback device timing: the TimedNLPModel role (src/utils.jl:271-408).  When on, every value callback is
+ * bracketed by CUDA events on the caller's stream (no synchronisation); exb_timings synchronises on them and returns
+ * the accumulated milliseconds and call counts for obj grad cons jac hess jprod jtprod hprod (8 entries each). */
+int exb_set_timing(exb_model* m, int on);
+int exb_timings(exb_model* m, double* ms8, int64_t* calls8, int reset);
+
 const char* exb_last_error(void);
 int exb_abi_version(void);
 

@@ -143,3 +143,26 @@ def test_plain_c_host_through_the_abi(exa, tmp_path):
     scale = np.abs(h).sum()
     assert abs(float(s) - h.sum()) <= 1e-10 * scale and abs(float(w) - (h * wts).sum()) <= 1e-10 * (np.abs(h) * wts).sum()
     assert abs(float(obj) - ora.obj(x)) <= 1e-10 * abs(ora.obj(x))
+
+
+def test_per_callback_timing(exa, torch_):
+    """The TimedNLPModel role: CUDA-event timing per callback, call counts, reset."""
+    from examodels_jl_b200 import models as M
+    torch = torch_
+    core = M.luksan_vlcek(200_000)
+    m = exa.ExaModel(core)
+    x, y = inputs(core)
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    h, j, g, c = m.new(m.nnzh), m.new(m.nnzj), m.new(m.nvar), m.new(m.ncon)
+    m.hess_coord(dx, dy, h); m.jac_coord(dx, j); m.grad(dx, g); m.cons_nln(dx, c); m.obj(dx)   # tuning calls, untimed
+    m.set_timing(True)
+    for _ in range(3):
+        m.hess_coord(dx, dy, h); m.jac_coord(dx, j)
+    m.grad(dx, g); m.cons_nln(dx, c); m.obj(dx)
+    t = m.timings(reset=True)
+    assert [t[k]["calls"] for k in ("obj", "grad", "cons", "jac", "hess")] == [1, 1, 1, 3, 3]
+    assert all(t[k]["ms"] > 0 for k in ("obj", "grad", "cons", "jac", "hess")) and t["hprod"]["calls"] == 0
+    assert t["hess"]["ms"] < 50.0
+    m.set_timing(False)
+    m.hess_coord(dx, dy, h)
+    assert m.timings()["hess"]["calls"] == 0
