@@ -180,7 +180,9 @@ def main():
 
     sampler = ClockSampler(local)
     if rank == 0:
+        import atexit
         sampler.start()
+        atexit.register(sampler.stop)
     stream = torch.cuda.current_stream()
     for _ in range(args.warmup):
         m.hess_coord(x, y, hess, obj_weight=1.0)

@@ -183,6 +183,12 @@ int make_plan(const void* ir, size_t bytes, exb_plan** out) {
   return EXB_OK;
 }
 
+std::string shq(const std::string& p) {   // single-quote a path for the shell
+  std::string o = "'";
+  for (char c : p) { if (c == '\'') o += "'\\''"; else o += c; }
+  return o + "'";
+}
+
 bool file_exists(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 && st.st_size > 0; }
 
 int compile_plan(exb_plan* p, bool allow_compile) {
@@ -201,8 +207,8 @@ int compile_plan(exb_plan* p, bool allow_compile) {
     if (file_exists(v.cubin_path)) continue;
     { std::ofstream f(v.cu_path); f << v.source; }
     std::string tmp = v.cubin_path + ".tmp" + std::to_string((long)getpid());
-    cmd += "( " + nvcc_path() + " " + NVCC_FLAGS_CLEAN + " -o " + tmp + " " + v.cu_path + " > " + v.cubin_path + ".log 2>&1 && mv " + tmp + " " +
-           v.cubin_path + " ) & ";
+    cmd += "( " + shq(nvcc_path()) + " " + NVCC_FLAGS_CLEAN + " -o " + shq(tmp) + " " + shq(v.cu_path) + " > " + shq(v.cubin_path + ".log") +
+           " 2>&1 && mv " + shq(tmp) + " " + shq(v.cubin_path) + " ) & ";
     todo.push_back(&v);
   }
   if (!todo.empty()) {
@@ -375,7 +381,8 @@ int upload_column(exb_model* m, const unsigned char* base, long long n, long lon
 int build_model(exb_model* m, const void* const* host_data, int n_data) {
   exb_plan* P = m->plan;
   const exb::Plan& pl = P->pl;
-  if (pl.m.ndatabufs > n_data) return fail(EXB_ERR_ARG, "IR references more data buffers than were passed");
+  if (pl.m.ndatabufs > n_data || (pl.m.ndatabufs > 0 && !host_data))
+    return fail(EXB_ERR_ARG, "IR references more data buffers than were passed");
   CU_TRY(m, cudaFree(0));
   if (!load_driver()) return fail(EXB_ERR_CUDA, "CUDA driver entry points unavailable");
   {  // sm_100 only

@@ -85,7 +85,7 @@ typedef struct exb_options {
   int32_t rank;        /* shard of every pattern's iterator this handle evaluates ... */
   int32_t world;       /* ... out of `world` contiguous shards (1 = whole model) */
   int32_t flags;       /* EXB_FLAG_* */
-  int64_t fuse_below;  /* patterns with fewer points share one launch; 0 = default */
+  int64_t fuse_below;  /* reserved (every pattern of a callback shares one launch); pass 0 */
 } exb_options;
 
 #define EXB_FLAG_NO_COMPILE 1 /* fail instead of invoking nvcc when the module is not cached */
