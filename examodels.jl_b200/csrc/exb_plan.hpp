@@ -51,6 +51,10 @@ struct PatternPlan {
   int ppt0 = 1, ppt1 = 1, ppt2 = 1;   // points per thread in the value / first-order / second-order kernels
   std::vector<int> leaf1;      // representative Var IR node per first-order slot
   std::vector<std::pair<int, int>> leaf2;
+  // owner-computes gradient (see gen_pattern, g1): every first-order slot's variable index is `t + shift1[j]` with
+  // t the value of a range iterator, so variable v receives slot j of point t = v - shift1[j] and nothing else
+  bool gather1 = false;
+  std::vector<i64> shift1;
 };
 
 struct Plan {
@@ -60,7 +64,7 @@ struct Plan {
   std::string source;  // generated module (without the device header)
   std::string error;
   // pattern lists per kernel (indices into pats), fixed at generation time
-  std::vector<int> k_hess, k_jac, k_sgrad, k_cons, k_obj, k_aug;
+  std::vector<int> k_hess, k_jac, k_sgrad, k_ggrad, k_cons, k_obj, k_aug;
   bool idx32 = false;          // every index (variables, points, slots) fits 31 bits: address arithmetic in 32 bits
   int block = 128, minb = 16;  // launch shape of the generated kernels (tuning knobs: EXB_TUNE_BLOCK / EXB_TUNE_MINB)
 };
@@ -116,6 +120,50 @@ inline bool ir_equal(const PatternIR& p, int a, int b) {   // Julia `===` on imm
     case T_OP2: return x.payload == y.payload && ir_equal(p, (int)x.a, (int)y.a) && ir_equal(p, (int)x.b, (int)y.b);
   }
   return false;
+}
+
+// Integer index expression as an affine function of the iterator value t (DATA_SELF): value = coef * t + cst.
+// Only the integer `+ - *` that index expressions are made of (nlp.jl:900-926,2012-2015); anything else -> false.
+inline bool affine_index(const PatternIR& p, int n, i64& coef, i64& cst) {
+  const IRNode& q = p.nodes[(size_t)n];
+  auto small = [](i64 v) { return v > -(1LL << 40) && v < (1LL << 40); };
+  switch (q.tag) {
+    case T_CONST_I: case T_VAL: coef = 0; cst = q.payload; return small(cst);
+    case T_DATA_SELF: coef = 1; cst = 0; return true;
+    case T_OP1: {
+      i64 a, b;
+      if (!affine_index(p, (int)q.a, a, b)) return false;
+      if (q.payload == U_PLUS) { coef = a; cst = b; return true; }
+      if (q.payload == U_MINUS) { coef = -a; cst = -b; return true; }
+      return false;
+    }
+    case T_OP2: {
+      i64 a1, b1, a2, b2;
+      if (!affine_index(p, (int)q.a, a1, b1) || !affine_index(p, (int)q.b, a2, b2)) return false;
+      if (q.payload == B_ADD) { coef = a1 + a2; cst = b1 + b2; return small(coef) && small(cst); }
+      if (q.payload == B_SUB) { coef = a1 - a2; cst = b1 - b2; return small(coef) && small(cst); }
+      if (q.payload == B_MUL && (a1 == 0 || a2 == 0)) {
+        if (a1 == 0) { coef = b1 * a2; cst = b1 * b2; } else { coef = a1 * b2; cst = b1 * b2; }
+        return small(coef) && small(cst) && small(b1) && small(b2);
+      }
+      return false;
+    }
+  }
+  return false;
+}
+// Can two variable index expressions be decided equal / unequal for EVERY data point?  1 always equal, 0 never, -1 unknown.
+inline int index_relation(const PatternIR& p, int a, int b) {
+  if (ir_equal(p, a, b)) return 1;
+  i64 c1, k1, c2, k2;
+  if (p.itr_kind == ITR_RANGE && affine_index(p, a, c1, k1) && affine_index(p, b, c2, k2)) {
+    if (c1 == c2) return k1 == k2 ? 1 : 0;
+    // (c1 - c2) t = k2 - k1 has at most one integer solution: only decidable when it has none
+    const i64 dc = c1 - c2, dk = k2 - k1;
+    if (dk % dc != 0) return 0;
+    const i64 t = dk / dc;
+    if (t < p.range_start || t >= p.range_start + p.nitr) return 0;
+  }
+  return -1;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -382,7 +430,9 @@ struct Gen {
     int j = (*comp)[(size_t)cnt++] - 1;
     if (adj.c && adj.v == 0) return;
     Ex v;
-    if (ir_equal(p.ir, (int)N(a).a, (int)N(b).a)) v = B.mul(K(2), adj);     // i == j structurally
+    const int rel = index_relation(p.ir, (int)N(a).a, (int)N(b).a);
+    if (rel == 1) v = B.mul(K(2), adj);     // i == j for every point (structurally, or equal affine index maps)
+    else if (rel == 0) v = adj;             // affine index maps that never meet: the compare is decided at build time
     else v = Sym(B.tmp("double", "exb_twice_if_eq(EXB_IX(" + nv[(size_t)a].idx + "), EXB_IX(" + nv[(size_t)b].idx + "), " + adj.s + ")"));
     slot[(size_t)j] = B.add(slot[(size_t)j], v);
   }
@@ -579,6 +629,35 @@ inline std::string gen_pattern(PatternPlan& p, int index) {
     }
     emit_fn(o, "void d1(" + A + ", const double* __restrict__ x, const double* __restrict__ th, double (&s)[" + std::to_string(a1) + "])", B, tail);
     p.ppt1 = ppt_for(body_weight(B), a1);
+    // Owner-computes gradient: objective over a range iterator whose slots all address x[t + const].  Variable v
+    // then receives exactly slot j of point t = v - shift1[j] (if that point exists), so ONE thread per variable
+    // re-evaluates the (cheap) body once per slot and writes g[v] once: no gradbuffer, no sorted list, no atomics
+    // (the reference writes nnzg slots and then segment-sums them, ext:310-336,691-697).  Bodies too heavy to be
+    // re-evaluated o1step times keep the slot + compress path.
+    p.gather1 = false; p.shift1.clear();
+    static const int gmax = getenv("EXB_TUNE_GATHER_W") ? atoi(getenv("EXB_TUNE_GATHER_W")) : 300;
+    if (p.ir.kind == KIND_OBJ && p.ir.itr_kind == ITR_RANGE && ns1 > 0 && body_weight(B) * ns1 <= gmax) {
+      bool ok = true;
+      for (int j = 0; j < ns1 && ok; j++) {
+        i64 cf, ct;
+        ok = affine_index(p.ir, (int)p.ir.nodes[(size_t)p.leaf1[(size_t)j]].a, cf, ct) && cf == 1;
+        p.shift1.push_back(ct);
+      }
+      p.gather1 = ok;
+    }
+    if (p.gather1) {
+      // summation order of the reference for one variable: ascending global slot number = ascending point, then slot
+      std::vector<int> ord((size_t)ns1);
+      for (int j = 0; j < ns1; j++) ord[(size_t)j] = j;
+      std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return p.shift1[(size_t)a] > p.shift1[(size_t)b]; });
+      o << "  __device__ static __forceinline__ double g1(const ExbPatArgs& pa, const long long v, const double* __restrict__ x, const double* __restrict__ th) {\n";
+      o << "    double acc = 0.0;\n";
+      for (int j : ord) {
+        o << "    { const long long kg = v - (" << Gen::ilit(p.shift1[(size_t)j]) << ") - pa.start;\n"
+          << "      if (kg >= pa.k0 && kg < pa.k0 + pa.n) { double s[" << a1 << "]; d1(pa, kg, x, th, s); acc += s[" << j << "]; } }\n";
+      }
+      o << "    return acc;\n  }\n";
+    }
   }
   {  // d2
     Body B; Gen g(p, B, 2);
@@ -669,14 +748,6 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes) {
     if (p.ir.o1 >= 0 && p.ir.o1 != p.o1) { pl.error = "o1 supplied in the IR disagrees with the counters"; return false; }
     if (p.ir.o2 >= 0 && p.ir.o2 != p.o2) { pl.error = "o2 supplied in the IR disagrees with the counters"; return false; }
   }
-  // kernel pattern lists
-  for (size_t k = 0; k < pl.pats.size(); k++) {
-    const PatternPlan& p = pl.pats[k];
-    if (p.o2step > 0) pl.k_hess.push_back((int)k);
-    if (p.ir.kind == KIND_OBJ) { pl.k_obj.push_back((int)k); if (p.o1step > 0) pl.k_sgrad.push_back((int)k); }
-    else { pl.k_cons.push_back((int)k); if (p.o1step > 0) pl.k_jac.push_back((int)k); }
-    if (p.ir.kind == KIND_AUG) pl.k_aug.push_back((int)k);
-  }
   // module source
   {
     i64 mx = std::max(std::max(pl.m.nvar, pl.m.npar), std::max(std::max(pl.nnzh, pl.nnzj), std::max(pl.nnzg, pl.ncon)));
@@ -689,6 +760,14 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes) {
   std::ostringstream o;
   o << "// generated by exb_plan.hpp -- one struct per pattern, kernels per callback\n";
   for (size_t k = 0; k < pl.pats.size(); k++) o << gen_pattern(pl.pats[k], (int)k);
+  // kernel pattern lists
+  for (size_t k = 0; k < pl.pats.size(); k++) {
+    const PatternPlan& p = pl.pats[k];
+    if (p.o2step > 0) pl.k_hess.push_back((int)k);
+    if (p.ir.kind == KIND_OBJ) { pl.k_obj.push_back((int)k); if (p.o1step > 0) (p.gather1 ? pl.k_ggrad : pl.k_sgrad).push_back((int)k); }
+    else { pl.k_cons.push_back((int)k); if (p.o1step > 0) pl.k_jac.push_back((int)k); }
+    if (p.ir.kind == KIND_AUG) pl.k_aug.push_back((int)k);
+  }
   auto kern = [&](const char* name, const char* body, const std::vector<int>& v, const char* targ) {
     if (v.empty()) return;
     o << "extern \"C\" __global__ void __launch_bounds__(EXB_BLOCK, EXB_MINB) " << name << "(const ExbGroup g, const ExbCall c) { "
@@ -697,6 +776,7 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes) {
   kern("exb_hess_g0", "exb_hess_body", pl.k_hess, "");
   kern("exb_jac_g0", "exb_d1_body", pl.k_jac, "");
   kern("exb_sgrad_g0", "exb_d1_body", pl.k_sgrad, "");
+  kern("exb_ggrad_g0", "exb_ggrad_body", pl.k_ggrad, "");
   kern("exb_cons_g0", "exb_cons_body", pl.k_cons, "");
   kern("exb_obj_g0", "exb_obj_body", pl.k_obj, "");
   kern("exb_jstruct64_g0", "exb_jstruct_body", pl.k_jac, "long long, ");

@@ -108,8 +108,8 @@ std::string cu_err(CUresult r) {
   return s ? s : "CUDA driver error " + std::to_string((int)r);
 }
 
-enum { KN_HESS, KN_JAC, KN_SGRAD, KN_CONS, KN_OBJ, KN_JSTRUCT64, KN_JSTRUCT32, KN_GSTRUCT64, KN_HSTRUCT64, KN_HSTRUCT32, KN_AUGROW, KN_COUNT };
-const char* KNAME[KN_COUNT] = {"exb_hess_g0", "exb_jac_g0", "exb_sgrad_g0", "exb_cons_g0", "exb_obj_g0", "exb_jstruct64_g0",
+enum { KN_HESS, KN_JAC, KN_SGRAD, KN_GGRAD, KN_CONS, KN_OBJ, KN_JSTRUCT64, KN_JSTRUCT32, KN_GSTRUCT64, KN_HSTRUCT64, KN_HSTRUCT32, KN_AUGROW, KN_COUNT };
+const char* KNAME[KN_COUNT] = {"exb_hess_g0", "exb_jac_g0", "exb_sgrad_g0", "exb_ggrad_g0", "exb_cons_g0", "exb_obj_g0", "exb_jstruct64_g0",
                                "exb_jstruct32_g0", "exb_gstruct64_g0", "exb_hstruct64_g0", "exb_hstruct32_g0", "exb_augrow_g0"};
 
 }  // namespace
@@ -132,6 +132,7 @@ struct exb_plan {
       case KN_HESS: case KN_HSTRUCT64: case KN_HSTRUCT32: return pl.k_hess;
       case KN_JAC: case KN_JSTRUCT64: case KN_JSTRUCT32: return pl.k_jac;
       case KN_SGRAD: case KN_GSTRUCT64: return pl.k_sgrad;
+      case KN_GGRAD: return pl.k_ggrad;
       case KN_CONS: return pl.k_cons;
       case KN_OBJ: return pl.k_obj;
       default: return pl.k_aug;
@@ -148,6 +149,8 @@ struct Launch {          // one generated kernel, ready to launch
   ExbGroup g{};          // device pointers
   unsigned nblocks = 0;
   unsigned smem = 0;
+  std::vector<ExbChunk> hchunk;       // host copy of the chunk table (windowed launches of the pipelined host shims)
+  std::vector<int> ppt, ns;           // per listed pattern: points per thread, slots per point
 };
 
 int make_plan(const void* ir, size_t bytes, exb_plan** out) {
@@ -254,7 +257,8 @@ struct exb_model {
   double *d_jacbuf = nullptr, *d_hessbuf = nullptr;
   std::vector<long long> lo, hi;   // local point range per pattern
   // host shims
-  cudaStream_t hstream = nullptr;
+  cudaStream_t hstream = nullptr, hstream2 = nullptr;
+  std::vector<cudaEvent_t> hev;
   double *hx = nullptr, *hy = nullptr, *hout = nullptr; size_t hx_n = 0, hy_n = 0, hout_n = 0;
   double *dx = nullptr, *dy = nullptr, *dout = nullptr; size_t dx_n = 0, dy_n = 0, dout_n = 0;
   long long launches = 0, last_launches = 0;
@@ -458,7 +462,7 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       if (r != CUDA_SUCCESS) return fail(EXB_ERR_COMPILE, std::string("kernel ") + KNAME[kn] + " missing from module: " + cu_err(r));
       L.cand.push_back(fn);
     }
-    const bool tunable = kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD || kn == KN_CONS || kn == KN_OBJ;
+    const bool tunable = kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD || kn == KN_GGRAD || kn == KN_CONS || kn == KN_OBJ;
     L.best = (!tunable || L.cand.size() == 1) ? 0 : tuned[kn];
     L.fn = L.cand[L.best >= 0 ? (size_t)L.best : 0];
     const long long BLK = P->pl.block;
@@ -474,6 +478,15 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       tot += nb[q]; if (nb[q] > maxnb) maxnb = nb[q];
       int ns = k2 ? p.o2step : k1 ? p.o1step : 1;
       if (ns <= EXB_TILE_MAX_NS && ns * ppt > maxns) maxns = ns * ppt;   // tile words per thread
+    }
+    if (kn == KN_GGRAD) {   // one thread per VARIABLE (exb_ggrad_body), no block -> pattern map; runs even when this shard has no points (g = 0)
+      void* d_args = nullptr;
+      int rc = dmalloc(m, &d_args, args.size() * sizeof(ExbPatArgs)); if (rc) return rc;
+      CU_TRY(m, cudaMemcpy(d_args, args.data(), args.size() * sizeof(ExbPatArgs), cudaMemcpyHostToDevice));
+      L.g.pat = (const ExbPatArgs*)d_args; L.g.chunk = nullptr; L.g.np = (int)lst.size(); L.g.shift = 0;
+      L.nblocks = (unsigned)((pl.m.nvar + BLK * EXB_GVPT - 1) / (BLK * EXB_GVPT));
+      L.smem = 0;
+      continue;
     }
     if (tot == 0) continue;   // nothing local to evaluate (e.g. a shard with no points)
     // chunked round-robin interleave of the patterns' block ranges (see ExbGroup)
@@ -509,6 +522,12 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
     CU_TRY(m, cudaMemcpy(d_chunk, chunks.data(), chunks.size() * sizeof(ExbChunk), cudaMemcpyHostToDevice));
     L.g.pat = (const ExbPatArgs*)d_args; L.g.chunk = (const ExbChunk*)d_chunk; L.g.np = (int)lst.size(); L.g.shift = shift;
     L.nblocks = (unsigned)(chunks.size() * csz);
+    L.hchunk = chunks;
+    for (size_t q = 0; q < lst.size(); q++) {
+      const exb::PatternPlan& p = pl.pats[(size_t)lst[q]];
+      L.ppt.push_back(kn == KN_HESS ? p.ppt2 : (kn == KN_JAC || kn == KN_SGRAD) ? p.ppt1 : (kn == KN_CONS || kn == KN_OBJ) ? p.ppt0 : 1);
+      L.ns.push_back(kn == KN_HESS ? p.o2step : (kn == KN_JAC || kn == KN_SGRAD) ? p.o1step : 1);
+    }
     L.smem = (kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD) ? (maxns > 1 ? (unsigned)(BLK * maxns * 8) : 16u) : 0u;
     if (L.smem > 48u * 1024u)   // tiles of patterns with many slots per point: opt in to large dynamic shared memory
       for (CUfunction fn : L.cand) {
@@ -576,6 +595,8 @@ void free_model(exb_model* m) {
   if (m->dy) cudaFree(m->dy);
   if (m->dout) cudaFree(m->dout);
   if (m->hstream) cudaStreamDestroy(m->hstream);
+  if (m->hstream2) cudaStreamDestroy(m->hstream2);
+  for (cudaEvent_t e : m->hev) cudaEventDestroy(e);
   for (auto& p : m->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
   delete m->plan;
   delete m;
@@ -746,10 +767,15 @@ int exb_grad(exb_model* m, const double* x, double* g, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const exb::Plan& pl = m->plan->pl;
   ExbCall c{}; c.x = x; c.th = m->d_theta; c.out = m->d_gradbuf;
+  const bool gathered = m->k[KN_GGRAD].nblocks > 0;
+  if (gathered) {   // shift-indexed objective patterns: one thread per variable writes g[v] (0 where untouched)
+    ExbCall cg{}; cg.x = x; cg.th = m->d_theta; cg.out = g; cg.nout = pl.m.nvar;
+    int rc = launch(m, KN_GGRAD, cg, st); if (rc) return rc;
+  }
   int rc = launch(m, KN_SGRAD, c, st); if (rc) return rc;                        // kerg, ext:669-679
   // fill!(g, 0) (ext:317) is only needed when some variable has no objective term; otherwise every g[v] is assigned
-  if (!(m->g_dense && m->g_runs == pl.m.nvar)) CU_TRY(m, cudaMemsetAsync(g, 0, (size_t)pl.m.nvar * 8, st));
-  CU_TRY(m, exb_fx_compress(m->d_gradbuf, m->g_ptr, m->g_slot, m->g_target, m->g_i32, m->g_runs, g, 0, st));   // ext:691-697
+  if (!gathered && !(m->g_dense && m->g_runs == pl.m.nvar)) CU_TRY(m, cudaMemsetAsync(g, 0, (size_t)pl.m.nvar * 8, st));
+  CU_TRY(m, exb_fx_compress(m->d_gradbuf, m->g_ptr, m->g_slot, m->g_target, m->g_i32, m->g_runs, g, gathered ? 1 : 0, st));   // ext:691-697
   if (m->g_runs > 0) { m->launches++; m->last_launches++; }
   return EXB_OK;
   EXB_END
@@ -1047,6 +1073,80 @@ static std::vector<std::pair<long long, long long>> slices(const exb_model* m, i
   }
   return v;
 }
+// Pipelined form of exb_host_jac / exb_host_hess for page-locked caller buffers: the COO values are 8-9x the size of
+// x and y, so the D2H copy is the step's critical path (PCIe).  The launch is cut into windows of consecutive chunks
+// of the block -> pattern table; a window covers one contiguous point range of each pattern, hence one contiguous
+// output slice per pattern, which is copied back on a second stream while the next window's multipliers go up and
+// its kernel runs.  x is needed by every window (indices are data), so it goes first and whole.
+static int host_coo_pipelined(exb_model* m, int kn, const double* x, const double* y, double sigma, double* out, bool* done) {
+  *done = false;
+  Launch& L = m->k[kn];
+  const exb::Plan& pl = m->plan->pl;
+  static const int wenv = getenv("EXB_HOST_WINDOWS") ? atoi(getenv("EXB_HOST_WINDOWS")) : 8;
+  const long long nch = (long long)L.hchunk.size();
+  const long long total = kn == KN_HESS ? pl.nnzh : pl.nnzj;
+  if (wenv < 2 || L.best < 0 || !L.fn || nch < 2 || total < (1LL << 20)) return EXB_OK;   // untuned kernel / tiny output: plain path
+  if (!is_pinned(x) || (y && !is_pinned(y))) return EXB_OK;
+  for (auto& s_ : slices(m, kn == KN_HESS ? 2 : 1)) if (s_.second > s_.first && !is_pinned(out + s_.first)) return EXB_OK;
+  const std::vector<int>& lst = m->plan->list(kn);
+  int rc = host_stream(m); if (rc) return rc;
+  if (!m->hstream2) CU_TRY(m, cudaStreamCreateWithFlags(&m->hstream2, cudaStreamNonBlocking));
+  const int W = (int)std::min<long long>(wenv, nch);
+  while ((int)m->hev.size() < W) { cudaEvent_t e; CU_TRY(m, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); m->hev.push_back(e); }
+  rc = ensure_host(m, &m->hx, &m->hx_n, &m->dx, &m->dx_n, 0, (size_t)pl.m.nvar); if (rc) return rc;
+  if (y) { rc = ensure_host(m, &m->hy, &m->hy_n, &m->dy, &m->dy_n, 0, (size_t)pl.ncon); if (rc) return rc; }
+  rc = ensure_host(m, &m->hout, &m->hout_n, &m->dout, &m->dout_n, 0, (size_t)total); if (rc) return rc;
+  CU_TRY(m, cudaMemcpyAsync(m->dx, x, (size_t)pl.m.nvar * 8, cudaMemcpyHostToDevice, m->hstream));
+  bool ywin = y != nullptr;   // multipliers can follow the windows only when every row is `o0 + k` (no augmentation in the list)
+  for (int pi : lst) if (pl.pats[(size_t)pi].ir.kind == exb::KIND_AUG) ywin = false;
+  if (y && !ywin) CU_TRY(m, cudaMemcpyAsync(m->dy, y, (size_t)pl.ncon * 8, cudaMemcpyHostToDevice, m->hstream));
+  const long long csz = 1LL << L.g.shift, BLK = pl.block;
+  std::vector<long long> bmin(lst.size()), bmax(lst.size());
+  for (int w = 0; w < W; w++) {
+    const long long c0 = nch * w / W, c1 = nch * (w + 1) / W;
+    if (c1 <= c0) continue;
+    for (size_t q = 0; q < lst.size(); q++) { bmin[q] = -1; bmax[q] = -1; }
+    for (long long c = c0; c < c1; c++) {
+      const int q = L.hchunk[(size_t)c].pat;
+      if (q < 0) continue;
+      const long long b0 = L.hchunk[(size_t)c].b0;
+      if (bmin[(size_t)q] < 0 || b0 < bmin[(size_t)q]) bmin[(size_t)q] = b0;
+      if (b0 + csz > bmax[(size_t)q]) bmax[(size_t)q] = b0 + csz;
+    }
+    std::vector<std::pair<long long, long long>> outs;
+    for (size_t q = 0; q < lst.size(); q++) {
+      if (bmin[q] < 0) continue;
+      const size_t pi = (size_t)lst[q];
+      const exb::PatternPlan& p = pl.pats[pi];
+      const long long n = m->hi[pi] - m->lo[pi], per = BLK * L.ppt[q];
+      const long long p0 = std::min(n, bmin[q] * per), p1 = std::min(n, bmax[q] * per);
+      if (p1 <= p0) continue;
+      if (ywin && p.ir.kind == exb::KIND_CON) {
+        const long long r0 = p.o0 + m->lo[pi] + p0;
+        CU_TRY(m, cudaMemcpyAsync(m->dy + r0, y + r0, (size_t)(p1 - p0) * 8, cudaMemcpyHostToDevice, m->hstream));
+      }
+      const long long o = kn == KN_HESS ? p.o2 : p.o1;
+      outs.push_back({o + (m->lo[pi] + p0) * L.ns[q], o + (m->lo[pi] + p1) * L.ns[q]});
+    }
+    {   // this window's blocks: the same kernel over a sub-range of the chunk table
+      ExbGroup g = L.g; g.chunk = L.g.chunk + c0;
+      ExbCall cc{}; cc.x = m->dx; cc.y = y ? m->dy : nullptr; cc.th = m->d_theta; cc.sigma = sigma; cc.out = m->dout;
+      void* params[2] = {&g, &cc};
+      CUresult r = g_drv.LaunchKernel(L.fn, (unsigned)((c1 - c0) * csz), 1, 1, (unsigned)pl.block, 1, 1, L.smem, (CUstream)m->hstream, params, nullptr);
+      if (r != CUDA_SUCCESS) return fail(EXB_ERR_CUDA, std::string("windowed launch of ") + KNAME[kn] + ": " + cu_err(r));
+      m->launches++; m->last_launches++;
+    }
+    CU_TRY(m, cudaEventRecord(m->hev[(size_t)w], m->hstream));
+    CU_TRY(m, cudaStreamWaitEvent(m->hstream2, m->hev[(size_t)w], 0));
+    for (auto& sl : outs)
+      CU_TRY(m, cudaMemcpyAsync(out + sl.first, m->dout + sl.first, (size_t)(sl.second - sl.first) * 8, cudaMemcpyDeviceToHost, m->hstream2));
+  }
+  CU_TRY(m, cudaStreamSynchronize(m->hstream2));
+  CU_TRY(m, cudaStreamSynchronize(m->hstream));
+  *done = true;
+  return EXB_OK;
+}
+
 int exb_host_obj(exb_model* m, const double* x, double* out) {
   EXB_BEGIN
   EXB_GUARD(m);
@@ -1076,10 +1176,12 @@ int exb_host_cons(exb_model* m, const double* x, double* out) {
 }
 int exb_host_jac(exb_model* m, const double* x, double* out) {
   const double* yy = nullptr;
+  { EXB_BEGIN EXB_GUARD(m); bool done = false; int prc = host_coo_pipelined(m, KN_JAC, x, nullptr, 0.0, out, &done); if (prc || done) return prc; EXB_END }
   EXB_HOST_VEC(pl.nnzj, slices(m, 1), exb_jac(m, m->dx, m->dout, m->hstream))
 }
 int exb_host_hess(exb_model* m, const double* x, const double* y, double obj_weight, double* out) {
   const double* yy = y;
+  { EXB_BEGIN EXB_GUARD(m); bool done = false; int prc = host_coo_pipelined(m, KN_HESS, x, y, obj_weight, out, &done); if (prc || done) return prc; EXB_END }
   EXB_HOST_VEC(pl.nnzh, slices(m, 2), exb_hess(m, m->dx, y ? m->dy : nullptr, obj_weight, m->dout, m->hstream))
 }
 static int host_structure(exb_model* m, int kn, long long n, int64_t* rows, int64_t* cols) {

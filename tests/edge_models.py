@@ -73,5 +73,25 @@ def field_types():
     return c
 
 
-EDGE = {"only_objective": only_objective, "only_constraints": only_constraints, "empty_patterns": empty_patterns,
+def mixed_gradient():
+    """Objective patterns of every gradient flavour in one model: shift-indexed over ranges (owner-computes kernel,
+    two of them overlapping on the same variables, shifts up to +-3), a strided index x[2i], a data-indexed one and a
+    body too heavy to re-evaluate per slot (all three: slot + segmented-sum path), plus variables no objective touches."""
+    rng = np.random.default_rng(10)
+    n = 41
+    c = E.ExaCore(); x = c.add_var(n, start=rng.uniform(0.4, 0.9, n)); z = c.add_var(5, start=rng.uniform(0.4, 0.9, 5))
+    c.add_obj(lambda i: (x[i - 3] - x[i + 3]) ** 2 * x[i], range(4, n - 6))
+    c.add_obj(lambda i: x[i] * x[i + 1] * x[i + 1 + 0] + 0.5 * x[1 + i], range(2, n - 1))
+    c.add_obj(lambda i: x[2 * i] ** 3, range(1, n // 2))
+    d = np.zeros(17, dtype=np.dtype([("i", "i8"), ("a", "f8")]))
+    d["i"] = rng.integers(1, n + 1, 17); d["a"] = rng.uniform(0.5, 1.5, 17)
+    c.add_obj(lambda q: q.a * sin(x[q.i]) * x[q.i], d)
+    c.add_obj(lambda i: exp(sin(x[i]) * cos(x[i + 1])) * exp(x[i + 2]) * sin(x[i + 3] * x[i]) * cos(exp(x[i + 1] - x[i + 2]))
+              * sin(cos(x[i]) + x[i + 3]) * exp(-x[i + 1] * x[i + 2]) * cos(sin(x[i + 3]) - x[i]) * sin(exp(x[i]) * 0.1)
+              * cos(x[i + 1] * x[i + 3]) * exp(sin(x[i + 2])), range(1, 9))
+    c.add_con(lambda i: x[i] * z[1] + x[i + 1], range(1, 6))
+    return c
+
+
+EDGE = {"mixed_gradient": mixed_gradient, "only_objective": only_objective, "only_constraints": only_constraints, "empty_patterns": empty_patterns,
         "single_points_and_constants": single_points_and_constants, "self_loops": self_loops, "field_types": field_types}

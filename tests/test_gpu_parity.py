@@ -166,3 +166,39 @@ def test_per_callback_timing(exa, torch_):
     m.set_timing(False)
     m.hess_coord(dx, dy, h)
     assert m.timings()["hess"]["calls"] == 0
+
+
+@pytest.mark.parametrize("which", ["lv", "lv_aug", "rocket"])
+def test_pipelined_host_shims(exa, torch_, which):
+    """exb_host_hess / exb_host_jac with page-locked caller buffers: windowed launches on one stream, D2H of each
+    window's per-pattern slices on a second one (csrc/exb_runtime.cpp host_coo_pipelined).  Same values as the oracle;
+    pageable buffers keep the single-launch path.  `lv_aug` has augmentation rows, so y is uploaded whole."""
+    from examodels_jl_b200 import models as M
+    from oracle.oracle_api import Oracle
+    torch = torch_
+    core = {"lv": lambda: M.luksan_vlcek(400_000), "lv_aug": lambda: M.luksan_vlcek_aug(80_000, 3),
+            "rocket": lambda: M.goddard_rocket(60_000)}[which]()
+    m, ora = exa.ExaModel(core), Oracle.from_core(core)
+    x, y = inputs(core)
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()   # noqa: E731
+    xp, yp = pin(x), pin(y)
+    hp, jp = pin(np.full(m.nnzh, np.nan)), pin(np.full(m.nnzj, np.nan))
+    m.hess_coord(xp, yp, hp, obj_weight=0.5); m.jac_coord(xp, jp)          # first calls tune the kernels (plain path)
+    ref_h, ref_j = ora.hess_coord(x, y, 0.5), ora.jac_coord(x)
+    assert_close(hp, ref_h, "host hess, tuning call"); assert_close(jp, ref_j, "host jac, tuning call")
+    for rep in range(2):
+        hp[:] = np.nan; jp[:] = np.nan
+        l0 = m.stats()["launches"]
+        m.hess_coord(xp, yp, hp, obj_weight=0.5)
+        l1 = m.stats()["launches"]
+        m.jac_coord(xp, jp)
+        l2 = m.stats()["launches"]
+        assert l1 - l0 > 1 and l2 - l1 > 1, "pinned buffers should take the windowed path"
+        assert_close(hp, ref_h, "pipelined host hess"); assert_close(jp, ref_j, "pipelined host jac")
+    hp[:] = np.nan
+    m.hess_coord(xp, None, hp, obj_weight=2.0)
+    assert_close(hp, ora.hess_coord(x, None, 2.0), "pipelined host hess, objective only")
+    hh = np.full(m.nnzh, np.nan)
+    l0 = m.stats()["launches"]
+    assert_close(m.hess_coord(x, y, hh, obj_weight=0.5), ref_h, "pageable host hess")
+    assert m.stats()["launches"] - l0 == 1

@@ -46,9 +46,21 @@ def test_generated_source_is_model_size_independent():
     a, b = E.Plan(M.luksan_vlcek(100)), E.Plan(M.luksan_vlcek(10_000))
     assert a.source() == b.source() and a.module_path() == b.module_path()
     src = a.source()
-    for kern in ("exb_hess_g0", "exb_jac_g0", "exb_sgrad_g0", "exb_cons_g0", "exb_obj_g0", "exb_hstruct64_g0"):
+    for kern in ("exb_hess_g0", "exb_jac_g0", "exb_ggrad_g0", "exb_cons_g0", "exb_obj_g0", "exb_hstruct64_g0"):
         assert f'extern "C" __global__ void __launch_bounds__(EXB_BLOCK, EXB_MINB) {kern}' in src
     assert "sincos" in src and "struct P0" in src and "struct P1" in src
+
+
+def test_gradient_kernel_choice():
+    """Shift-indexed objectives over a range (x[i-1], x[i]) get the owner-computes gradient kernel; objectives whose
+    variable indices come from iterator data keep the slot + segmented-sum path of the reference (ext:310-336,691-697)."""
+    lv = E.Plan(M.luksan_vlcek(50)).source()
+    assert "exb_ggrad_g0" in lv and "exb_sgrad_g0" not in lv
+    # slot order for variable v: point v (slot of x[i]) before point v + 1 (slot of x[i-1]) = ascending slot number
+    g1 = lv[lv.index("double g1("):]
+    assert g1.index("acc += s[1]") < g1.index("acc += s[0]")
+    fam = E.Plan(M.pattern_family(100, 8)).source()
+    assert "exb_sgrad_g0" in fam and "exb_ggrad_g0" not in fam
 
 
 def test_header_symbols_exported():
