@@ -288,7 +288,7 @@ struct Gen {
           else if (op == U_ABS) r.rs = B.tmp("long long", "(" + a.rs + " < 0 ? -" + a.rs + " : " + a.rs + ")");
           else r.rs = B.tmp("long long", a.rs + " * " + a.rs);
         } else {
-          r.rs = B.tmp("double", "exb_f1<" + std::to_string(op) + ">(" + as_double(a) + ")");
+          r.rs = B.tmp("double", "exb_f1<" + std::to_string(op) + ", SLOW>(" + as_double(a) + ", bad)");
         }
       } break;
       case T_OP2: {
@@ -339,9 +339,9 @@ struct Gen {
         case U_MINUS: r.x = B.neg(a.x); r.y1 = K(-1); r.h11 = K(0); return r;
         case U_ABS2: r.x = B.mul(a.x, a.x); r.y1 = B.mul(K(2), a.x); r.h11 = K(2); return r;
       }
-      if (order == 0) { r.x = Sym(B.tmp("double", "exb_f1<" + std::to_string(op) + ">(" + a.x.s + ")")); return r; }
+      if (order == 0) { r.x = Sym(B.tmp("double", "exb_f1<" + std::to_string(op) + ", SLOW>(" + a.x.s + ", bad)")); return r; }
       std::string f = fresh("f", n), d = fresh("d", n), dd = fresh("dd", n);
-      B.raw("double " + f + ", " + d + ", " + dd + "; exb_uni<" + std::to_string(op) + ", " + O + ">(" + a.x.s + ", " + f + ", " + d + ", " + dd + ");");
+      B.raw("double " + f + ", " + d + ", " + dd + "; exb_uni<" + std::to_string(op) + ", " + O + ", SLOW>(" + a.x.s + ", " + f + ", " + d + ", " + dd + ", bad);");
       r.x = Sym(f); r.y1 = Sym(d); r.h11 = Sym(dd);
       switch (op) {   // structurally constant derivatives
         case U_ABS: case U_DEG2RAD: case U_RAD2DEG: r.h11 = K(0); break;
@@ -564,8 +564,46 @@ inline void probe(PatternPlan& p) {   // simdfunction.jl:66-100
 // ---------------------------------------------------------------------------------------
 inline void emit_fn(std::ostringstream& o, const std::string& sig, const Body& B, const std::vector<std::string>& tail) {
   o << "  __device__ static __forceinline__ " << sig << " {\n";
+  o << "    constexpr bool SLOW = false; bool bad = false; (void)SLOW; (void)bad;\n";
   for (auto& l : B.lines) o << "    " << l << "\n";
   for (auto& l : tail) o << "    " << l << "\n";
+  o << "  }\n";
+}
+// does the body call a routine with a range-limited fast path (sin, cos, exp: exb_sincos / exb_exp in exb_device.cuh)?
+inline bool body_uses_fast(const Body& B) {
+  for (auto& l : B.lines)
+    for (int op : {(int)U_EXP, (int)U_SIN, (int)U_COS}) {
+      const std::string k = "<" + std::to_string(op) + ", ";
+      if (l.find("exb_uni" + k) != std::string::npos || l.find("exb_f1" + k) != std::string::npos) return true;
+    }
+  return false;
+}
+// A value / derivative function of a pattern: `NAME_t<SLOW>` holds the body; NAME evaluates the fast form and, when some
+// transcendental argument was out of its fast range (rare: |a| >= 2^31, |x| >= 708, inf, nan), re-evaluates the point
+// through the __noinline__ NAME_slow built on libdevice's full-range routines.  `ns` = 0: returns double; else writes s[ns].
+inline void emit_eval_fn(std::ostringstream& o, const std::string& name, const std::string& params, const std::string& args, int ns,
+                         const Body& B, const std::vector<std::string>& tail) {
+  const std::string ret = ns == 0 ? "double" : "void";
+  const std::string sp = ns == 0 ? "" : ", double (&s)[" + std::to_string(ns) + "]";
+  o << "  template <bool SLOW> __device__ static __forceinline__ " << ret << " " << name << "_t(" << params << sp << ", bool& bad) {\n";
+  for (auto& l : B.lines) o << "    " << l << "\n";
+  for (auto& l : tail) o << "    " << l << "\n";
+  o << "  }\n";
+  const bool fast = body_uses_fast(B);
+  if (fast) {
+    if (ns == 0) o << "  __device__ static __noinline__ double " << name << "_slow(" << params << ") { bool bad = false; return " << name << "_t<true>(" << args << ", bad); }\n";
+    else o << "  __device__ static __noinline__ void " << name << "_slow(" << params << ", double* __restrict__ so) { bool bad = false; double s[" << ns << "]; "
+           << name << "_t<true>(" << args << ", s, bad); for (int j = 0; j < " << ns << "; j++) so[j] = s[j]; }\n";
+  }
+  o << "  __device__ static __forceinline__ " << ret << " " << name << "(" << params << sp << ") {\n    bool bad = false;\n";
+  if (ns == 0) {
+    o << "    double r = " << name << "_t<false>(" << args << ", bad);\n";
+    if (fast) o << "    if (bad) r = " << name << "_slow(" << args << ");\n";
+    o << "    return r;\n";
+  } else {
+    o << "    " << name << "_t<false>(" << args << ", s, bad);\n";
+    if (fast) o << "    if (bad) { double q[" << ns << "]; " << name << "_slow(" << args << ", q); for (int j = 0; j < " << ns << "; j++) s[j] = q[j]; }\n";
+  }
   o << "  }\n";
 }
 
@@ -615,7 +653,7 @@ inline std::string gen_pattern(PatternPlan& p, int index) {
   {  // val
     Body B; Gen g(p, B, 0);
     NV& r = g.fwd(p.ir.root);
-    emit_fn(o, "double val(" + A + ", const double* __restrict__ x, const double* __restrict__ th)", B, {"return " + r.x.s + ";"});
+    emit_eval_fn(o, "val", A + ", const double* __restrict__ x, const double* __restrict__ th", "pa, kg, x, th", 0, B, {"return " + r.x.s + ";"});
     p.ppt0 = ppt_for(body_weight(B), 1);
   }
   {  // d1
@@ -627,7 +665,7 @@ inline std::string gen_pattern(PatternPlan& p, int index) {
       g.rpass1(p.ir.root, K(1));
       for (int j = 0; j < ns1; j++) tail.push_back("s[" + std::to_string(j) + "] = " + g.slot[(size_t)j].s + ";");
     }
-    emit_fn(o, "void d1(" + A + ", const double* __restrict__ x, const double* __restrict__ th, double (&s)[" + std::to_string(a1) + "])", B, tail);
+    emit_eval_fn(o, "d1", A + ", const double* __restrict__ x, const double* __restrict__ th", "pa, kg, x, th", a1, B, tail);
     p.ppt1 = ppt_for(body_weight(B), a1);
     // Owner-computes gradient: objective over a range iterator whose slots all address x[t + const].  Variable v
     // then receives exactly slot j of point t = v - shift1[j] (if that point exists), so ONE thread per variable
@@ -651,11 +689,14 @@ inline std::string gen_pattern(PatternPlan& p, int index) {
       for (int j = 0; j < ns1; j++) ord[(size_t)j] = j;
       std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return p.shift1[(size_t)a] > p.shift1[(size_t)b]; });
       o << "  __device__ static __forceinline__ double g1(const ExbPatArgs& pa, const long long v, const double* __restrict__ x, const double* __restrict__ th) {\n";
-      o << "    double acc = 0.0;\n";
+      // branch-free: an out-of-range point is replaced by the pattern's first local point and its slot discarded, so the
+      // loads of every slot are issued up front (the kernel is latency-bound: ~10 flops per 8-byte word)
+      o << "    double acc = 0.0;\n    if (pa.n > 0) {\n";
       for (int j : ord) {
-        o << "    { const long long kg = v - (" << Gen::ilit(p.shift1[(size_t)j]) << ") - pa.start;\n"
-          << "      if (kg >= pa.k0 && kg < pa.k0 + pa.n) { double s[" << a1 << "]; d1(pa, kg, x, th, s); acc += s[" << j << "]; } }\n";
+        o << "      { const long long kg = v - (" << Gen::ilit(p.shift1[(size_t)j]) << ") - pa.start; const bool in = kg >= pa.k0 && kg < pa.k0 + pa.n;\n"
+          << "        double s[" << a1 << "]; d1(pa, in ? kg : pa.k0, x, th, s); acc += in ? s[" << j << "] : 0.0; }\n";
       }
+      o << "    }\n";
       o << "    return acc;\n  }\n";
     }
   }
@@ -668,7 +709,7 @@ inline std::string gen_pattern(PatternPlan& p, int index) {
       g.hrpass0(p.ir.root, Sym("a0"), K(0));
       for (int j = 0; j < ns2; j++) tail.push_back("s[" + std::to_string(j) + "] = " + g.slot[(size_t)j].s + ";");
     }
-    emit_fn(o, "void d2(" + A + ", const double* __restrict__ x, const double* __restrict__ th, const double a0, double (&s)[" + std::to_string(a2) + "])", B, tail);
+    emit_eval_fn(o, "d2", A + ", const double* __restrict__ x, const double* __restrict__ th, const double a0", "pa, kg, x, th, a0", a2, B, tail);
     p.ppt2 = ppt_for(body_weight(B), a2);
   }
   {  // s1: variable index per first-order slot (jacobian.jl:69-83)

@@ -58,7 +58,7 @@ def test_gradient_kernel_choice():
     assert "exb_ggrad_g0" in lv and "exb_sgrad_g0" not in lv
     # slot order for variable v: point v (slot of x[i]) before point v + 1 (slot of x[i-1]) = ascending slot number
     g1 = lv[lv.index("double g1("):]
-    assert g1.index("acc += s[1]") < g1.index("acc += s[0]")
+    assert g1.index("s[1] : 0.0") < g1.index("s[0] : 0.0")
     fam = E.Plan(M.pattern_family(100, 8)).source()
     assert "exb_sgrad_g0" in fam and "exb_ggrad_g0" not in fam
 
