@@ -71,6 +71,17 @@ std::string nvcc_path() {
   return "nvcc";
 }
 
+// development knob: EXB_TUNE_DEFS="A,B" prepends `#define A 1` ... to the generated module (part of its hash)
+std::string extra_defs() {
+  std::string out;
+  const char* e = getenv("EXB_TUNE_DEFS");
+  if (!e) return out;
+  std::stringstream ss(e);
+  std::string tok;
+  while (std::getline(ss, tok, ',')) if (!tok.empty()) out += "#define " + tok + " 1\n";
+  return out;
+}
+
 // ---- driver entry points (no link-time dependency on libcuda) ---------------------------
 struct Drv {
   CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
@@ -165,11 +176,11 @@ int make_plan(const void* ir, size_t bytes, exb_plan** out) {
   if (getenv("EXB_TUNE_MINB")) minbs = {p->pl.minb};
   std::string d = cache_dir();
   char buf[32];
-  snprintf(buf, sizeof buf, "%016llx", (unsigned long long)fnv1a(NVCC_FLAGS_CLEAN, fnv1a(std::string(exb_device_header_text) + p->pl.source + std::to_string(p->pl.block))));
+  snprintf(buf, sizeof buf, "%016llx", (unsigned long long)fnv1a(NVCC_FLAGS_CLEAN, fnv1a(std::string(exb_device_header_text) + extra_defs() + p->pl.source + std::to_string(p->pl.block))));
   p->hash = buf;
   for (int mb : minbs) {
     Variant v; v.minb = mb;
-    v.source = "#define EXB_BLOCK " + std::to_string(p->pl.block) + "\n#define EXB_MINB " + std::to_string(mb) + "\n" +
+    v.source = "#define EXB_BLOCK " + std::to_string(p->pl.block) + "\n#define EXB_MINB " + std::to_string(mb) + "\n" + extra_defs() +
                (p->pl.idx32 ? "#define EXB_IDX32 1\n" : "") +
                ((int)p->pl.pats.size() <= exb::EXB_CPAT_MAX && !p->pl.pats.empty() ? "#define EXB_NPAT " + std::to_string(p->pl.pats.size()) + "\n" : std::string()) +
                std::string(exb_device_header_text) + "\n" + p->pl.source;
