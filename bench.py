@@ -156,6 +156,7 @@ def main():
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's own log lines (version banner) must not precede the JSON line on stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     E.build_library()
 

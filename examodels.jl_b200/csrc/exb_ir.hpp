@@ -21,10 +21,15 @@ enum {
   U_EXPM1, U_LOG, U_LOG2, U_LOG1P, U_LOG10, U_SIN, U_COS, U_TAN, U_ASIN, U_ACOS, U_ATAN,
   U_ACOT, U_CSC, U_SEC, U_COT, U_SINH, U_COSH, U_TANH, U_ASINH, U_ACOSH, U_CSCH, U_SECH,
   U_COTH, U_SIND, U_COSD, U_TAND, U_CSCD, U_SECD, U_COTD, U_ATAND, U_ACOTD, U_SINPI,
-  U_COSPI, U_SINC, U_DEG2RAD, U_RAD2DEG, U_SIGNBIT, U_FLOOR, U_CEIL, U_ATANH, U_ACOTH, U_COUNT
+  U_COSPI, U_SINC, U_DEG2RAD, U_RAD2DEG, U_SIGNBIT, U_FLOOR, U_CEIL, U_ATANH, U_ACOTH,
+  // SpecialFunctions extension: order of /root/reference/ext/functionlist.jl:6-104
+  U_ERF, U_ERFC, U_ERFI, U_ERFCX, U_DIGAMMA, U_TRIGAMMA, U_INVDIGAMMA, U_GAMMA, U_AIRYAI, U_AIRYBI, U_AIRYAIPRIME,
+  U_AIRYBIPRIME, U_BESSELJ0, U_BESSELY0, U_BESSELJ1, U_BESSELY1, U_DAWSON, U_ERFINV, U_ERFCINV, U_COUNT
 };
 // bivariate op codes: order of /root/reference/src/functionlist.jl:71-81
-enum { B_ADD, B_SUB, B_MUL, B_DIV, B_POW, B_ATAN, B_HYPOT, B_MAX, B_MIN, B_COUNT };
+enum { B_ADD, B_SUB, B_MUL, B_DIV, B_POW, B_ATAN, B_HYPOT, B_MAX, B_MIN,
+       B_BETA, B_LOGBETA,   // SpecialFunctions extension: ext/functionlist.jl:111-126
+       B_COUNT };
 
 struct IRNode { i64 tag, a, b, payload; };
 struct Field { i64 off, type; };

@@ -34,8 +34,14 @@ UNIVARIATE = [
     "csch", "sech", "coth", "sind", "cosd", "tand", "cscd", "secd", "cotd", "atand",
     "acotd", "sinpi", "cospi", "sinc", "deg2rad", "rad2deg", "signbit", "floor",
     "ceil", "atanh", "acoth",
+    # SpecialFunctions extension, order of /root/reference/ext/functionlist.jl:6-104
+    "erf", "erfc", "erfi", "erfcx", "digamma", "trigamma", "invdigamma", "gamma", "airyai", "airybi",
+    "airyaiprime", "airybiprime", "besselj0", "bessely0", "besselj1", "bessely1", "dawson", "erfinv", "erfcinv",
 ]
-BIVARIATE = ["+", "-", "*", "/", "^", "atan", "hypot", "max", "min"]
+SPECIAL_UNIVARIATE = UNIVARIATE[UNIVARIATE.index("erf"):]
+BIVARIATE = ["+", "-", "*", "/", "^", "atan", "hypot", "max", "min",
+             "beta", "logbeta"]  # ext/functionlist.jl:111-126
+SPECIAL_BIVARIATE = ["beta", "logbeta"]
 OP1_CODE = {n: i for i, n in enumerate(UNIVARIATE)}
 OP2_CODE = {n: i for i, n in enumerate(BIVARIATE)}
 
@@ -304,8 +310,23 @@ _PYF2 = {
 }
 
 
+def _special_folds():
+    """Constant folding of the SpecialFunctions ops on the host (a Real argument is evaluated eagerly, register.jl:70)."""
+    import scipy.special as S
+    one = {"erf": S.erf, "erfc": S.erfc, "erfi": S.erfi, "erfcx": S.erfcx, "digamma": S.digamma,
+           "trigamma": lambda x: S.polygamma(1, x), "gamma": S.gamma, "airyai": lambda x: S.airy(x)[0],
+           "airybi": lambda x: S.airy(x)[2], "airyaiprime": lambda x: S.airy(x)[1], "airybiprime": lambda x: S.airy(x)[3],
+           "besselj0": S.j0, "bessely0": S.y0, "besselj1": S.j1, "bessely1": S.y1, "dawson": S.dawsn,
+           "erfinv": S.erfinv, "erfcinv": S.erfcinv}
+    return ({k: (lambda x, f=f: float(f(x))) for k, f in one.items()},
+            {"beta": lambda a, b: float(S.beta(a, b)), "logbeta": lambda a, b: float(S.betaln(a, b))})
+
+
 def _fold1(op, v):
     f = _PYF1.get(op)
+    if f is None and op in SPECIAL_UNIVARIATE and op != "invdigamma":
+        _PYF1.update(_special_folds()[0])
+        f = _PYF1.get(op)
     if f is None:
         raise NotImplementedError(f"constant folding of {op} is not available on the host")
     return f(v)
@@ -330,6 +351,8 @@ def _isone(c):
 def _op2(op, a, b):
     an, bn = isinstance(a, AbstractNode), isinstance(b, AbstractNode)
     if isinstance(a, Constant) and isinstance(b, Constant):  # register.jl:135
+        if op in SPECIAL_BIVARIATE and op not in _PYF2:
+            _PYF2.update(_special_folds()[1])
         return Constant(_PYF2[op](a.value, b.value))
     # Constant algebra, specialization.jl:311-339 (a Constant meeting a node)
     if an and bn:
@@ -376,6 +399,8 @@ def _op2(op, a, b):
         if not bn and not _is_real(b) and not isinstance(b, Val):
             return NotImplemented
         return Node2(op, a, b)
+    if op in SPECIAL_BIVARIATE and op not in _PYF2:
+        _PYF2.update(_special_folds()[1])
     return _PYF2[op](a, b)
 
 
@@ -433,6 +458,16 @@ for _n in UNIVARIATE:
         continue
     _g[_n if _n not in ("abs",) else "abs_"] = _make_unary(_n)
 abs_ = _g["abs_"]
+
+
+def beta(a, b):
+    """`SpecialFunctions.beta` (ext/functionlist.jl:111-118)."""
+    return _op2("beta", a, b)
+
+
+def logbeta(a, b):
+    """`SpecialFunctions.logbeta` (ext/functionlist.jl:119-126)."""
+    return _op2("logbeta", a, b)
 
 
 def atan2(a, b):

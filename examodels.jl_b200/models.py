@@ -269,15 +269,17 @@ def all_ops(n=64, part=0, seed=6):
     d["i"] = np.arange(1, n + 1)
     d["a"] = rng.uniform(1.1, 1.9, n)
     big = {"acosh", "acoth"}                      # need |arg| > 1
-    # three parts keep each generated module small (compile time grows quickly with the pattern count)
-    uni = G.UNIVARIATE[:26] if part == 0 else G.UNIVARIATE[26:] if part == 1 else []
+    # parts keep each generated module small (compile time grows quickly with the pattern count); part 3 is the
+    # SpecialFunctions extension (ext/functionlist.jl): 19 univariate + 2 bivariate operators
+    nb = G.UNIVARIATE.index("erf")
+    uni = G.UNIVARIATE[:26] if part == 0 else G.UNIVARIATE[26:nb] if part == 1 else G.UNIVARIATE[nb:] if part == 3 else []
     for name in uni:
         f = (lambda z, nm=name: G._op1(nm, z))
         if name in big:
             c.add_con(lambda p, f=f: f(p.a + x[p.i] * x[p.i + 1]) * x[p.i], d)
         else:
             c.add_con(lambda p, f=f: f(x[p.i] * x[p.i + 1]) * x[p.i] + p.a, d)
-    for name in (G.BIVARIATE if part == 2 else []):
+    for name in ([b for b in G.BIVARIATE if b not in G.SPECIAL_BIVARIATE] if part == 2 else G.SPECIAL_BIVARIATE if part == 3 else []):
         f = (lambda u, v, nm=name: G._op2(nm, u, v))
         c.add_con(lambda p, f=f: f(x[p.i] + 0.5, x[p.i + 1] * p.a) * x[p.i], d)       # node, node
         c.add_con(lambda p, f=f: f(x[p.i] * x[p.i + 1] + 0.5, p.a) * x[p.i + 1], d)   # node, Real

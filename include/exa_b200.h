@@ -53,6 +53,10 @@
  *              9 VAL(payload)   -- Val{p} exponent (specialization.jl:199-202)
  *   OP1 codes follow the order of src/functionlist.jl:6-60 (0 '+', 1 '-', 2 inv, ...),
  *   OP2 codes the order of src/functionlist.jl:71-81 (+ - * / ^ atan hypot max min).
+ *   The SpecialFunctions extension (ext/functionlist.jl:6-126) continues both tables in its
+ *   registration order: OP1 52.. erf erfc erfi erfcx digamma trigamma invdigamma gamma airyai
+ *   airybi airyaiprime airybiprime besselj0 bessely0 besselj1 bessely1 dawson erfinv erfcinv;
+ *   OP2 9 beta, 10 logbeta.
  *   Children precede parents.
  * ============================================================================= */
 #ifndef EXA_B200_H

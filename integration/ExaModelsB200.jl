@@ -34,6 +34,12 @@ check(rc) = rc == 0 || error("libexa_b200: ", unsafe_string(ccall((:exb_last_err
 # ---- IR emitter: walks the TYPE + fields of each pattern's tree (SURVEY.md Appendix A) -------------
 const OP1 = Dict(f => i - 1 for (i, f) in enumerate(first.(ExaModels._UNIVARIATES)))   # src/functionlist.jl:6-60
 const OP2 = Dict(f => i - 1 for (i, f) in enumerate(first.(ExaModels._BIVARIATES)))    # src/functionlist.jl:71-81
+# SpecialFunctions extension (ext/functionlist.jl:6-126): codes continue after the base tables, in registration order
+for (k, f) in enumerate((:erf, :erfc, :erfi, :erfcx, :digamma, :trigamma, :invdigamma, :gamma, :airyai, :airybi, :airyaiprime,
+                         :airybiprime, :besselj0, :bessely0, :besselj1, :bessely1, :dawson, :erfinv, :erfcinv))
+    OP1[f] = length(ExaModels._UNIVARIATES) + k - 1
+end
+OP2[:beta] = length(ExaModels._BIVARIATES); OP2[:logbeta] = length(ExaModels._BIVARIATES) + 1
 const T_CONST_I, T_CONST_F, T_DATA_SELF, T_DATA_FIELD, T_VAR, T_PAR, T_NULL, T_OP1, T_OP2, T_VAL = 0:9
 
 mutable struct Emitter

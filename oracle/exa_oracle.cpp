@@ -47,10 +47,15 @@ enum {
   U_EXPM1, U_LOG, U_LOG2, U_LOG1P, U_LOG10, U_SIN, U_COS, U_TAN, U_ASIN, U_ACOS, U_ATAN,
   U_ACOT, U_CSC, U_SEC, U_COT, U_SINH, U_COSH, U_TANH, U_ASINH, U_ACOSH, U_CSCH, U_SECH,
   U_COTH, U_SIND, U_COSD, U_TAND, U_CSCD, U_SECD, U_COTD, U_ATAND, U_ACOTD, U_SINPI,
-  U_COSPI, U_SINC, U_DEG2RAD, U_RAD2DEG, U_SIGNBIT, U_FLOOR, U_CEIL, U_ATANH, U_ACOTH, U_COUNT
+  U_COSPI, U_SINC, U_DEG2RAD, U_RAD2DEG, U_SIGNBIT, U_FLOOR, U_CEIL, U_ATANH, U_ACOTH,
+  // SpecialFunctions extension: order of /root/reference/ext/functionlist.jl:6-104
+  U_ERF, U_ERFC, U_ERFI, U_ERFCX, U_DIGAMMA, U_TRIGAMMA, U_INVDIGAMMA, U_GAMMA, U_AIRYAI, U_AIRYBI, U_AIRYAIPRIME,
+  U_AIRYBIPRIME, U_BESSELJ0, U_BESSELY0, U_BESSELJ1, U_BESSELY1, U_DAWSON, U_ERFINV, U_ERFCINV, U_COUNT
 };
 // bivariate op codes: order of src/functionlist.jl:71-81
-enum { B_ADD, B_SUB, B_MUL, B_DIV, B_POW, B_ATAN, B_HYPOT, B_MAX, B_MIN, B_COUNT };
+enum { B_ADD, B_SUB, B_MUL, B_DIV, B_POW, B_ATAN, B_HYPOT, B_MAX, B_MIN,
+       B_BETA, B_LOGBETA,   // SpecialFunctions extension: ext/functionlist.jl:111-126
+       B_COUNT };
 
 struct IRNode { i64 tag, a, b, payload; };
 struct Field { i64 off, type; };
@@ -131,6 +136,151 @@ inline double jl_sinc(double x) { return x == 0.0 ? 1.0 : jl_sinpi(x) / (PI * x)
 inline double jl_sign(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : x); }
 const double LOG2 = 0.69314718055994530942, LOG10 = 2.30258509299404568402;
 const double D2R = PI / 180.0;
+
+
+// ---- SpecialFunctions extension (ext/functionlist.jl; values from SpecialFunctions.jl / openspecfun, a third-party
+// dependency that is not vendored: published algorithms restated in extended precision, independently of the device
+// code in examodels.jl_b200/csrc/exb_special.h, and pinned against scipy / mpmath in tests/test_special_functions.py) ----
+typedef long double ld;
+const ld PIl = 3.14159265358979323846264338327950288L;
+inline ld sinpil_(ld x) { ld r = fmodl(x, 2.0L); return sinl(PIl * r); }
+inline ld cospil_(ld x) { ld r = fmodl(x, 2.0L); return cosl(PIl * r); }
+// psi^(n)(x), n = 0..3, x > 0: recurrence up to x >= 30, then the asymptotic series with Bernoulli numbers B_2..B_20
+ld polygamma_pos(int n, ld x) {
+  static const ld B[10] = {1.0L / 6, -1.0L / 30, 1.0L / 42, -1.0L / 30, 5.0L / 66, -691.0L / 2730, 7.0L / 6, -3617.0L / 510, 43867.0L / 798, -174611.0L / 330};
+  ld r = 0.0L;
+  const ld fact[4] = {1.0L, 1.0L, 2.0L, 6.0L};
+  while (x < 30.0L) {
+    if (n == 0) r -= 1.0L / x; else r += ((n & 1) ? 1.0L : -1.0L) * fact[n] / powl(x, n + 1);
+    x += 1.0L;
+  }
+  ld s;
+  if (n == 0) {
+    s = logl(x) - 0.5L / x;
+    for (int k = 1; k <= 10; k++) s -= B[k - 1] / (2.0L * k * powl(x, 2 * k));
+  } else {
+    // (-1)^(n+1) [ (n-1)!/x^n + n!/(2 x^(n+1)) + sum_k B_2k (2k+n-1)!/((2k)! x^(2k+n)) ]
+    s = fact[n - 1] / powl(x, n) + fact[n] / (2.0L * powl(x, n + 1));
+    for (int k = 1; k <= 10; k++) {
+      ld c = 1.0L;                                   // (2k+n-1)! / (2k)!
+      for (int j = 2 * k + 1; j <= 2 * k + n - 1; j++) c *= j;
+      s += B[k - 1] * c / powl(x, 2 * k + n);
+    }
+    if (!(n & 1)) s = -s;
+  }
+  return r + s;
+}
+ld polygamma_l(int n, ld x) {
+  if (x > 0.0L) return polygamma_pos(n, x);
+  const ld sn = sinpil_(x), cs = cospil_(x), ct = cs / sn, c2 = 1.0L / (sn * sn);   // reflection about 1 - x
+  switch (n) {
+    case 0: return polygamma_pos(0, 1.0L - x) - PIl * ct;
+    case 1: return -polygamma_pos(1, 1.0L - x) + PIl * PIl * c2;
+    case 2: return polygamma_pos(2, 1.0L - x) - 2.0L * PIl * PIl * PIl * ct * c2;
+    default: return -polygamma_pos(3, 1.0L - x) + 2.0L * PIl * PIl * PIl * PIl * c2 * (2.0L * ct * ct + c2);
+  }
+}
+double sf_digamma(double x) { return (double)polygamma_l(0, x); }
+double sf_trigamma(double x) { return (double)polygamma_l(1, x); }
+double sf_polygamma(int n, double x) { return (double)polygamma_l(n, x); }
+double sf_invdigamma(double y) {   // Minka's iteration (SpecialFunctions.jl invdigamma)
+  ld xo = y >= -2.22 ? expl((ld)y) + 0.5L : -1.0L / ((ld)y + 0.57721566490153286060651209L);
+  for (int it = 0; it < 40; it++) {
+    ld xn = xo - (polygamma_l(0, xo) - (ld)y) / polygamma_l(1, xo);
+    bool done = fabsl(xn - xo) <= 1e-17L * fabsl(xn);
+    xo = xn;
+    if (done) break;
+  }
+  return (double)xo;
+}
+// (sqrt(pi)/2) erfi(x) = sum x^(2k+1)/(k! (2k+1)); Dawson D(x) = e^{-x^2} * that; asymptotic series for |x| >= 8
+ld erfi_series_l(ld x) {
+  ld t = x, s = x;
+  for (int k = 1; k < 400; k++) { t *= x * x / k; ld a = t / (2 * k + 1); s += a; if (fabsl(a) < 1e-22L * fabsl(s)) break; }
+  return s;
+}
+ld dawson_asym_l(ld x) {
+  ld q = 1.0L / (2.0L * x * x), t = 1.0L, s = 1.0L;
+  for (int k = 1; k < 200; k++) { ld tn = t * (2 * k - 1) * q; if (fabsl(tn) >= fabsl(t) || fabsl(tn) < 1e-24L) break; t = tn; s += t; }
+  return s / (2.0L * x);
+}
+double sf_dawson(double x) { return fabs(x) < 8.0 ? (double)(expl(-(ld)x * x) * erfi_series_l(x)) : (double)dawson_asym_l(x); }
+double sf_erfi(double x) {
+  const ld c = 2.0L / sqrtl(PIl);
+  return fabs(x) < 8.0 ? (double)(c * erfi_series_l(x)) : (double)(c * expl((ld)x * x) * dawson_asym_l(x));
+}
+double sf_erfcx(double x) {
+  if (x < 25.0) return (double)(expl((ld)x * x) * erfcl((ld)x));
+  ld q = 1.0L / (2.0L * (ld)x * x), t = 1.0L, s = 1.0L;   // 1/(x sqrt(pi)) sum (-1)^k (2k-1)!!/(2x^2)^k
+  for (int k = 1; k < 60; k++) { ld tn = -t * (2 * k - 1) * q; if (fabsl(tn) >= fabsl(t)) break; t = tn; s += t; }
+  return (double)(s / ((ld)x * sqrtl(PIl)));
+}
+double sf_erfinv(double y) {       // Newton on erf in extended precision from a rational start (Winitzki)
+  if (!(y > -1.0 && y < 1.0)) return y == 1.0 ? INFINITY : y == -1.0 ? -INFINITY : NAN;
+  const ld a = 0.147L, l = logl(1.0L - (ld)y * y), t = 2.0L / (PIl * a) + l / 2.0L;
+  ld x = sqrtl(sqrtl(t * t - l / a) - t); if (y < 0) x = -x;
+  for (int it = 0; it < 60; it++) { ld dx = (erfl(x) - (ld)y) / (2.0L / sqrtl(PIl) * expl(-x * x)); x -= dx; if (fabsl(dx) <= 1e-19L * fabsl(x)) break; }
+  return (double)x;
+}
+double sf_erfcinv(double y) {      // Newton on erfc (keeps relative accuracy for small y)
+  if (!(y > 0.0 && y < 2.0)) return y == 0.0 ? INFINITY : y == 2.0 ? -INFINITY : NAN;
+  ld x = y >= 0.25 && y <= 1.75 ? (ld)sf_erfinv(1.0 - y) : (y < 1 ? 1.0L : -1.0L) * sqrtl(-logl((y < 1 ? (ld)y : 2.0L - (ld)y)));
+  for (int it = 0; it < 80; it++) { ld dx = (erfcl(x) - (ld)y) / (-2.0L / sqrtl(PIl) * expl(-x * x)); x -= dx; if (fabsl(dx) <= 1e-19L * fabsl(x)) break; }
+  return (double)x;
+}
+// Airy: Maclaurin series in QUAD precision (__float128: the series cancels ~e^{2 zeta} for x > 0) for |x| <= 9 --
+// Ai = c1 f - c2 g, Bi = sqrt(3)(c1 f + c2 g) -- else the Poincare asymptotic series (its truncation error e^{-2 zeta} is
+// below 1e-15 there).  Independent of the device path's tabulated Taylor expansion.
+void airy_l(ld x, ld& ai, ld& aip, ld& bi, ld& bip) {
+  if (fabsl(x) <= 9.0L) {
+    typedef __float128 qd;
+    const qd c1 = 0.355028053887817239260063186004183176Q, c2 = 0.258819403792806798405183560189203963Q,
+             s3 = 1.732050807568877293527446341505872367Q;
+    // f = sum a_k, a_0 = 1, a_k = a_{k-1} x^3 / ((3k-1)(3k)); g = sum b_k, b_0 = x, b_k = b_{k-1} x^3 / ((3k)(3k+1));
+    // f' = sum 3k a_k / x, g' = sum (3k+1) b_k / x  (accumulated as series in x^2 to stay finite at x = 0)
+    const qd xq = x, x3 = xq * xq * xq;
+    qd a = 1.0Q, b = xq, f = 1.0Q, g = xq, ap = 0.0Q, bp = 1.0Q, fp = 0.0Q, gp = 1.0Q;   // ap = a_k' , bp = b_k'
+    for (int k = 1; k < 400; k++) {
+      // a_k' = a_{k-1}' x^3/((3k-1)3k) * (3k)/(3k-3)  for k >= 2; a_1' = x^2/2
+      ap = k == 1 ? xq * xq / 2.0Q : ap * x3 / ((3.0Q * k - 1) * (3.0Q * k - 3));
+      bp = bp * x3 / ((3.0Q * k) * (3.0Q * k - 2));          // b_k' = x^(3k) / prod: (3k+1) b_k / x
+      a *= x3 / ((3.0Q * k - 1) * (3.0Q * k)); b *= x3 / ((3.0Q * k) * (3.0Q * k + 1));
+      f += a; g += b; fp += ap; gp += bp;
+      const qd ta = a < 0 ? -a : a, tb = b < 0 ? -b : b, tf = f < 0 ? -f : f, tg = g < 0 ? -g : g;
+      if (k > 3 && ta <= 1e-40Q * (tf + 1e-300Q) && tb <= 1e-40Q * (tg + 1e-300Q)) break;
+    }
+    ai = (ld)(c1 * f - c2 * g); aip = (ld)(c1 * fp - c2 * gp); bi = (ld)(s3 * (c1 * f + c2 * g)); bip = (ld)(s3 * (c1 * fp + c2 * gp));
+    return;
+  }
+  const ld z = fabsl(x), z14 = sqrtl(sqrtl(z)), zeta = 2.0L / 3.0L * z * sqrtl(z), sp = sqrtl(PIl);
+  ld u[16], v[16]; u[0] = v[0] = 1.0L;
+  for (int k = 1; k < 16; k++) { u[k] = u[k - 1] * (6.0L * k - 5) * (6.0L * k - 3) * (6.0L * k - 1) / ((2.0L * k - 1) * 216.0L * k); v[k] = u[k] * (6.0L * k + 1) / (1.0L - 6.0L * k); }
+  // sums truncated at the smallest term
+  if (x > 0) {
+    ld sa = 0, sap = 0, sb = 0, sbp = 0, p = 1.0L, sg = 1.0L, last = 1e300L;
+    for (int k = 0; k < 16; k++) { ld t = u[k] * p; if (fabsl(t) > last) break; last = fabsl(t); sa += sg * t; sb += t; sap += sg * v[k] * p; sbp += v[k] * p; p /= zeta; sg = -sg; }
+    ai = expl(-zeta) / (2.0L * sp * z14) * sa; aip = -z14 * expl(-zeta) / (2.0L * sp) * sap;
+    bi = expl(zeta) / (sp * z14) * sb; bip = z14 * expl(zeta) / sp * sbp;
+  } else {
+    ld pe = 0, po = 0, qe = 0, qo = 0, p = 1.0L, last = 1e300L;
+    for (int k = 0; k + 1 < 16; k += 2) {
+      ld t = u[k] * p; if (fabsl(t) > last) break; last = fabsl(t);
+      ld sg = (k & 2) ? -1.0L : 1.0L;
+      pe += sg * u[k] * p; qe += sg * v[k] * p; p /= zeta;
+      po += sg * u[k + 1] * p; qo += sg * v[k + 1] * p; p /= zeta;
+    }
+    ld th = zeta - PIl / 4.0L, c = cosl(th), sn = sinl(th);
+    ai = (c * pe + sn * po) / (sp * z14); aip = z14 / sp * (sn * qe - c * qo);
+    bi = (-sn * pe + c * po) / (sp * z14); bip = z14 / sp * (c * qe + sn * qo);
+  }
+}
+double sf_airy(double x, int which) { ld a, ap, b, bp; airy_l(x, a, ap, b, bp); return (double)(which == 0 ? a : which == 1 ? ap : which == 2 ? b : bp); }
+double sf_logbeta(double a, double b) { return (double)(lgammal(a) + lgammal(b) - lgammal((ld)a + b)); }
+double sf_beta(double a, double b) {
+  if (a > 0 && b > 0) return (double)expl(lgammal(a) + lgammal(b) - lgammal((ld)a + b));
+  return (double)(tgammal(a) * tgammal(b) / tgammal((ld)a + b));
+}
+const double INVSQRTPI = 0.56418958354775628695, SQRTPIHALF = 0.88622692545275801365;   // _cinvsqrtpi, _csqrtpihalf (ext/ExaModelsSpecialFunctions.jl:6-8)
 
 // ---- univariate table: f, f', f''  (src/functionlist.jl:6-60, formulas kept literally) -----
 void uni(int op, double x, double& f, double& d, double& dd, int order) {
@@ -225,6 +375,30 @@ void uni(int op, double x, double& f, double& d, double& dd, int order) {
     case U_ACOTH: f = std::atanh(1.0 / x);
       if (order) { if (std::fabs(x) < 1.0) { d = NAN; dd = NAN; }
         else { double iv = 1.0 / (1.0 - sq(x)); d = iv; dd = (-sq(iv)) * (-2.0 * x); } } break; // :59
+    // ---- SpecialFunctions extension: ext/functionlist.jl:6-104, formulas kept literally ----
+    case U_ERF: f = std::erf(x); if (order) { d = (2 * INVSQRTPI) * std::exp(-sq(x)); dd = -(4 * INVSQRTPI) * x * std::exp(-sq(x)); } break;       // ext:6-10
+    case U_ERFC: f = std::erfc(x); if (order) { d = -(2 * INVSQRTPI) * std::exp(-sq(x)); dd = (4 * INVSQRTPI) * x * std::exp(-sq(x)); } break;    // ext:11-15
+    case U_ERFI: f = sf_erfi(x); if (order) { d = (2 * INVSQRTPI) * std::exp(sq(x)); dd = (4 * INVSQRTPI) * x * std::exp(sq(x)); } break;          // ext:16-20
+    case U_ERFCX: f = sf_erfcx(x); if (order) { d = 2 * (-INVSQRTPI + x * f); dd = 2 * (f + 2 * x * (-INVSQRTPI + x * f)); } break;                // ext:21-25
+    case U_DIGAMMA: f = sf_digamma(x); if (order) { d = sf_trigamma(x); dd = sf_polygamma(2, x); } break;                                          // ext:26-30
+    case U_TRIGAMMA: f = sf_trigamma(x); if (order) { d = sf_polygamma(2, x); dd = sf_polygamma(3, x); } break;                                    // ext:31-35
+    case U_INVDIGAMMA: f = sf_invdigamma(x);
+      if (order) { d = 1 / sf_trigamma(f); dd = (-sf_polygamma(2, f)) / cube(sf_trigamma(f)); } break;                                             // ext:36-40
+    case U_GAMMA: f = std::tgamma(x);
+      if (order) { d = f * sf_digamma(x); dd = f * (sf_trigamma(x) + sq(sf_digamma(x))); } break;                                                  // ext:41-45
+    case U_AIRYAI: f = sf_airy(x, 0); if (order) { d = sf_airy(x, 1); dd = x * f; } break;                                                         // ext:46-50
+    case U_AIRYBI: f = sf_airy(x, 2); if (order) { d = sf_airy(x, 3); dd = x * f; } break;                                                         // ext:51-55
+    case U_AIRYAIPRIME: f = sf_airy(x, 1); if (order) { d = x * sf_airy(x, 0); dd = sf_airy(x, 0) + x * f; } break;                                // ext:56-60
+    case U_AIRYBIPRIME: f = sf_airy(x, 3); if (order) { d = x * sf_airy(x, 2); dd = sf_airy(x, 2) + x * f; } break;                                // ext:61-65
+    case U_BESSELJ0: f = ::j0(x); if (order) { d = -::j1(x); dd = (-f + ::jn(2, x)) / 2; } break;                                                  // ext:66-70
+    case U_BESSELY0: f = ::y0(x); if (order) { d = -::y1(x); dd = (-f + ::yn(2, x)) / 2; } break;                                                  // ext:71-75
+    case U_BESSELJ1: f = ::j1(x); if (order) { d = (::j0(x) - ::jn(2, x)) / 2; dd = ((-::jn(1, x) + ::jn(3, x)) / 2 - f) / 2; } break;             // ext:76-80
+    case U_BESSELY1: f = ::y1(x); if (order) { d = (::y0(x) - ::yn(2, x)) / 2; dd = ((::yn(3, x) - ::yn(1, x)) / 2 - f) / 2; } break;              // ext:81-85
+    case U_DAWSON: f = sf_dawson(x); if (order) { d = 1 - 2 * x * f; dd = -2 * f - 2 * x * (1 - 2 * x * f); } break;                               // ext:86-90
+    case U_ERFINV: f = sf_erfinv(x);
+      if (order) { d = SQRTPIHALF * std::exp(sq(f)); dd = SQRTPIHALF * std::exp(sq(f)) * 2 * f * SQRTPIHALF * std::exp(sq(f)); } break;            // ext:93-97
+    case U_ERFCINV: f = sf_erfcinv(x);
+      if (order) { d = -SQRTPIHALF * std::exp(sq(f)); dd = (PI / 2) * f * std::exp(2 * sq(f)); } break;                                            // ext:98-102
     default: f = d = dd = NAN;
   }
 }
@@ -277,6 +451,14 @@ void bi(int op, double x1, double x2, const Real& e1, const Real& e2, Bi& r, boo
       r.y1 = x1 > x2 ? 1.0 : 0.0; r.y2 = x1 > x2 ? 0.0 : 1.0; r.h11 = r.h12 = r.h22 = 0.0; break;
     case B_MIN: r.f = (x2 < x1 || std::isnan(x2)) ? x2 : x1;                                 // :80
       r.y1 = x1 < x2 ? 1.0 : 0.0; r.y2 = x1 < x2 ? 0.0 : 1.0; r.h11 = r.h12 = r.h22 = 0.0; break;
+    case B_BETA: { r.f = sf_beta(x1, x2);                                                          // ext:111-118
+      double p1 = sf_digamma(x1), p2 = sf_digamma(x2), p12 = sf_digamma(x1 + x2), t1 = sf_trigamma(x1), t2 = sf_trigamma(x2), t12 = sf_trigamma(x1 + x2);
+      r.y1 = r.f * (p1 - p12); r.y2 = r.f * (-p12 + p2);
+      r.h11 = r.f * (t1 - t12 + sq(p1 - p12)); r.h12 = -r.f * t12 + r.f * (p1 - p12) * (-p12 + p2); r.h22 = r.f * (-t12 + t2 + sq(-p12 + p2)); } break;
+    case B_LOGBETA: { r.f = sf_logbeta(x1, x2);                                                    // ext:119-126
+      double p12 = sf_digamma(x1 + x2), t12 = sf_trigamma(x1 + x2);
+      r.y1 = sf_digamma(x1) - p12; r.y2 = -p12 + sf_digamma(x2);
+      r.h11 = sf_trigamma(x1) - t12; r.h12 = -t12; r.h22 = -t12 + sf_trigamma(x2); } break;
     default: r.f = NAN;
   }
 }

@@ -31,6 +31,7 @@ def _models():
         "all_ops_0": lambda: M.all_ops(64, 0),
         "all_ops_1": lambda: M.all_ops(64, 1),
         "all_ops_2": lambda: M.all_ops(64, 2),
+        "all_ops_3_special": lambda: M.all_ops(64, 3),   # SpecialFunctions extension (ext/functionlist.jl)
     }
 
 
