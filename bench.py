@@ -285,9 +285,11 @@ def main():
     except Exception:
         peak = 6650.0
     traffic = None
+    choice = m.kernel_choice("hess")   # the first-call tuner's verdict: launch-shape variant, classic or persistent form
+    hess_kernel = "exb_hessp_g0" if choice["persistent"] else "exb_hess_g0"
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("exb_hess_g0")
+            traffic = json.load(f).get(hess_kernel)
     except Exception:
         pass
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
@@ -314,7 +316,7 @@ def main():
                    "l2": f"per step {alg_bytes / 1e6:.0f} MB of inputs+outputs > L2 ({L2_BYTES / 1e6:.0f} MB); no explicit flush",
                    "inputs": "x = x0 + 0.01 U(-1,1) seed 0; y ~ N(0,1) seed 1; obj_weight = 1"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "exb_hess_g0", "algorithmic_bytes_per_launch": alg_bytes,
+                     "traffic": traffic, "kernel": hess_kernel, "kernel_choice": choice, "algorithmic_bytes_per_launch": alg_bytes,
                      "kernel_ms": kernel_ms, "peak_source": peak_src},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 8 * (m.nvar + m.ncon) * world, "d2h_bytes_per_step": 8 * local_nnz * world,
                 "api": "exb_host_hess (C ABI, pinned host buffers)", "steps": e2e_steps, "finite": ok},

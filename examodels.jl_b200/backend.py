@@ -38,7 +38,7 @@ exb_obj_async exb_grad exb_cons exb_jac_structure64 exb_jac_structure32 exb_jac 
 exb_hess_structure32 exb_hess exb_host_obj exb_host_grad exb_host_cons exb_host_jac exb_host_hess
 exb_host_jac_structure64 exb_host_hess_structure64 exb_shard exb_stats exb_last_error exb_abi_version
 exb_jprod exb_jtprod exb_hprod exb_compressed_dims exb_jac_structure_compressed64 exb_hess_structure_compressed64
-exb_jac_compressed exb_hess_compressed exb_set_timing exb_timings""".split()
+exb_jac_compressed exb_hess_compressed exb_set_timing exb_timings exb_kernel_choice""".split()
 
 
 class ExbError(RuntimeError):
@@ -341,6 +341,12 @@ class ExaModel:
         _check(lib().exb_timings(self.h, _np_ptr(ms), _np_ptr(calls), 1 if reset else 0))
         names = ("obj", "grad", "cons", "jac", "hess", "jprod", "jtprod", "hprod")
         return {n: {"ms": float(m), "calls": int(c)} for n, m, c in zip(names, ms, calls)}
+
+    def kernel_choice(self, callback):
+        """Which generated kernel `callback` ('obj' | 'grad' | 'cons' | 'jac' | 'hess') launches (first-call tuner's verdict)."""
+        o = np.zeros(4, dtype=np.int64)
+        _check(lib().exb_kernel_choice(self.h, ("obj", "grad", "cons", "jac", "hess").index(callback), _np_ptr(o)))
+        return {"min_blocks": int(o[0]), "persistent": bool(o[1]), "grid": int(o[2]), "owner_computes": bool(o[3])}
 
     def stats(self):
         o = np.zeros(4, dtype=np.int64)

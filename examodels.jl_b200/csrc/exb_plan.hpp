@@ -55,6 +55,10 @@ struct PatternPlan {
   // t the value of a range iterator, so variable v receives slot j of point t = v - shift1[j] and nothing else
   bool gather1 = false;
   std::vector<i64> shift1;
+  // x window (persistent Hessian kernel): every variable index of the pattern is `t + c` with t the value of a range
+  // iterator and xlo <= c <= xhi, so a tile of consecutive points reads one contiguous window of x (and of y)
+  bool win = false;
+  i64 xlo = 0, xhi = 0;
 };
 
 struct Plan {
@@ -65,6 +69,7 @@ struct Plan {
   std::string error;
   // pattern lists per kernel (indices into pats), fixed at generation time
   std::vector<int> k_hess, k_jac, k_sgrad, k_ggrad, k_cons, k_obj, k_aug;
+  bool hess_windowed = false;  // every Hessian pattern has an x window: the persistent kernel exb_hessp_g0 is generated too
   bool idx32 = false;          // every index (variables, points, slots) fits 31 bits: address arithmetic in 32 bits
   int block = 128, minb = 16;  // launch shape of the generated kernels (tuning knobs: EXB_TUNE_BLOCK / EXB_TUNE_MINB)
 };
@@ -328,7 +333,10 @@ struct Gen {
     if (in.kind == K_VAR) {
       NV& ix = real((int)q.a);
       r.idx = ix.rs;
-      r.x = Sym(B.tmp("double", "__ldg(x + EXB_IX(" + ix.rs + " - 1))"));
+      // a variable at a FIXED index (e.g. a step length shared by every point) is outside any per-tile window of x
+      i64 cf = 1, ct = 0;
+      const bool fixed = affine_index(p.ir, (int)q.a, cf, ct) && cf == 0;
+      r.x = Sym(B.tmp("double", std::string(fixed ? "x.ldc(" : "x.ld(") + "EXB_IX(" + ix.rs + " - 1))"));
       return r;
     }
     if (q.tag == T_OP1) {
@@ -583,19 +591,20 @@ inline bool body_uses_fast(const Body& B) {
 // through the __noinline__ NAME_slow built on libdevice's full-range routines.  `ns` = 0: returns double; else writes s[ns].
 inline void emit_eval_fn(std::ostringstream& o, const std::string& name, const std::string& params, const std::string& args, int ns,
                          const Body& B, const std::vector<std::string>& tail) {
+  // XA = how x is read: ExbXG (global memory, __ldg) or ExbXS (the block's shared-memory window, exb_hessp_body)
   const std::string ret = ns == 0 ? "double" : "void";
   const std::string sp = ns == 0 ? "" : ", double (&s)[" + std::to_string(ns) + "]";
-  o << "  template <bool SLOW> __device__ static __forceinline__ " << ret << " " << name << "_t(" << params << sp << ", bool& bad) {\n";
+  o << "  template <bool SLOW, class XA> __device__ static __forceinline__ " << ret << " " << name << "_t(" << params << sp << ", bool& bad) {\n";
   for (auto& l : B.lines) o << "    " << l << "\n";
   for (auto& l : tail) o << "    " << l << "\n";
   o << "  }\n";
   const bool fast = body_uses_fast(B);
   if (fast) {
-    if (ns == 0) o << "  __device__ static __noinline__ double " << name << "_slow(" << params << ") { bool bad = false; return " << name << "_t<true>(" << args << ", bad); }\n";
-    else o << "  __device__ static __noinline__ void " << name << "_slow(" << params << ", double* __restrict__ so) { bool bad = false; double s[" << ns << "]; "
+    if (ns == 0) o << "  template <class XA> __device__ static __noinline__ double " << name << "_slow(" << params << ") { bool bad = false; return " << name << "_t<true>(" << args << ", bad); }\n";
+    else o << "  template <class XA> __device__ static __noinline__ void " << name << "_slow(" << params << ", double* __restrict__ so) { bool bad = false; double s[" << ns << "]; "
            << name << "_t<true>(" << args << ", s, bad); for (int j = 0; j < " << ns << "; j++) so[j] = s[j]; }\n";
   }
-  o << "  __device__ static __forceinline__ " << ret << " " << name << "(" << params << sp << ") {\n    bool bad = false;\n";
+  o << "  template <class XA> __device__ static __forceinline__ " << ret << " " << name << "(" << params << sp << ") {\n    bool bad = false;\n";
   if (ns == 0) {
     o << "    double r = " << name << "_t<false>(" << args << ", bad);\n";
     if (fast) o << "    if (bad) r = " << name << "_slow(" << args << ");\n";
@@ -606,7 +615,6 @@ inline void emit_eval_fn(std::ostringstream& o, const std::string& name, const s
   }
   o << "  }\n";
 }
-
 // Points per thread: cheap bodies are dominated by the per-block prologue / tile-store epilogue, so they get
 // several points per thread (also more loads in flight per thread); heavy bodies keep one.
 inline int body_weight(const Body& B) {
@@ -624,13 +632,31 @@ inline int ppt_for(int weight, int ns) {
   return p;
 }
 
-inline std::string gen_pattern(PatternPlan& p, int index) {
+// x window of a pattern (see PatternPlan::win)
+inline void compute_window(PatternPlan& p) {
+  p.win = p.ir.itr_kind == ITR_RANGE && p.ir.kind != KIND_AUG && p.o2step > 0;
+  bool first = true;
+  for (size_t q = 0; q < p.ir.nodes.size() && p.win; q++) {
+    if (p.ir.nodes[q].tag != T_VAR) continue;
+    i64 cf, ct;
+    if (!affine_index(p.ir, (int)p.ir.nodes[q].a, cf, ct) || (cf != 1 && cf != 0)) { p.win = false; break; }
+    if (cf == 0) continue;   // fixed index: read from global memory (ExbXS::ldc)
+    if (first || ct < p.xlo) p.xlo = ct;
+    if (first || ct > p.xhi) p.xhi = ct;
+    first = false;
+  }
+  if (first || p.xhi - p.xlo > 4096) p.win = false;
+}
+
+inline std::string gen_pattern(PatternPlan& p, int index, bool windowed) {
   std::ostringstream o;
   const int ns1 = p.o1step, ns2 = p.o2step;
   const int a1 = ns1 > 0 ? ns1 : 1, a2 = ns2 > 0 ? ns2 : 1;
   const std::string A = "const ExbPatArgs& pa, const long long kg";
   o << "struct P" << index << " {\n";
   o << "  static constexpr int INDEX = " << index << ", KIND = " << p.ir.kind << ", NS1 = " << ns1 << ", NS2 = " << ns2 << ";\n";
+  o << "  static constexpr bool WIN = " << (windowed ? "true" : "false") << "; static constexpr long long XLO = " << (windowed ? p.xlo : 0)
+    << ", XHI = " << (windowed ? p.xhi : 0) << ";\n";
   {  // row (offset0, nlp.jl:1980-2001; idxx :2012-2015)
     Body B; Gen g(p, B, 0);
     std::vector<std::string> tail;
@@ -653,7 +679,7 @@ inline std::string gen_pattern(PatternPlan& p, int index) {
   {  // val
     Body B; Gen g(p, B, 0);
     NV& r = g.fwd(p.ir.root);
-    emit_eval_fn(o, "val", A + ", const double* __restrict__ x, const double* __restrict__ th", "pa, kg, x, th", 0, B, {"return " + r.x.s + ";"});
+    emit_eval_fn(o, "val", A + ", const XA x, const double* __restrict__ th", "pa, kg, x, th", 0, B, {"return " + r.x.s + ";"});
     p.ppt0 = ppt_for(body_weight(B), 1);
   }
   {  // d1
@@ -665,7 +691,7 @@ inline std::string gen_pattern(PatternPlan& p, int index) {
       g.rpass1(p.ir.root, K(1));
       for (int j = 0; j < ns1; j++) tail.push_back("s[" + std::to_string(j) + "] = " + g.slot[(size_t)j].s + ";");
     }
-    emit_eval_fn(o, "d1", A + ", const double* __restrict__ x, const double* __restrict__ th", "pa, kg, x, th", a1, B, tail);
+    emit_eval_fn(o, "d1", A + ", const XA x, const double* __restrict__ th", "pa, kg, x, th", a1, B, tail);
     p.ppt1 = ppt_for(body_weight(B), a1);
     // Owner-computes gradient: objective over a range iterator whose slots all address x[t + const].  Variable v
     // then receives exactly slot j of point t = v - shift1[j] (if that point exists), so ONE thread per variable
@@ -688,7 +714,7 @@ inline std::string gen_pattern(PatternPlan& p, int index) {
       std::vector<int> ord((size_t)ns1);
       for (int j = 0; j < ns1; j++) ord[(size_t)j] = j;
       std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return p.shift1[(size_t)a] > p.shift1[(size_t)b]; });
-      o << "  __device__ static __forceinline__ double g1(const ExbPatArgs& pa, const long long v, const double* __restrict__ x, const double* __restrict__ th) {\n";
+      o << "  __device__ static __forceinline__ double g1(const ExbPatArgs& pa, const long long v, const ExbXG x, const double* __restrict__ th) {\n";
       // branch-free: an out-of-range point is replaced by the pattern's first local point and its slot discarded, so the
       // loads of every slot are issued up front (the kernel is latency-bound: ~10 flops per 8-byte word)
       o << "    double acc = 0.0;\n    if (pa.n > 0) {\n";
@@ -709,7 +735,7 @@ inline std::string gen_pattern(PatternPlan& p, int index) {
       g.hrpass0(p.ir.root, Sym("a0"), K(0));
       for (int j = 0; j < ns2; j++) tail.push_back("s[" + std::to_string(j) + "] = " + g.slot[(size_t)j].s + ";");
     }
-    emit_eval_fn(o, "d2", A + ", const double* __restrict__ x, const double* __restrict__ th, const double a0", "pa, kg, x, th, a0", a2, B, tail);
+    emit_eval_fn(o, "d2", A + ", const XA x, const double* __restrict__ th, const double a0", "pa, kg, x, th, a0", a2, B, tail);
     p.ppt2 = ppt_for(body_weight(B), a2);
   }
   {  // s1: variable index per first-order slot (jacobian.jl:69-83)
@@ -800,7 +826,14 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes) {
   if (const char* e = getenv("EXB_TUNE_MINB")) { int b = atoi(e); if (b >= 1 && b <= 32) pl.minb = b; }
   std::ostringstream o;
   o << "// generated by exb_plan.hpp -- one struct per pattern, kernels per callback\n";
-  for (size_t k = 0; k < pl.pats.size(); k++) o << gen_pattern(pl.pats[k], (int)k);
+  // the persistent Hessian kernel needs an x window for EVERY pattern with second-order slots
+  pl.hess_windowed = getenv("EXB_TUNE_NO_PERSISTENT") == nullptr;
+  {
+    bool any = false;
+    for (auto& p : pl.pats) { compute_window(p); if (p.o2step > 0) { any = true; pl.hess_windowed = pl.hess_windowed && p.win; } }
+    pl.hess_windowed = pl.hess_windowed && any;
+  }
+  for (size_t k = 0; k < pl.pats.size(); k++) o << gen_pattern(pl.pats[k], (int)k, pl.hess_windowed && pl.pats[k].win);
   // kernel pattern lists
   for (size_t k = 0; k < pl.pats.size(); k++) {
     const PatternPlan& p = pl.pats[k];
@@ -815,6 +848,7 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes) {
       << body << "<" << targ << plist(v) << ">(g, c); }\n";
   };
   kern("exb_hess_g0", "exb_hess_body", pl.k_hess, "");
+  if (pl.hess_windowed) kern("exb_hessp_g0", "exb_hessp_body", pl.k_hess, "");
   kern("exb_jac_g0", "exb_d1_body", pl.k_jac, "");
   kern("exb_sgrad_g0", "exb_d1_body", pl.k_sgrad, "");
   kern("exb_ggrad_g0", "exb_ggrad_body", pl.k_ggrad, "");

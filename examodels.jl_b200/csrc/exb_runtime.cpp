@@ -92,6 +92,7 @@ struct Drv {
   CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
   CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  CUresult (*OccupancyMaxActiveBlocks)(int*, CUfunction, int, size_t) = nullptr;
   bool ok = false;
 };
 Drv g_drv;
@@ -109,7 +110,8 @@ bool load_driver() {
   std::call_once(g_drv_once, [] {
     g_drv.ok = entry("cuModuleLoadData", g_drv.ModuleLoadData) && entry("cuModuleUnload", g_drv.ModuleUnload) &&
                entry("cuModuleGetFunction", g_drv.ModuleGetFunction) && entry("cuModuleGetGlobal", g_drv.ModuleGetGlobal) && entry("cuLaunchKernel", g_drv.LaunchKernel) &&
-               entry("cuFuncGetAttribute", g_drv.FuncGetAttribute) && entry("cuFuncSetAttribute", g_drv.FuncSetAttribute) && entry("cuGetErrorString", g_drv.GetErrorString);
+               entry("cuFuncGetAttribute", g_drv.FuncGetAttribute) && entry("cuFuncSetAttribute", g_drv.FuncSetAttribute) && entry("cuGetErrorString", g_drv.GetErrorString) &&
+               entry("cuOccupancyMaxActiveBlocksPerMultiprocessor", g_drv.OccupancyMaxActiveBlocks);
   });
   return g_drv.ok;
 }
@@ -160,6 +162,10 @@ struct Launch {          // one generated kernel, ready to launch
   ExbGroup g{};          // device pointers
   unsigned nblocks = 0;
   unsigned smem = 0;
+  // persistent form of the kernel (exb_hessp_g0, only when every pattern has an x window): one more candidate per variant
+  std::vector<CUfunction> pcand; std::vector<unsigned> pgrid;
+  int use_p = -1;                     // >= 0: index into pcand of the persistent kernel in use
+  unsigned psmem = 0; int pw[4] = {0, 0, 0, 0};
   std::vector<ExbChunk> hchunk;       // host copy of the chunk table (windowed launches of the pipelined host shims)
   std::vector<int> ppt, ns;           // per listed pattern: points per thread, slots per point
 };
@@ -311,6 +317,18 @@ int launch_fn(exb_model* m, int kn, CUfunction fn, const ExbCall& c, cudaStream_
   return EXB_OK;
 }
 
+int launch_persistent(exb_model* m, int kn, size_t pi, const ExbCall& c, cudaStream_t st) {
+  Launch& L = m->k[kn];
+  ExbGroup g = L.g;
+  ExbCall cc = c;
+  for (int q = 0; q < 4; q++) cc.pw[q] = L.pw[q];
+  void* params[2] = {&g, &cc};
+  CUresult r = g_drv.LaunchKernel(L.pcand[pi], L.pgrid[pi], 1, 1, (unsigned)m->plan->pl.block, 1, 1, L.psmem, (CUstream)st, params, nullptr);
+  if (r != CUDA_SUCCESS) return fail(EXB_ERR_CUDA, std::string("launch of the persistent ") + KNAME[kn] + ": " + cu_err(r));
+  m->launches++; m->last_launches++;
+  return EXB_OK;
+}
+
 // First call of a tunable kernel: run every variant on the caller's own buffers (each one fully
 // defines the output, so the result is valid whichever ran last), time them with events and keep
 // the fastest.  This one call synchronises the stream; later calls do not.
@@ -318,26 +336,33 @@ int tune(exb_model* m, int kn, const ExbCall& c, cudaStream_t st) {
   Launch& L = m->k[kn];
   cudaEvent_t e0, e1;
   CU_TRY(m, cudaEventCreate(&e0)); CU_TRY(m, cudaEventCreate(&e1));
-  int rc = EXB_OK; float best_ms = 0; int best = 0;
-  for (size_t v = 0; v < L.cand.size() && !rc; v++) {
-    rc = launch_fn(m, kn, L.cand[v], c, st);                       // warm-up (module load, caches)
+  int rc = EXB_OK; float best_ms = 0, best_classic_ms = 0; int best = 0, best_classic = 0;
+  const size_t nc = L.cand.size(), np = L.pcand.size();
+  for (size_t v = 0; v < nc + np && !rc; v++) {
+    auto run = [&]() { return v < nc ? launch_fn(m, kn, L.cand[v], c, st) : launch_persistent(m, kn, v - nc, c, st); };
+    rc = run();                                                    // warm-up (module load, caches)
     float ms = 1e30f;
     for (int rep = 0; rep < 2 && !rc; rep++) {
       cudaEventRecord(e0, st);
-      rc = launch_fn(m, kn, L.cand[v], c, st);
+      rc = run();
       cudaEventRecord(e1, st);
       if (cudaEventSynchronize(e1) != cudaSuccess) rc = fail(EXB_ERR_CUDA, "kernel failed while tuning");
       float t = 0; cudaEventElapsedTime(&t, e0, e1);
       if (t < ms) ms = t;
     }
     if (v == 0 || ms < best_ms) { best_ms = ms; best = (int)v; }
+    if (v < nc && (v == 0 || ms < best_classic_ms)) { best_classic_ms = ms; best_classic = (int)v; }
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (rc) return rc;
-  L.best = best; L.fn = L.cand[(size_t)best];
+  // the classic form stays available (windowed launches of the host shims, graph capture); the persistent one is used
+  // for whole-grid launches when it measured faster
+  L.best = best_classic; L.fn = L.cand[(size_t)best_classic];
+  L.use_p = best >= (int)nc ? best - (int)nc : -1;
   if (m->rank == 0 && best_ms >= 0.03f) {   // remember, unless the launch was too short to rank variants (append; last entry wins)
     std::ofstream tf(m->plan->tune_path, std::ios::app);
-    tf << KNAME[kn] << " " << m->plan->var[(size_t)best].minb << "\n";
+    tf << KNAME[kn] << " " << m->plan->var[(size_t)best_classic].minb << "\n";
+    if (np > 0) tf << KNAME[kn] << "+persistent " << (L.use_p >= 0 ? m->plan->var[(size_t)L.use_p].minb : -1) << "\n";
   }
   return EXB_OK;
 }
@@ -350,6 +375,7 @@ int launch(exb_model* m, int kn, const ExbCall& c, cudaStream_t st) {
     if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
     if (cs == cudaStreamCaptureStatusNone) return tune(m, kn, c, st);   // timing needs a stream sync: not while capturing a graph
   }
+  if (L.use_p >= 0) return launch_persistent(m, kn, (size_t)L.use_p, c, st);
   return launch_fn(m, kn, L.fn, c, st);
 }
 
@@ -418,14 +444,19 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
     m->mods.push_back(mod);
   }
   // a previous run's tuning result for this model's kernels: "<kernel> <minb>" lines
-  std::vector<int> tuned(KN_COUNT, -1);
+  std::vector<int> tuned(KN_COUNT, -1), tuned_p(KN_COUNT, -2);   // tuned_p: -2 unknown, -1 classic wins, >= 0 persistent variant
   {
     std::ifstream tf(P->tune_path);
     std::string name; int mb;
     while (tf >> name >> mb)
-      for (int kn = 0; kn < KN_COUNT; kn++)
+      for (int kn = 0; kn < KN_COUNT; kn++) {
         if (name == KNAME[kn])
           for (size_t vi = 0; vi < P->var.size(); vi++) if (P->var[vi].minb == mb) tuned[kn] = (int)vi;
+        if (name == std::string(KNAME[kn]) + "+persistent") {
+          tuned_p[kn] = -1;
+          for (size_t vi = 0; vi < P->var.size(); vi++) if (P->var[vi].minb == mb) tuned_p[kn] = (int)vi;
+        }
+      }
   }
 
   // per-pattern arguments
@@ -545,6 +576,40 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
         r = g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)L.smem);
         if (r != CUDA_SUCCESS) return fail(EXB_ERR_CUDA, std::string("cuFuncSetAttribute(max dynamic smem): ") + cu_err(r));
       }
+    if (kn == KN_HESS && pl.hess_windowed) {   // persistent form: same tiles and chunk table, windows of x / y staged in shared memory
+      int xw = 2, yw = 0;
+      for (size_t q = 0; q < lst.size(); q++) {
+        const exb::PatternPlan& p = pl.pats[(size_t)lst[q]];
+        const int T = (int)BLK * p.ppt2;
+        xw = std::max(xw, T + (int)(p.xhi - p.xlo));
+        if (p.ir.kind == exb::KIND_CON) yw = std::max(yw, T);
+      }
+      xw = (xw + 1) & ~1; yw = (yw + 1) & ~1;
+      L.pw[0] = (int)((L.smem + 15) / 16 * 2); L.pw[1] = xw; L.pw[2] = yw; L.pw[3] = (int)L.nblocks;
+      L.psmem = (unsigned)(8 * (L.pw[0] + 2 * (xw + yw)));
+      int nsm = 0;
+      CU_TRY(m, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, m->device));
+      for (CUmodule mod : m->mods) {
+        CUfunction fn = nullptr;
+        r = g_drv.ModuleGetFunction(&fn, mod, "exb_hessp_g0");
+        if (r != CUDA_SUCCESS) return fail(EXB_ERR_COMPILE, std::string("kernel exb_hessp_g0 missing from module: ") + cu_err(r));
+        if (L.psmem > 48u * 1024u) {
+          r = g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)L.psmem);
+          if (r != CUDA_SUCCESS) return fail(EXB_ERR_CUDA, std::string("cuFuncSetAttribute(max dynamic smem): ") + cu_err(r));
+        }
+        int per_sm = 0;
+        r = g_drv.OccupancyMaxActiveBlocks(&per_sm, fn, (int)BLK, (size_t)L.psmem);
+        if (r != CUDA_SUCCESS || per_sm < 1) per_sm = 1;
+        L.pcand.push_back(fn);
+        L.pgrid.push_back((unsigned)std::min<long long>((long long)L.nblocks, (long long)per_sm * nsm));
+      }
+      if (tuned_p[kn] >= -1 && L.best >= 0) L.use_p = tuned_p[kn];
+      else L.best = -1;   // no verdict on the persistent form yet: tune at the first call
+      if (const char* e = getenv("EXB_TUNE_FORCE_PERSISTENT")) {   // test / development knob: 1 = always, 0 = never
+        if (L.best < 0) { L.best = 0; L.fn = L.cand[0]; }
+        L.use_p = atoi(e) ? 0 : -1;
+      }
+    }
   }
   // scratch owned by the handle (ext:21-31,180-190)
   int rc;
@@ -1253,6 +1318,19 @@ int exb_timings(exb_model* m, double* ms8, int64_t* calls8, int reset) {
   }
   return EXB_OK;
   EXB_END
+}
+int exb_kernel_choice(const exb_model* m, int callback, int64_t* o) {
+  if (!m || !o) return fail(EXB_ERR_HANDLE, "invalid handle");
+  static const int map[5] = {KN_OBJ, KN_GGRAD, KN_CONS, KN_JAC, KN_HESS};
+  if (callback < 0 || callback > 4) return fail(EXB_ERR_ARG, "callback must be 0 (obj) .. 4 (hess)");
+  int kn = map[callback];
+  if (kn == KN_GGRAD && m->k[kn].nblocks == 0) kn = KN_SGRAD;
+  const Launch& L = m->k[kn];
+  o[0] = L.best >= 0 && (size_t)L.best < m->plan->var.size() ? m->plan->var[(size_t)L.best].minb : -1;
+  o[1] = L.use_p >= 0 ? 1 : 0;
+  o[2] = L.use_p >= 0 ? (int64_t)L.pgrid[(size_t)L.use_p] : (int64_t)L.nblocks;
+  o[3] = kn == KN_GGRAD ? 1 : 0;
+  return EXB_OK;
 }
 int exb_stats(const exb_model* m, int64_t* o) {
   if (!m || !o) return fail(EXB_ERR_HANDLE, "invalid handle");

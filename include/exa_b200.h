@@ -184,6 +184,10 @@ int exb_shard(const exb_model* m, int k, int64_t* out6);
 /* out[0] = kernels launched since creation, out[1] = last callback launches,
  * out[2] = device bytes owned by the handle, out[3] = 1 if module came from cache */
 int exb_stats(const exb_model* m, int64_t* out4);
+/* Which generated kernel a value callback launches (callback: 0 obj, 1 grad, 2 cons, 3 jac, 4 hess), as decided by the
+ * first-call tuner: out[0] = min-blocks-per-SM of the launch-shape variant (-1: not tuned yet), out[1] = 1 if the
+ * persistent shared-memory-window form is in use (hess), out[2] = grid size, out[3] = 1 if grad uses the owner-computes kernel */
+int exb_kernel_choice(const exb_model* m, int callback, int64_t* out4);
 
 /* Per-callback device timing: the TimedNLPModel role (src/utils.jl:271-408).  When on, every value callback is
  * bracketed by CUDA events on the caller's stream (no synchronisation); exb_timings synchronises on them and returns

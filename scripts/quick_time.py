@@ -28,7 +28,7 @@ for name, f, bytes_ in [
     med, mn = timeit(f)
     print(f"{name}: median {med:.4f} ms min {mn:.4f} ms  -> {bytes_ / med / 1e6:.1f} GB/s algorithmic")
 med, _ = timeit(lambda: m.hess_coord(x, y, h))
-print("hess nnz/s", m.nnzh / (med * 1e-3))
+print("hess nnz/s", m.nnzh / (med * 1e-3), "kernel choice:", {cb: m.kernel_choice(cb) for cb in ("hess", "jac", "grad", "cons", "obj")})
 # parity of this build / knob set against the oracle on a small instance
 from oracle.oracle_api import Oracle
 small = M.luksan_vlcek(3000); o, ms = Oracle.from_core(small), E.ExaModel(small)

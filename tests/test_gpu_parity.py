@@ -203,3 +203,40 @@ def test_pipelined_host_shims(exa, torch_, which):
     l0 = m.stats()["launches"]
     assert_close(m.hess_coord(x, y, hh, obj_weight=0.5), ref_h, "pageable host hess")
     assert m.stats()["launches"] - l0 == 1
+
+
+@pytest.mark.parametrize("which", ["lv_bench", "lv_guide_ragged", "only_objective", "lv_sharded"])
+def test_persistent_hessian_kernel(exa, torch_, which, monkeypatch):
+    """The persistent form of the Hessian kernel (x / y windows of the next tile prefetched into shared memory with
+    cp.async, csrc/exb_device.cuh exb_hessp_body) forced on: same values as the oracle, for every obj_weight / y form,
+    ragged last tiles and a sharded handle; and the classic form forced on gives bitwise the same vector."""
+    from examodels_jl_b200 import models as M
+    from oracle.oracle_api import Oracle
+    from edge_models import EDGE
+    torch = torch_
+    core = {"lv_bench": lambda: M.luksan_vlcek(200_003), "lv_guide_ragged": lambda: M.luksan_vlcek(1029, order="guide"),
+            "only_objective": EDGE["only_objective"], "lv_sharded": lambda: M.luksan_vlcek(70_001)}[which]()
+    ora = Oracle.from_core(core)
+    x, y = inputs(core)
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    kw = dict(rank=1, world=3) if which == "lv_sharded" else {}
+    monkeypatch.setenv("EXB_TUNE_FORCE_PERSISTENT", "1")
+    mp_ = exa.ExaModel(core, **kw)
+    assert mp_.kernel_choice("hess")["persistent"]
+    monkeypatch.setenv("EXB_TUNE_FORCE_PERSISTENT", "0")
+    mc = exa.ExaModel(core, **kw)
+    assert not mc.kernel_choice("hess")["persistent"]
+    if kw:
+        ora.set_shard(1, 3)
+    for yy, w in ((dy, 1.0), (dy, 0.5), (None, 2.0)):
+        hp = mp_.hess_coord(dx, yy, mp_.new(mp_.nnzh).fill_(float("nan")), obj_weight=w)
+        hc = mc.hess_coord(dx, yy, mc.new(mc.nnzh).fill_(float("nan")), obj_weight=w)
+        assert torch.equal(torch.nan_to_num(hp, nan=-7.0), torch.nan_to_num(hc, nan=-7.0)), "persistent and classic kernels differ"
+        ref = ora.hess_coord(x, None if yy is None else y, w)
+        got = hp.cpu().numpy()
+        if kw:   # a sharded handle writes only its slices
+            mine = ~np.isnan(got)
+            assert mine.any() and not mine.all()
+            assert_close(got[mine], ref[mine], f"persistent hess shard (w={w})")
+        else:
+            assert_close(got, ref, f"persistent hess (w={w})")
