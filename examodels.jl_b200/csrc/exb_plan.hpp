@@ -826,8 +826,12 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes) {
   if (const char* e = getenv("EXB_TUNE_MINB")) { int b = atoi(e); if (b >= 1 && b <= 32) pl.minb = b; }
   std::ostringstream o;
   o << "// generated by exb_plan.hpp -- one struct per pattern, kernels per callback\n";
-  // the persistent Hessian kernel needs an x window for EVERY pattern with second-order slots
-  pl.hess_windowed = getenv("EXB_TUNE_NO_PERSISTENT") == nullptr;
+  // The persistent Hessian kernel needs an x window for EVERY pattern with second-order slots.  Opt-in (EXB_TUNE_PERSISTENT=1):
+  // measured on LV N=1e7 it is SLOWER than the classic one-tile-per-block kernel (0.174 ms with the classic tiles and a single
+  // staging buffer, 0.221 ms with one point per thread and double-buffered staging, against 0.158 ms): the hardware block
+  // scheduler over 16 small resident blocks per SM hides the x / y latency better than a software pipeline that pays two
+  // barriers per tile and loses occupancy to its shared-memory windows.  Kept as a tuner candidate for experiments.
+  pl.hess_windowed = getenv("EXB_TUNE_PERSISTENT") != nullptr && atoi(getenv("EXB_TUNE_PERSISTENT")) != 0;
   {
     bool any = false;
     for (auto& p : pl.pats) { compute_window(p); if (p.o2step > 0) { any = true; pl.hess_windowed = pl.hess_windowed && p.win; } }

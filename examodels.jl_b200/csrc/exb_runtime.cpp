@@ -166,6 +166,7 @@ struct Launch {          // one generated kernel, ready to launch
   std::vector<CUfunction> pcand; std::vector<unsigned> pgrid;
   int use_p = -1;                     // >= 0: index into pcand of the persistent kernel in use
   unsigned psmem = 0; int pw[4] = {0, 0, 0, 0};
+  ExbGroup gp{};                      // the persistent kernel's own block -> pattern table
   std::vector<ExbChunk> hchunk;       // host copy of the chunk table (windowed launches of the pipelined host shims)
   std::vector<int> ppt, ns;           // per listed pattern: points per thread, slots per point
 };
@@ -319,7 +320,7 @@ int launch_fn(exb_model* m, int kn, CUfunction fn, const ExbCall& c, cudaStream_
 
 int launch_persistent(exb_model* m, int kn, size_t pi, const ExbCall& c, cudaStream_t st) {
   Launch& L = m->k[kn];
-  ExbGroup g = L.g;
+  ExbGroup g = L.gp;
   ExbCall cc = c;
   for (int q = 0; q < 4; q++) cc.pw[q] = L.pw[q];
   void* params[2] = {&g, &cc};
@@ -417,6 +418,36 @@ int upload_column(exb_model* m, const unsigned char* base, long long n, long lon
     *col = d;
   }
   return EXB_OK;
+}
+
+// Block -> pattern table of one launch: nb[q] blocks of pattern q, handed out in chunks of (1 << shift) blocks (see ExbGroup)
+void make_chunks(const std::vector<long long>& nb, int& shift, std::vector<ExbChunk>& chunks) {
+  long long tot = 0;
+  for (long long v : nb) tot += v;
+  shift = 0;
+  while ((tot >> shift) > 4096 && shift < 9) shift++;
+  const long long csz = 1LL << shift;
+  chunks.clear();
+  if (nb.size() <= 4) {   // few patterns: interleave them so shared parts of x are streamed from HBM once
+    // proportional merge: always take the pattern that is least far through its own range, so patterns with
+    // different points-per-block still walk x side by side
+    std::vector<long long> nch(nb.size()), at(nb.size(), 0);
+    long long left = 0;
+    for (size_t q = 0; q < nb.size(); q++) { nch[q] = (nb[q] + csz - 1) / csz; left += nch[q]; }
+    while (left-- > 0) {
+      size_t best = 0; double bf = 2.0;
+      for (size_t q = 0; q < nb.size(); q++) {
+        if (at[q] >= nch[q]) continue;
+        const double f = ((double)at[q] + 0.5) / (double)nch[q];
+        if (f < bf) { bf = f; best = q; }
+      }
+      chunks.push_back(ExbChunk{(int)best, (int)(at[best] * csz)});
+      at[best]++;
+    }
+  } else {                 // many patterns: one after the other, so an SM runs one pattern's code at a time
+    for (size_t q = 0; q < nb.size(); q++)   // (interleaving 32 patterns thrashes the instruction cache: 3x slower)
+      for (long long r = 0; r * csz < nb[q]; r++) chunks.push_back(ExbChunk{(int)q, (int)(r * csz)});
+  }
 }
 
 int build_model(exb_model* m, const void* const* host_data, int n_data) {
@@ -533,29 +564,9 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
     if (tot == 0) continue;   // nothing local to evaluate (e.g. a shard with no points)
     // chunked round-robin interleave of the patterns' block ranges (see ExbGroup)
     int shift = 0;
-    while ((tot >> shift) > 4096 && shift < 9) shift++;
-    const long long csz = 1LL << shift;
     std::vector<ExbChunk> chunks;
-    if (lst.size() <= 4) {   // few patterns: interleave them so shared parts of x are streamed from HBM once
-      // proportional merge: always take the pattern that is least far through its own range, so patterns with
-      // different points-per-block still walk x side by side
-      std::vector<long long> nch(lst.size()), at(lst.size(), 0);
-      long long left = 0;
-      for (size_t q = 0; q < lst.size(); q++) { nch[q] = (nb[q] + csz - 1) / csz; left += nch[q]; }
-      while (left-- > 0) {
-        size_t best = 0; double bf = 2.0;
-        for (size_t q = 0; q < lst.size(); q++) {
-          if (at[q] >= nch[q]) continue;
-          const double f = ((double)at[q] + 0.5) / (double)nch[q];
-          if (f < bf) { bf = f; best = q; }
-        }
-        chunks.push_back(ExbChunk{(int)best, (int)(at[best] * csz)});
-        at[best]++;
-      }
-    } else {                 // many patterns: one after the other, so an SM runs one pattern's code at a time
-      for (size_t q = 0; q < lst.size(); q++)   // (interleaving 32 patterns thrashes the instruction cache: 3x slower)
-        for (long long r = 0; r * csz < nb[q]; r++) chunks.push_back(ExbChunk{(int)q, (int)(r * csz)});
-    }
+    make_chunks(nb, shift, chunks);
+    const long long csz = 1LL << shift;
     if ((long long)chunks.size() * csz > 2147483647LL) return fail(EXB_ERR_ARG, "too many blocks");
     void *d_args = nullptr, *d_chunk = nullptr;
     int rc = dmalloc(m, &d_args, args.size() * sizeof(ExbPatArgs)); if (rc) return rc;
@@ -576,17 +587,28 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
         r = g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)L.smem);
         if (r != CUDA_SUCCESS) return fail(EXB_ERR_CUDA, std::string("cuFuncSetAttribute(max dynamic smem): ") + cu_err(r));
       }
-    if (kn == KN_HESS && pl.hess_windowed) {   // persistent form: same tiles and chunk table, windows of x / y staged in shared memory
-      int xw = 2, yw = 0;
+    if (kn == KN_HESS && pl.hess_windowed) {   // persistent form: ONE point per thread per tile (small tiles keep 14+ blocks per SM
+      // resident next to the double-buffered staging tile and x / y windows), its own block -> pattern table
+      int xw = 2, yw = 0, stw = 2;
+      std::vector<long long> nbp(lst.size());
       for (size_t q = 0; q < lst.size(); q++) {
         const exb::PatternPlan& p = pl.pats[(size_t)lst[q]];
-        const int T = (int)BLK * p.ppt2;
-        xw = std::max(xw, T + (int)(p.xhi - p.xlo));
-        if (p.ir.kind == exb::KIND_CON) yw = std::max(yw, T);
+        nbp[q] = (args[q].n + BLK - 1) / BLK;
+        xw = std::max(xw, (int)BLK + (int)(p.xhi - p.xlo));
+        if (p.ir.kind == exb::KIND_CON) yw = std::max(yw, (int)BLK);
+        if (p.o2step > 1 && p.o2step <= EXB_TILE_MAX_NS) stw = std::max(stw, (int)BLK * p.o2step);
       }
-      xw = (xw + 1) & ~1; yw = (yw + 1) & ~1;
-      L.pw[0] = (int)((L.smem + 15) / 16 * 2); L.pw[1] = xw; L.pw[2] = yw; L.pw[3] = (int)L.nblocks;
-      L.psmem = (unsigned)(8 * (L.pw[0] + 2 * (xw + yw)));
+      xw = (xw + 1) & ~1; yw = (yw + 1) & ~1; stw = (stw + 1) & ~1;
+      int pshift = 0;
+      std::vector<ExbChunk> pch;
+      make_chunks(nbp, pshift, pch);
+      if ((long long)pch.size() << pshift > 2147483647LL) return fail(EXB_ERR_ARG, "too many blocks");
+      void* d_pch = nullptr;
+      int prc = dmalloc(m, &d_pch, pch.size() * sizeof(ExbChunk)); if (prc) return prc;
+      CU_TRY(m, cudaMemcpy(d_pch, pch.data(), pch.size() * sizeof(ExbChunk), cudaMemcpyHostToDevice));
+      L.gp = L.g; L.gp.chunk = (const ExbChunk*)d_pch; L.gp.shift = pshift;
+      L.pw[0] = stw; L.pw[1] = xw; L.pw[2] = yw; L.pw[3] = (int)(pch.size() << pshift);
+      L.psmem = (unsigned)(8 * (2 * stw + 2 * (xw + yw)));
       int nsm = 0;
       CU_TRY(m, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, m->device));
       for (CUmodule mod : m->mods) {
@@ -601,7 +623,7 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
         r = g_drv.OccupancyMaxActiveBlocks(&per_sm, fn, (int)BLK, (size_t)L.psmem);
         if (r != CUDA_SUCCESS || per_sm < 1) per_sm = 1;
         L.pcand.push_back(fn);
-        L.pgrid.push_back((unsigned)std::min<long long>((long long)L.nblocks, (long long)per_sm * nsm));
+        L.pgrid.push_back((unsigned)std::min<long long>((long long)L.pw[3], (long long)per_sm * nsm));
       }
       if (tuned_p[kn] >= -1 && L.best >= 0) L.use_p = tuned_p[kn];
       else L.best = -1;   // no verdict on the persistent form yet: tune at the first call

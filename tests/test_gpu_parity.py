@@ -207,8 +207,8 @@ def test_pipelined_host_shims(exa, torch_, which):
 
 @pytest.mark.parametrize("which", ["lv_bench", "lv_guide_ragged", "only_objective", "lv_sharded"])
 def test_persistent_hessian_kernel(exa, torch_, which, monkeypatch):
-    """The persistent form of the Hessian kernel (x / y windows of the next tile prefetched into shared memory with
-    cp.async, csrc/exb_device.cuh exb_hessp_body) forced on: same values as the oracle, for every obj_weight / y form,
+    """The experimental persistent form of the Hessian kernel (x / y windows of the next tile prefetched into shared memory
+    with cp.async, csrc/exb_device.cuh exb_hessp_body; opt-in, measured slower than the classic kernel) forced on: same values as the oracle, for every obj_weight / y form,
     ragged last tiles and a sharded handle; and the classic form forced on gives bitwise the same vector."""
     from examodels_jl_b200 import models as M
     from oracle.oracle_api import Oracle
@@ -220,6 +220,7 @@ def test_persistent_hessian_kernel(exa, torch_, which, monkeypatch):
     x, y = inputs(core)
     dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
     kw = dict(rank=1, world=3) if which == "lv_sharded" else {}
+    monkeypatch.setenv("EXB_TUNE_PERSISTENT", "1")          # opt-in: generate the persistent kernel next to the classic one
     monkeypatch.setenv("EXB_TUNE_FORCE_PERSISTENT", "1")
     mp_ = exa.ExaModel(core, **kw)
     assert mp_.kernel_choice("hess")["persistent"]
