@@ -104,3 +104,34 @@ def test_lv_1e7_grad_and_obj_consistency(lv_big):
         ref = ora.grad(lv_big["x"][s: s + K])
         lo = 0 if s == 0 else 1
         assert_close(g[s + lo: s + K - 1].cpu().numpy(), ref[lo: K - 1], f"grad window {s}")
+
+
+@pytest.mark.parametrize("which", ["lv_1e7", "rocket_1e6", "opf_10k", "family_32x1e6"])
+def test_baseline_configs_full_size_direct(exa, which):
+    """BASELINE.json configs 2-5 at their FULL sizes, every value callback against the oracle run with all host threads
+    (a few seconds each), plus the integer structure where it fits comfortably in host memory."""
+    import torch
+    from examodels_jl_b200 import models as M
+    from oracle.oracle_api import Oracle
+    core = {"lv_1e7": lambda: M.luksan_vlcek(10_000_000), "rocket_1e6": lambda: M.goddard_rocket(1_000_000),
+            "opf_10k": lambda: M.ac_power(M.synthetic_power_data()), "family_32x1e6": lambda: M.pattern_family(1_000_000, 32)}[which]()
+    ora = Oracle.from_core(core)
+    ora.set_threads(Oracle.max_threads())
+    m = exa.ExaModel(core)
+    meta = core.meta()
+    x = meta["x0"] + 0.01 * np.random.default_rng(0).uniform(-1, 1, m.nvar)
+    y = np.random.default_rng(1).standard_normal(m.ncon)
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    nan = float("nan")
+    assert_close(m.hess_coord(dx, dy, m.new(m.nnzh).fill_(nan), obj_weight=0.5).cpu().numpy(), ora.hess_coord(x, y, 0.5), "hess")
+    assert_close(m.jac_coord(dx, m.new(m.nnzj).fill_(nan)).cpu().numpy(), ora.jac_coord(x), "jac")
+    assert_close(m.grad(dx, m.new(m.nvar).fill_(nan)).cpu().numpy(), ora.grad(x), "grad")
+    assert_close(m.cons_nln(dx, m.new(m.ncon).fill_(nan)).cpu().numpy(), ora.cons(x), "cons")
+    ref = ora.obj(x)
+    assert abs(m.obj(dx) - ref) <= 1e-10 * max(1.0, abs(ref))
+    if which in ("rocket_1e6", "opf_10k"):
+        hr, hc = ora.hess_structure(); jr, jc = ora.jac_structure()
+        r, c = m.new(m.nnzh, torch.int64), m.new(m.nnzh, torch.int64); m.hess_structure(r, c)
+        assert np.array_equal(r.cpu().numpy(), hr) and np.array_equal(c.cpu().numpy(), hc)
+        r, c = m.new(m.nnzj, torch.int32), m.new(m.nnzj, torch.int32); m.jac_structure(r, c)
+        assert np.array_equal(r.cpu().numpy().astype(np.int64), jr) and np.array_equal(c.cpu().numpy().astype(np.int64), jc)
