@@ -135,3 +135,49 @@ def test_baseline_configs_full_size_direct(exa, which):
         assert np.array_equal(r.cpu().numpy(), hr) and np.array_equal(c.cpu().numpy(), hc)
         r, c = m.new(m.nnzj, torch.int32), m.new(m.nnzj, torch.int32); m.jac_structure(r, c)
         assert np.array_equal(r.cpu().numpy().astype(np.int64), jr) and np.array_equal(c.cpu().numpy().astype(np.int64), jc)
+
+
+def test_lv_3e8_slot_numbers_beyond_int32(exa):
+    """Maximum-size edge case: LV N = 3x10^8 has nnzh = 2.7x10^9 > 2^31 output slots (21.6 GB of values).  Windows of the
+    result -- including the last one, whose slot numbers need 64-bit arithmetic -- against a small oracle model over the
+    same x-window; structure of the last constraint points in closed form."""
+    import torch
+    from examodels_jl_b200 import models as M
+    from oracle.oracle_api import Oracle
+    N = 300_000_000
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * 2 ** 30:
+        pytest.skip("needs ~50 GB of free device memory")
+    core = M.luksan_vlcek(N)
+    m = exa.ExaModel(core)
+    assert m.nnzh == 9 * N - 15 and m.nnzh > 2 ** 31
+    g = torch.Generator(device="cuda").manual_seed(3)
+    i = torch.arange(1, N + 1, device="cuda", dtype=torch.int32)
+    dx = torch.where(i % 2 == 1, -1.2, 1.0).to(torch.float64) + 0.01 * (2.0 * torch.rand(N, device="cuda", dtype=torch.float64, generator=g) - 1.0)
+    del i
+    dy = torch.randn(N - 2, device="cuda", dtype=torch.float64, generator=g)
+    h = m.hess_coord(dx, dy, m.new(m.nnzh), obj_weight=0.5)
+    j = m.jac_coord(dx, m.new(m.nnzj))
+    gr = m.grad(dx, m.new(m.nvar))
+    K = 1500
+    ora = Oracle.from_core(M.luksan_vlcek(K + 2))
+    o2 = 6 * (N - 2)
+    for s in (0, 123_456_789, 250_000_001, N - 2 - K):
+        xw, yw = dx[s: s + K + 2].cpu().numpy(), dy[s: s + K].cpu().numpy()
+        ref_h = ora.hess_coord(xw, yw, 0.5)
+        assert_close(h[6 * s: 6 * (s + K)].cpu().numpy(), ref_h[: 6 * K], f"hess con window {s}")
+        assert_close(h[o2 + 3 * s: o2 + 3 * (s + K + 1)].cpu().numpy(), ref_h[6 * K: 6 * K + 3 * (K + 1)], f"hess obj window {s}")
+        assert_close(j[3 * s: 3 * (s + K)].cpu().numpy(), ora.jac_coord(xw), f"jac window {s}")
+        ref_g = ora.grad(xw)
+        lo = 0 if s == 0 else 1
+        hi = K + 2 if s == N - 2 - K else K + 1
+        assert_close(gr[s + lo: s + hi].cpu().numpy(), ref_g[lo: hi], f"grad window {s}")
+    assert bool(torch.isfinite(h[-3 * K:]).all())
+    del h, j, gr
+    r, c = m.new(m.nnzh, torch.int32), m.new(m.nnzh, torch.int32)
+    m.hess_structure(r, c)
+    k = torch.arange(N - 2 - K + 1, N - 1, device="cuda", dtype=torch.int32)      # the last K constraint points (1-based i)
+    rows = torch.stack([k + 1, k + 2, k + 2, k + 2, k, k + 1], dim=1).reshape(-1)
+    cols = torch.stack([k + 1, k + 2, k + 1, k + 1, k, k], dim=1).reshape(-1)
+    assert torch.equal(r[6 * (N - 2 - K): 6 * (N - 2)], rows) and torch.equal(c[6 * (N - 2 - K): 6 * (N - 2)], cols)
+    assert int(r[-1]) == N and int(c[-1]) == N - 1     # last objective slot: (i, i-1) at i = N
