@@ -29,6 +29,7 @@ _LIBPATH = os.path.join(_CSRC, "libexa_b200.so")
 _LIB = None
 
 EXB_FLAG_NO_COMPILE = 1
+EXB_FLAG_SORTED_PRODUCTS = 2
 _ERRS = {1: "invalid handle", 2: "internal error", 3: "malformed IR", 4: "kernel module compile/load failed",
          5: "CUDA error / no device", 6: "bad argument"}
 
@@ -144,7 +145,7 @@ def _is_torch(a):
 class ExaModel:
     """`ExaModel(core)` on one B200 (or on shard `rank` of `world` when sharded)."""
 
-    def __init__(self, core, device=None, rank=0, world=1, allow_compile=True):
+    def __init__(self, core, device=None, rank=0, world=1, allow_compile=True, sorted_products=False):
         import torch  # device memory + streams only
 
         self._torch = torch
@@ -162,7 +163,8 @@ class ExaModel:
         ir, bufs = core.to_ir()
         self._ir, self._bufs = ir, bufs
         arr = (C.c_void_p * max(1, len(bufs)))(*[b.ctypes.data for b in bufs])
-        opt = _Options(self.device.index, self.rank, self.world, 0 if allow_compile else EXB_FLAG_NO_COMPILE, 0)
+        flags = (0 if allow_compile else EXB_FLAG_NO_COMPILE) | (EXB_FLAG_SORTED_PRODUCTS if sorted_products else 0)
+        opt = _Options(self.device.index, self.rank, self.world, flags, 0)
         self.h = C.c_void_p()
         _check(lib().exb_create(ir, C.c_size_t(len(ir)), arr, len(bufs), C.byref(opt), C.byref(self.h)))
         d = np.zeros(8, dtype=np.int64)

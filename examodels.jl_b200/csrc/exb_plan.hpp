@@ -864,6 +864,9 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes) {
   kern("exb_hstruct64_g0", "exb_hstruct_body", pl.k_hess, "long long, ");
   kern("exb_hstruct32_g0", "exb_hstruct_body", pl.k_hess, "int, ");
   kern("exb_augrow_g0", "exb_augrow_body", pl.k_aug, "");
+  kern("exb_jprod_g0", "exb_jprod_body", pl.k_jac, "");
+  kern("exb_jtprod_g0", "exb_jtprod_body", pl.k_jac, "");
+  kern("exb_hprod_g0", "exb_hprod_body", pl.k_hess, "");
   pl.source = o.str();
   return true;
 }

@@ -121,9 +121,10 @@ std::string cu_err(CUresult r) {
   return s ? s : "CUDA driver error " + std::to_string((int)r);
 }
 
-enum { KN_HESS, KN_JAC, KN_SGRAD, KN_GGRAD, KN_CONS, KN_OBJ, KN_JSTRUCT64, KN_JSTRUCT32, KN_GSTRUCT64, KN_HSTRUCT64, KN_HSTRUCT32, KN_AUGROW, KN_COUNT };
+enum { KN_HESS, KN_JAC, KN_SGRAD, KN_GGRAD, KN_CONS, KN_OBJ, KN_JSTRUCT64, KN_JSTRUCT32, KN_GSTRUCT64, KN_HSTRUCT64, KN_HSTRUCT32, KN_AUGROW, KN_JPROD, KN_JTPROD, KN_HPROD, KN_COUNT };
 const char* KNAME[KN_COUNT] = {"exb_hess_g0", "exb_jac_g0", "exb_sgrad_g0", "exb_ggrad_g0", "exb_cons_g0", "exb_obj_g0", "exb_jstruct64_g0",
-                               "exb_jstruct32_g0", "exb_gstruct64_g0", "exb_hstruct64_g0", "exb_hstruct32_g0", "exb_augrow_g0"};
+                               "exb_jstruct32_g0", "exb_gstruct64_g0", "exb_hstruct64_g0", "exb_hstruct32_g0", "exb_augrow_g0",
+                               "exb_jprod_g0", "exb_jtprod_g0", "exb_hprod_g0"};
 
 }  // namespace
 
@@ -142,8 +143,8 @@ struct exb_plan {
   bool from_cache = false;
   const std::vector<int>& list(int kn) const {
     switch (kn) {
-      case KN_HESS: case KN_HSTRUCT64: case KN_HSTRUCT32: return pl.k_hess;
-      case KN_JAC: case KN_JSTRUCT64: case KN_JSTRUCT32: return pl.k_jac;
+      case KN_HESS: case KN_HSTRUCT64: case KN_HSTRUCT32: case KN_HPROD: return pl.k_hess;
+      case KN_JAC: case KN_JSTRUCT64: case KN_JSTRUCT32: case KN_JPROD: case KN_JTPROD: return pl.k_jac;
       case KN_SGRAD: case KN_GSTRUCT64: return pl.k_sgrad;
       case KN_GGRAD: return pl.k_ggrad;
       case KN_CONS: return pl.k_cons;
@@ -257,6 +258,7 @@ int compile_plan(exb_plan* p, bool allow_compile) {
 struct exb_model {
   exb_plan* plan = nullptr;
   int device = 0, rank = 0, world = 1;
+  bool sorted_products = false;   // EXB_FLAG_SORTED_PRODUCTS: the reference's sorted-structure SpMV instead of the fused kernels
   std::vector<CUmodule> mods;
   Launch k[KN_COUNT];
   std::vector<void*> dev;      // everything cudaMalloc'ed by the handle
@@ -371,6 +373,11 @@ int tune(exb_model* m, int kn, const ExbCall& c, cudaStream_t st) {
 int launch(exb_model* m, int kn, const ExbCall& c, cudaStream_t st) {
   Launch& L = m->k[kn];
   if (!L.fn || L.nblocks == 0) return EXB_OK;
+  if (kn == KN_JPROD || kn == KN_JTPROD || kn == KN_HPROD) {   // not idempotent (atomics): never tuned themselves; they use the
+    const Launch& V = m->k[kn == KN_HPROD ? KN_HESS : KN_JAC];  // launch-shape variant their value kernel was tuned to
+    const size_t vi = V.best >= 0 && (size_t)V.best < L.cand.size() ? (size_t)V.best : 0;
+    return launch_fn(m, kn, L.cand[vi], c, st);
+  }
   if (L.best < 0) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
@@ -545,7 +552,7 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
     for (size_t q = 0; q < lst.size(); q++) {
       args[q] = pa[(size_t)lst[q]];
       const exb::PatternPlan& p = pl.pats[(size_t)lst[q]];
-      const bool k2 = kn == KN_HESS, k1 = kn == KN_JAC || kn == KN_SGRAD, k0 = kn == KN_CONS || kn == KN_OBJ;
+      const bool k2 = kn == KN_HESS || kn == KN_HPROD, k1 = kn == KN_JAC || kn == KN_SGRAD || kn == KN_JPROD || kn == KN_JTPROD, k0 = kn == KN_CONS || kn == KN_OBJ;
       const int ppt = k2 ? p.ppt2 : k1 ? p.ppt1 : k0 ? p.ppt0 : 1;
       nb[q] = (args[q].n + BLK * ppt - 1) / (BLK * ppt);
       tot += nb[q]; if (nb[q] > maxnb) maxnb = nb[q];
@@ -811,6 +818,7 @@ int exb_create(const void* ir, size_t ir_bytes, const void* const* host_data, in
   if (rc) { delete P; return rc; }
   exb_model* m = new exb_model();
   m->plan = P; m->device = dev; m->rank = o.rank; m->world = o.world;
+  m->sorted_products = (o.flags & EXB_FLAG_SORTED_PRODUCTS) != 0;
   DeviceGuard dg(dev);
   rc = build_model(m, host_data, n_data);
   if (rc) { std::string keep = g_err; free_model(m); g_err = keep; return rc; }
@@ -1021,14 +1029,27 @@ int spmv(exb_model* m, const exb_model::Sorted& S, const double* buf, const doub
 
 extern "C" {
 
+// Matrix-free products.  Default: fused into the derivative sweep (csrc/exb_device.cuh exb_jprod_block / exb_jtprod_block /
+// exb_hprod_block): no COO values are written or re-read, no sorted structure is built, sharded handles return partial sums.
+// EXB_FLAG_SORTED_PRODUCTS: the reference's device scheme (COO into scratch, then SpMV over a pre-sorted structure, ext:353-511).
 int exb_jprod(exb_model* m, const double* x, const double* v, double* Jv, void* stream) {
   EXB_BEGIN
   EXB_GUARD(m);
   TimeScope ts_(m, CB_JPROD, stream);
-  int rc = ensure_sorted(m, 1); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  const exb::Plan& pl = m->plan->pl;
+  if (!m->sorted_products) {
+    CU_TRY(m, cudaMemsetAsync(Jv, 0, (size_t)pl.ncon * 8, st));
+    if (pl.nconaug > 0) CU_TRY(m, cudaMemsetAsync(m->d_conbuf, 0, (size_t)pl.nconaug * 8, st));
+    ExbCall c{}; c.x = x; c.v = v; c.th = m->d_theta; c.out = Jv; c.out2 = m->d_conbuf;
+    int rc = launch(m, KN_JPROD, c, st); if (rc) return rc;
+    CU_TRY(m, exb_fx_compress(m->d_conbuf, m->a_ptr, m->a_slot, m->a_target, m->a_i32, m->a_runs, Jv, 1, st));
+    if (m->a_runs > 0) { m->launches++; m->last_launches++; }
+    return EXB_OK;
+  }
+  int rc = ensure_sorted(m, 1); if (rc) return rc;
   rc = exb_jac(m, x, m->d_jacbuf, stream); if (rc) return rc;
-  CU_TRY(m, cudaMemsetAsync(Jv, 0, (size_t)m->plan->pl.ncon * 8, st));
+  CU_TRY(m, cudaMemsetAsync(Jv, 0, (size_t)pl.ncon * 8, st));
   return spmv(m, m->jrow, m->d_jacbuf, v, Jv, 0, 0, st);                 // kerspmv, ext:482-488
   EXB_END
 }
@@ -1036,10 +1057,16 @@ int exb_jtprod(exb_model* m, const double* x, const double* v, double* Jtv, void
   EXB_BEGIN
   EXB_GUARD(m);
   TimeScope ts_(m, CB_JTPROD, stream);
-  int rc = ensure_sorted(m, 1); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  const exb::Plan& pl = m->plan->pl;
+  if (!m->sorted_products) {
+    CU_TRY(m, cudaMemsetAsync(Jtv, 0, (size_t)pl.m.nvar * 8, st));
+    ExbCall c{}; c.x = x; c.v = v; c.th = m->d_theta; c.out = Jtv;
+    return launch(m, KN_JTPROD, c, st);
+  }
+  int rc = ensure_sorted(m, 1); if (rc) return rc;
   rc = exb_jac(m, x, m->d_jacbuf, stream); if (rc) return rc;
-  CU_TRY(m, cudaMemsetAsync(Jtv, 0, (size_t)m->plan->pl.m.nvar * 8, st));
+  CU_TRY(m, cudaMemsetAsync(Jtv, 0, (size_t)pl.m.nvar * 8, st));
   return spmv(m, m->jcol, m->d_jacbuf, v, Jtv, 0, 0, st);                // kerspmv2, ext:489-495
   EXB_END
 }
@@ -1047,10 +1074,16 @@ int exb_hprod(exb_model* m, const double* x, const double* y, const double* v, d
   EXB_BEGIN
   EXB_GUARD(m);
   TimeScope ts_(m, CB_HPROD, stream);
-  int rc = ensure_sorted(m, 1); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  const exb::Plan& pl = m->plan->pl;
+  if (!m->sorted_products) {
+    CU_TRY(m, cudaMemsetAsync(Hv, 0, (size_t)pl.m.nvar * 8, st));
+    ExbCall c{}; c.x = x; c.y = y; c.v = v; c.th = m->d_theta; c.sigma = obj_weight; c.out = Hv;
+    return launch(m, KN_HPROD, c, st);
+  }
+  int rc = ensure_sorted(m, 1); if (rc) return rc;
   rc = exb_hess(m, x, y, obj_weight, m->d_hessbuf, stream); if (rc) return rc;
-  CU_TRY(m, cudaMemsetAsync(Hv, 0, (size_t)m->plan->pl.m.nvar * 8, st));
+  CU_TRY(m, cudaMemsetAsync(Hv, 0, (size_t)pl.m.nvar * 8, st));
   rc = spmv(m, m->hrow, m->d_hessbuf, v, Hv, 0, 0, st); if (rc) return rc;   // lower triangle incl. diagonal (kersyspmv, ext:496-503)
   return spmv(m, m->hcol, m->d_hessbuf, v, Hv, 1, 1, st);                    // transpose of the strict lower part (kersyspmv2, ext:504-511)
   EXB_END

@@ -93,6 +93,9 @@ typedef struct exb_options {
 } exb_options;
 
 #define EXB_FLAG_NO_COMPILE 1 /* fail instead of invoking nvcc when the module is not cached */
+#define EXB_FLAG_SORTED_PRODUCTS 2 /* exb_jprod / exb_jtprod / exb_hprod: the reference's scheme (COO values into scratch, then
+                                     SpMV over a pre-sorted structure, ext:353-511; bitwise reproducible) instead of the default
+                                     kernels fused into the derivative sweep (jtprod / hprod use FP64 atomic adds) */
 
 /* out[0..7] = nvar ncon nnzj nnzh nobj nnzg nconaug npar
  * (NLPModelMeta fields of src/nlp.jl:765-798 plus the scratch sizes of ext:21-31) */
@@ -148,9 +151,12 @@ int exb_hess(exb_model* m, const double* x, const double* y, double obj_weight, 
              void* stream);
 
 /* ---- matrix-free products: jprod_nln! / jtprod_nln! / hprod! (src/nlp.jl:1882-1978; device form
- * ext/ExaModelsKernelAbstractions.jl:353-511, `ExaModel(c; prod = true)`): the COO values are evaluated
- * into a buffer owned by the handle and multiplied through row- / column-sorted copies of the structure
- * (built on first use, ext:56-175).  Deterministic (no atomics).  Not available on sharded handles. */
+ * ext/ExaModelsKernelAbstractions.jl:353-511, `ExaModel(c; prod = true)`).  Default: fused into the derivative sweep --
+ * every point multiplies its first- / second-order slots (still in registers) with v; jprod assigns / segment-sums rows
+ * (deterministic), jtprod and hprod add into the pre-zeroed output with FP64 atomics; nothing of size nnzj / nnzh is
+ * written or read and sharded handles return their partial sums.  With EXB_FLAG_SORTED_PRODUCTS: the reference's scheme,
+ * COO values into a buffer owned by the handle, multiplied through row- / column-sorted copies of the structure (built on
+ * first use, ext:56-175); bitwise reproducible; not available on sharded handles. */
 int exb_jprod(exb_model* m, const double* x, const double* v, double* Jv, void* stream);    /* Jv[ncon]  */
 int exb_jtprod(exb_model* m, const double* x, const double* v, double* Jtv, void* stream);  /* Jtv[nvar] */
 int exb_hprod(exb_model* m, const double* x, const double* y, const double* v, double obj_weight, double* Hv,

@@ -19,12 +19,15 @@ def _models():
     }
 
 
+@pytest.mark.parametrize("mode", ["fused", "sorted"])
 @pytest.mark.parametrize("name", list(_models().keys()))
-def test_products_match_oracle(exa, name):
+def test_products_match_oracle(exa, name, mode):
+    """`fused` (default): products formed inside the derivative sweep (jprod deterministic, jtprod / hprod with FP64
+    atomics); `sorted`: the reference's COO + sorted-structure SpMV (EXB_FLAG_SORTED_PRODUCTS), bitwise reproducible."""
     import torch
     from oracle.oracle_api import Oracle
     core = _models()[name]()
-    ora, m = Oracle.from_core(core), exa.ExaModel(core)
+    ora, m = Oracle.from_core(core), exa.ExaModel(core, sorted_products=(mode == "sorted"))
     x, y = inputs(core)
     rng = np.random.default_rng(11)
     v, w = rng.standard_normal(m.nvar), rng.standard_normal(m.ncon)
@@ -34,10 +37,35 @@ def test_products_match_oracle(exa, name):
     assert_close(m.jtprod_nln(dx, dw, m.new(m.nvar).fill_(nan)).cpu().numpy(), ora.jtprod(x, w), "jtprod")
     assert_close(m.hprod(dx, dy, dv, m.new(m.nvar).fill_(nan), obj_weight=0.7).cpu().numpy(), ora.hprod(x, y, v, 0.7), "hprod")
     assert_close(m.hprod(dx, None, dv, m.new(m.nvar).fill_(nan), obj_weight=2.0).cpu().numpy(), ora.hprod(x, None, v, 2.0), "hprod obj-only")
-    # products are deterministic (sorted segmented sums, no atomics)
     a = m.hprod(dx, dy, dv, m.new(m.nvar), obj_weight=0.7)
     b = m.hprod(dx, dy, dv, m.new(m.nvar), obj_weight=0.7)
-    assert torch.equal(a, b)
+    if mode == "sorted":      # sorted segmented sums, no atomics: bitwise reproducible
+        assert torch.equal(a, b)
+    else:                     # atomic adds: reproducible to rounding; jprod stays bitwise reproducible
+        assert_close(a.cpu().numpy(), b.cpu().numpy(), "hprod twice", rtol=1e-13)
+        j1 = m.jprod_nln(dx, dv, m.new(m.ncon)); j2 = m.jprod_nln(dx, dv, m.new(m.ncon))
+        assert torch.equal(j1, j2)
+
+
+def test_fused_products_on_a_sharded_handle(exa):
+    """Partial products of the shards add up to the full product (the sorted scheme is not available on shards)."""
+    import torch
+    from examodels_jl_b200 import models as M
+    from oracle.oracle_api import Oracle
+    core = M.luksan_vlcek_aug(21, 3)
+    ora = Oracle.from_core(core)
+    x, y = inputs(core)
+    rng = np.random.default_rng(12)
+    v, w = rng.standard_normal(ora.nvar), rng.standard_normal(ora.ncon)
+    dx, dy, dv, dw = (torch.from_numpy(a).cuda() for a in (x, y, v, w))
+    Jv, Jtw, Hv = (torch.zeros(n, dtype=torch.float64, device="cuda") for n in (ora.ncon, ora.nvar, ora.nvar))
+    for r in range(3):
+        m = exa.ExaModel(core, rank=r, world=3)
+        Jv += m.jprod_nln(dx, dv, m.new(m.ncon)); Jtw += m.jtprod_nln(dx, dw, m.new(m.nvar))
+        Hv += m.hprod(dx, dy, dv, m.new(m.nvar), obj_weight=0.7)
+    assert_close(Jv.cpu().numpy(), ora.jprod(x, v), "sharded jprod")
+    assert_close(Jtw.cpu().numpy(), ora.jtprod(x, w), "sharded jtprod")
+    assert_close(Hv.cpu().numpy(), ora.hprod(x, y, v, 0.7), "sharded hprod")
 
 
 def _compress_ref(rows, cols, vals):
