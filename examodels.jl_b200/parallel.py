@@ -10,6 +10,8 @@ SURVEY.md §8e over torch.distributed (NCCL over NVLink on the GPU box, gloo in 
                [o + step*lo_r, o + step*hi_r): nothing to reduce.  `gather=False` leaves the COO
                buffer sharded (what a sharded consumer wants and what bench.py times);
                `gather=True` replicates it with one broadcast per (pattern, owner rank).
+  jprod_nln! / jtprod_nln! / hprod!
+               the fused product kernels of a shard return its partial product -> all_reduce(SUM) over ncon / nvar
   structures   computed replicated (each rank evaluates every point once, at build time).
 
 The reference has no multi-device path at all (single device, ext/ExaModelsKernelAbstractions.jl);
@@ -56,6 +58,22 @@ class ShardedExaModel:
         self.local.cons_nln(x, c)
         self.dist.all_reduce(c, group=self.group)
         return c
+
+    # -- matrix-free products: partial products of the shards add up ----------------------
+    def jprod_nln(self, x, v, Jv):
+        self.local.jprod_nln(x, v, Jv)
+        self.dist.all_reduce(Jv, group=self.group)
+        return Jv
+
+    def jtprod_nln(self, x, v, Jtv):
+        self.local.jtprod_nln(x, v, Jtv)
+        self.dist.all_reduce(Jtv, group=self.group)
+        return Jtv
+
+    def hprod(self, x, y, v, Hv, obj_weight=1.0):
+        self.local.hprod(x, y, v, Hv, obj_weight=obj_weight)
+        self.dist.all_reduce(Hv, group=self.group)
+        return Hv
 
     # -- sharded COO outputs -------------------------------------------------------------
     def slices(self, which, rank):

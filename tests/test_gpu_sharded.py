@@ -47,6 +47,11 @@ def _worker(rank, world, port, which, q):
         assert_close(sm.jac_coord(dx, local.new(local.nnzj).fill_(float("nan"))).cpu().numpy(), full.jac_coord(x), "jac")
         assert_close(sm.hess_coord(dx, dy, local.new(local.nnzh).fill_(float("nan")), obj_weight=0.5).cpu().numpy(),
                      full.hess_coord(x, y, 0.5), "hess")
+        v = torch.from_numpy(np.random.default_rng(2).standard_normal(full.nvar)).cuda()
+        w = torch.from_numpy(np.random.default_rng(3).standard_normal(full.ncon)).cuda()
+        assert_close(sm.jprod_nln(dx, v, local.new(local.ncon)).cpu().numpy(), full.jprod(x, v.cpu().numpy()), "jprod")
+        assert_close(sm.jtprod_nln(dx, w, local.new(local.nvar)).cpu().numpy(), full.jtprod(x, w.cpu().numpy()), "jtprod")
+        assert_close(sm.hprod(dx, dy, v, local.new(local.nvar), obj_weight=0.5).cpu().numpy(), full.hprod(x, y, v.cpu().numpy(), 0.5), "hprod")
         # sharded output left in place: only this rank's slices are written
         sm.gather = False
         h = sm.hess_coord(dx, dy, local.new(local.nnzh).fill_(float("nan")), obj_weight=0.5).cpu().numpy()

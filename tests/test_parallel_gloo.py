@@ -40,6 +40,15 @@ class _OracleShard:
     def hess_coord(self, x, y, v, obj_weight=1.0):
         v.copy_(torch.from_numpy(self.o.hess_coord(x.numpy(), y.numpy(), obj_weight))); return v
 
+    def jprod_nln(self, x, v, out):
+        out.copy_(torch.from_numpy(self.o.jprod(x.numpy(), v.numpy()))); return out
+
+    def jtprod_nln(self, x, v, out):
+        out.copy_(torch.from_numpy(self.o.jtprod(x.numpy(), v.numpy()))); return out
+
+    def hprod(self, x, y, v, out, obj_weight=1.0):
+        out.copy_(torch.from_numpy(self.o.hprod(x.numpy(), y.numpy(), v.numpy(), obj_weight))); return out
+
 
 def _worker(rank, world, port, which, q):
     sys.path.insert(0, ROOT)
@@ -67,6 +76,12 @@ def _worker(rank, world, port, which, q):
         assert np.array_equal(j.numpy(), full.jac_coord(x.numpy()))
         h = sm.hess_coord(x, y, torch.full((full.nnzh,), float("nan"), dtype=torch.float64), obj_weight=0.5)
         assert np.array_equal(h.numpy(), full.hess_coord(x.numpy(), y.numpy(), 0.5))
+        # matrix-free products: partial products of the shards, summed
+        v = torch.from_numpy(np.random.default_rng(2).standard_normal(full.nvar)); w = torch.from_numpy(np.random.default_rng(3).standard_normal(full.ncon))
+        e = lambda n: torch.empty(n, dtype=torch.float64)   # noqa: E731
+        np.testing.assert_allclose(sm.jprod_nln(x, v, e(full.ncon)).numpy(), full.jprod(x.numpy(), v.numpy()), **tol)
+        np.testing.assert_allclose(sm.jtprod_nln(x, w, e(full.nvar)).numpy(), full.jtprod(x.numpy(), w.numpy()), **tol)
+        np.testing.assert_allclose(sm.hprod(x, y, v, e(full.nvar), obj_weight=0.5).numpy(), full.hprod(x.numpy(), y.numpy(), v.numpy(), 0.5), **tol)
         # slices of all ranks tile each buffer exactly once
         for w_, n in ((1, full.nnzj), (2, full.nnzh)):
             cover = np.zeros(n, dtype=np.int64)
