@@ -39,7 +39,7 @@ exb_obj_async exb_grad exb_cons exb_jac_structure64 exb_jac_structure32 exb_jac 
 exb_hess_structure32 exb_hess exb_host_obj exb_host_grad exb_host_cons exb_host_jac exb_host_hess
 exb_host_jac_structure64 exb_host_hess_structure64 exb_shard exb_stats exb_last_error exb_abi_version
 exb_jprod exb_jtprod exb_hprod exb_compressed_dims exb_jac_structure_compressed64 exb_hess_structure_compressed64
-exb_jac_compressed exb_hess_compressed exb_set_timing exb_timings exb_kernel_choice""".split()
+exb_jac_compressed exb_hess_compressed exb_set_timing exb_timings exb_kernel_choice exb_host_bytes""".split()
 
 
 class ExbError(RuntimeError):
@@ -349,6 +349,12 @@ class ExaModel:
         o = np.zeros(4, dtype=np.int64)
         _check(lib().exb_kernel_choice(self.h, ("obj", "grad", "cons", "jac", "hess").index(callback), _np_ptr(o)))
         return {"min_blocks": int(o[0]), "persistent": bool(o[1]), "grid": int(o[2]), "owner_computes": bool(o[3])}
+
+    def host_bytes(self):
+        """(H2D, D2H) bytes moved by the last host-buffer callback on this handle."""
+        o = np.zeros(2, dtype=np.int64)
+        _check(lib().exb_host_bytes(self.h, _np_ptr(o)))
+        return int(o[0]), int(o[1])
 
     def stats(self):
         o = np.zeros(4, dtype=np.int64)

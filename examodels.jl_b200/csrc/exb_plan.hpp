@@ -59,6 +59,10 @@ struct PatternPlan {
   // iterator and xlo <= c <= xhi, so a tile of consecutive points reads one contiguous window of x (and of y)
   bool win = false;
   i64 xlo = 0, xhi = 0;
+  // part of x the pattern can read at all: shifts [rlo, rhi] relative to the range value plus fixed indices [flo, fhi]
+  // (1-based); xr_ok = false: indices come from iterator data, anything may be read
+  bool xr_ok = false, xr_shift = false, xr_fixed = false;
+  i64 rlo = 0, rhi = 0, flo = 0, fhi = 0;
 };
 
 struct Plan {
@@ -648,6 +652,24 @@ inline void compute_window(PatternPlan& p) {
   if (first || p.xhi - p.xlo > 4096) p.win = false;
 }
 
+inline void compute_xrange(PatternPlan& p) {
+  p.xr_ok = true; p.xr_shift = p.xr_fixed = false;
+  for (size_t q = 0; q < p.ir.nodes.size() && p.xr_ok; q++) {
+    if (p.ir.nodes[q].tag != T_VAR) continue;
+    i64 cf, ct;
+    if (!affine_index(p.ir, (int)p.ir.nodes[q].a, cf, ct)) { p.xr_ok = false; break; }
+    if (cf == 1 && p.ir.itr_kind == ITR_RANGE) {
+      if (!p.xr_shift || ct < p.rlo) p.rlo = ct;
+      if (!p.xr_shift || ct > p.rhi) p.rhi = ct;
+      p.xr_shift = true;
+    } else if (cf == 0) {
+      if (!p.xr_fixed || ct < p.flo) p.flo = ct;
+      if (!p.xr_fixed || ct > p.fhi) p.fhi = ct;
+      p.xr_fixed = true;
+    } else p.xr_ok = false;
+  }
+}
+
 inline std::string gen_pattern(PatternPlan& p, int index, bool windowed) {
   std::ostringstream o;
   const int ns1 = p.o1step, ns2 = p.o2step;
@@ -834,7 +856,7 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes) {
   pl.hess_windowed = getenv("EXB_TUNE_PERSISTENT") != nullptr && atoi(getenv("EXB_TUNE_PERSISTENT")) != 0;
   {
     bool any = false;
-    for (auto& p : pl.pats) { compute_window(p); if (p.o2step > 0) { any = true; pl.hess_windowed = pl.hess_windowed && p.win; } }
+    for (auto& p : pl.pats) { compute_window(p); compute_xrange(p); if (p.o2step > 0) { any = true; pl.hess_windowed = pl.hess_windowed && p.win; } }
     pl.hess_windowed = pl.hess_windowed && any;
   }
   for (size_t k = 0; k < pl.pats.size(); k++) o << gen_pattern(pl.pats[k], (int)k, pl.hess_windowed && pl.pats[k].win);

@@ -276,6 +276,8 @@ struct exb_model {
   bool prod_ready = false, cmp_ready = false;
   double *d_jacbuf = nullptr, *d_hessbuf = nullptr;
   std::vector<long long> lo, hi;   // local point range per pattern
+  long long x_lo = 0, x_hi = 0;    // [x_lo, x_hi): the part of x this handle's points can read (the host shims upload only that)
+  long long last_h2d = 0, last_d2h = 0;   // bytes moved by the last exb_host_* call
   // host shims
   cudaStream_t hstream = nullptr, hstream2 = nullptr;
   std::vector<cudaEvent_t> hev;
@@ -521,6 +523,22 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
         if (is32) a.i32mask |= (1LL << f);
       }
     }
+  }
+  {  // the part of x the local points can read: shifts of range values and fixed indices are known to the plan
+    long long xl = pl.m.nvar, xh = 0; bool all = false;
+    for (size_t k = 0; k < np && !all; k++) {
+      const exb::PatternPlan& p = pl.pats[k];
+      if (pa[k].n == 0) continue;
+      if (!p.xr_ok) { all = true; break; }
+      if (p.xr_shift) {
+        xl = std::min<long long>(xl, p.ir.range_start + pa[k].k0 + p.rlo - 1);
+        xh = std::max<long long>(xh, p.ir.range_start + pa[k].k0 + pa[k].n - 1 + p.rhi);
+      }
+      if (p.xr_fixed) { xl = std::min<long long>(xl, p.flo - 1); xh = std::max<long long>(xh, p.fhi); }
+    }
+    if (all || xl < 0 || xh > pl.m.nvar) { xl = 0; xh = pl.m.nvar; }
+    if (xh < xl) { xl = 0; xh = 0; }
+    m->x_lo = xl; m->x_hi = xh;
   }
   // per-pattern arguments into each module's constant bank (see EXB_PAT in exb_device.cuh)
   if ((int)np <= exb::EXB_CPAT_MAX && np > 0) {
@@ -1162,8 +1180,10 @@ static int host_in(exb_model* m, const double* x, const double* y) {
   int rc = host_stream(m); if (rc) return rc;
   const bool px = is_pinned(x);
   rc = ensure_host(m, &m->hx, &m->hx_n, &m->dx, &m->dx_n, px ? 0 : (size_t)pl.m.nvar, (size_t)pl.m.nvar); if (rc) return rc;
-  if (!px) memcpy(m->hx, x, (size_t)pl.m.nvar * 8);
-  CU_TRY(m, cudaMemcpyAsync(m->dx, px ? x : m->hx, (size_t)pl.m.nvar * 8, cudaMemcpyHostToDevice, m->hstream));
+  const size_t xn = (size_t)(m->x_hi - m->x_lo);   // only the part of x this handle's points can read (all of it unless sharded)
+  if (!px && xn) memcpy(m->hx + m->x_lo, x + m->x_lo, xn * 8);
+  if (xn) CU_TRY(m, cudaMemcpyAsync(m->dx + m->x_lo, (px ? x : m->hx) + m->x_lo, xn * 8, cudaMemcpyHostToDevice, m->hstream));
+  m->last_h2d = (long long)xn * 8 + (y ? pl.ncon * 8 : 0); m->last_d2h = 0;
   if (y) {
     const bool py = is_pinned(y);
     rc = ensure_host(m, &m->hy, &m->hy_n, &m->dy, &m->dy_n, py ? 0 : (size_t)pl.ncon, (size_t)pl.ncon); if (rc) return rc;
@@ -1178,6 +1198,7 @@ static int host_out(exb_model* m, double* out, const std::vector<std::pair<long 
   for (auto& s : sl) {
     const size_t n = (size_t)(s.second - s.first);
     if (n == 0) continue;
+    m->last_d2h += (long long)n * 8;
     if (is_pinned(out + s.first)) {
       CU_TRY(m, cudaMemcpyAsync(out + s.first, m->dout + s.first, n * 8, cudaMemcpyDeviceToHost, m->hstream));
     } else {
@@ -1227,10 +1248,11 @@ static int host_coo_pipelined(exb_model* m, int kn, const double* x, const doubl
   rc = ensure_host(m, &m->hx, &m->hx_n, &m->dx, &m->dx_n, 0, (size_t)pl.m.nvar); if (rc) return rc;
   if (y) { rc = ensure_host(m, &m->hy, &m->hy_n, &m->dy, &m->dy_n, 0, (size_t)pl.ncon); if (rc) return rc; }
   rc = ensure_host(m, &m->hout, &m->hout_n, &m->dout, &m->dout_n, 0, (size_t)total); if (rc) return rc;
-  CU_TRY(m, cudaMemcpyAsync(m->dx, x, (size_t)pl.m.nvar * 8, cudaMemcpyHostToDevice, m->hstream));
+  if (m->x_hi > m->x_lo) CU_TRY(m, cudaMemcpyAsync(m->dx + m->x_lo, x + m->x_lo, (size_t)(m->x_hi - m->x_lo) * 8, cudaMemcpyHostToDevice, m->hstream));
+  m->last_h2d = (m->x_hi - m->x_lo) * 8; m->last_d2h = 0;
   bool ywin = y != nullptr;   // multipliers can follow the windows only when every row is `o0 + k` (no augmentation in the list)
   for (int pi : lst) if (pl.pats[(size_t)pi].ir.kind == exb::KIND_AUG) ywin = false;
-  if (y && !ywin) CU_TRY(m, cudaMemcpyAsync(m->dy, y, (size_t)pl.ncon * 8, cudaMemcpyHostToDevice, m->hstream));
+  if (y && !ywin) { CU_TRY(m, cudaMemcpyAsync(m->dy, y, (size_t)pl.ncon * 8, cudaMemcpyHostToDevice, m->hstream)); m->last_h2d += pl.ncon * 8; }
   const long long csz = 1LL << L.g.shift, BLK = pl.block;
   std::vector<long long> bmin(lst.size()), bmax(lst.size());
   for (int w = 0; w < W; w++) {
@@ -1255,6 +1277,7 @@ static int host_coo_pipelined(exb_model* m, int kn, const double* x, const doubl
       if (ywin && p.ir.kind == exb::KIND_CON) {
         const long long r0 = p.o0 + m->lo[pi] + p0;
         CU_TRY(m, cudaMemcpyAsync(m->dy + r0, y + r0, (size_t)(p1 - p0) * 8, cudaMemcpyHostToDevice, m->hstream));
+        m->last_h2d += (p1 - p0) * 8;
       }
       const long long o = kn == KN_HESS ? p.o2 : p.o1;
       outs.push_back({o + (m->lo[pi] + p0) * L.ns[q], o + (m->lo[pi] + p1) * L.ns[q]});
@@ -1269,8 +1292,10 @@ static int host_coo_pipelined(exb_model* m, int kn, const double* x, const doubl
     }
     CU_TRY(m, cudaEventRecord(m->hev[(size_t)w], m->hstream));
     CU_TRY(m, cudaStreamWaitEvent(m->hstream2, m->hev[(size_t)w], 0));
-    for (auto& sl : outs)
+    for (auto& sl : outs) {
       CU_TRY(m, cudaMemcpyAsync(out + sl.first, m->dout + sl.first, (size_t)(sl.second - sl.first) * 8, cudaMemcpyDeviceToHost, m->hstream2));
+      m->last_d2h += (sl.second - sl.first) * 8;
+    }
   }
   CU_TRY(m, cudaStreamSynchronize(m->hstream2));
   CU_TRY(m, cudaStreamSynchronize(m->hstream));
@@ -1373,6 +1398,11 @@ int exb_timings(exb_model* m, double* ms8, int64_t* calls8, int reset) {
   }
   return EXB_OK;
   EXB_END
+}
+int exb_host_bytes(const exb_model* m, int64_t* o) {
+  if (!m || !o) return fail(EXB_ERR_HANDLE, "invalid handle");
+  o[0] = m->last_h2d; o[1] = m->last_d2h;
+  return EXB_OK;
 }
 int exb_kernel_choice(const exb_model* m, int callback, int64_t* o) {
   if (!m || !o) return fail(EXB_ERR_HANDLE, "invalid handle");

@@ -194,6 +194,9 @@ int exb_stats(const exb_model* m, int64_t* out4);
  * first-call tuner: out[0] = min-blocks-per-SM of the launch-shape variant (-1: not tuned yet), out[1] = 1 if the
  * persistent shared-memory-window form is in use (hess), out[2] = grid size, out[3] = 1 if grad uses the owner-computes kernel */
 int exb_kernel_choice(const exb_model* m, int callback, int64_t* out4);
+/* out[0] / out[1] = bytes copied host -> device / device -> host by the last exb_host_* call on this handle (a sharded
+ * handle uploads only the part of x its points can read and its own rows of y, and downloads only the slices it wrote) */
+int exb_host_bytes(const exb_model* m, int64_t* out2);
 
 /* Per-callback device timing: the TimedNLPModel role (src/utils.jl:271-408).  When on, every value callback is
  * bracketed by CUDA events on the caller's stream (no synchronisation); exb_timings synchronises on them and returns

@@ -241,3 +241,37 @@ def test_persistent_hessian_kernel(exa, torch_, which, monkeypatch):
             assert_close(got[mine], ref[mine], f"persistent hess shard (w={w})")
         else:
             assert_close(got, ref, f"persistent hess (w={w})")
+
+
+def test_sharded_host_shims_upload_only_what_the_shard_reads(exa, torch_):
+    """A sharded handle's host entry points copy the part of x its points can read (shifts of a range iterator are known
+    to the plan), its own rows of y and the slices it wrote -- and still match the oracle."""
+    from examodels_jl_b200 import models as M
+    from oracle.oracle_api import Oracle
+    torch = torch_
+    core = M.luksan_vlcek(400_000)
+    ora = Oracle.from_core(core)
+    x, y = inputs(core)
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()   # noqa: E731
+    xp, yp = pin(x), pin(y)
+    ref = ora.hess_coord(x, y, 0.5)
+    got = np.full(ora.nnzh, np.nan)
+    tot_h2d = tot_d2h = 0
+    for r in range(4):
+        m = exa.ExaModel(core, rank=r, world=4)
+        hp = pin(np.full(m.nnzh, np.nan))
+        m.hess_coord(xp, yp, hp, obj_weight=0.5)       # tuning call (plain path)
+        hp[:] = np.nan
+        m.hess_coord(xp, yp, hp, obj_weight=0.5)       # windowed path
+        h2d, d2h = m.host_bytes()
+        assert h2d <= 8 * (m.nvar // 4 + 8 + m.ncon // 4 + 8) and d2h <= 8 * (m.nnzh // 4 + 16), (h2d, d2h)
+        tot_h2d += h2d; tot_d2h += d2h
+        mine = ~np.isnan(hp)
+        assert not (mine & ~np.isnan(got)).any()
+        got[mine] = hp[mine]
+        g = np.full(m.nvar, np.nan)
+        m.grad(x, g)                                    # pageable buffers, partial x upload as well
+        og = Oracle.from_core(core); og.set_shard(r, 4)
+        assert_close(g, og.grad(x), f"host grad shard {r}")
+    assert d2h > 0 and tot_d2h == 8 * ora.nnzh
+    assert_close(got, ref, "sharded host hess, assembled")
