@@ -95,7 +95,7 @@ def cpu_hess_rate(n_points, threads, reps=1):
     return ora.nnzh / best, best
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -121,7 +121,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / steps
     val = ora.nnzh / dt
     sample = f"LV N={n} ({ora.nnzh} nnz) per step, same patterns as N=10^7; oracle/exa_oracle.cpp, {threads} host threads"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
@@ -129,7 +129,7 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def main():
@@ -142,8 +142,19 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE line, the JSON: anything a library prints on fd 1 meanwhile (NCCL's version banner, ...)
+    # is sent to stderr, and fd 1 is restored just before the line is written
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(obj), flush=True)
+
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import torch
     import torch.distributed as dist
@@ -156,7 +167,6 @@ def main():
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's own log lines (version banner) must not precede the JSON line on stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     E.build_library()
 
@@ -331,7 +341,7 @@ def main():
         out["cpu_baseline"] = cpu
     if full:
         out["full_callback"] = full
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
