@@ -93,5 +93,35 @@ def mixed_gradient():
     return c
 
 
+SPECIAL_SWEEPS = {   # argument sweeps inside each SpecialFunctions operator's domain, away from poles (ext/functionlist.jl)
+    "erf": (-4.0, 4.0), "erfc": (-3.0, 5.0), "erfi": (-2.5, 2.5), "erfcx": (-2.0, 30.0), "digamma": (-3.63, 14.0),
+    "trigamma": (-3.63, 14.0), "invdigamma": (-4.0, 3.0), "gamma": (-3.63, 6.0), "airyai": (-12.0, 4.0), "airybi": (-12.0, 4.0),
+    "airyaiprime": (-12.0, 4.0), "airybiprime": (-12.0, 4.0), "besselj0": (-15.0, 15.0), "bessely0": (0.3, 25.0),
+    "besselj1": (-15.0, 15.0), "bessely1": (0.3, 25.0), "dawson": (-9.0, 9.0), "erfinv": (-0.98, 0.98), "erfcinv": (0.02, 1.98),
+}
+
+
+def special_sweep_args(name, n):
+    lo, hi = SPECIAL_SWEEPS[name]
+    a = np.linspace(lo, hi, n)
+    if name in ("digamma", "trigamma", "gamma"):   # nudge points within 0.12 of a pole (non-positive integers) away
+        near = (a < 0.5) & (np.abs(a - np.round(a)) < 0.12)
+        a = np.where(near, np.round(a) + 0.37, a)
+    return a
+
+
+def special_sweep(n=257):
+    """One constraint pattern `op(x[i] + a_i)` per SpecialFunctions operator, a_i sweeping the operator's domain (x starts
+    at 0).  Pattern k owns rows / Jacobian slots / Hessian slots [k n, (k + 1) n)."""
+    from examodels_jl_b200 import graph as G
+    c = E.ExaCore(); x = c.add_var(n, start=np.zeros(n))
+    for name in G.SPECIAL_UNIVARIATE:
+        d = np.zeros(n, dtype=np.dtype([("i", "i8"), ("a", "f8")]))
+        d["i"] = np.arange(1, n + 1); d["a"] = special_sweep_args(name, n)
+        c.add_con(lambda p, nm=name: G._op1(nm, x[p.i] + p.a), d)
+    c.add_obj(lambda i: x[i] ** 2, range(1, n + 1))
+    return c
+
+
 EDGE = {"mixed_gradient": mixed_gradient, "only_objective": only_objective, "only_constraints": only_constraints, "empty_patterns": empty_patterns,
         "single_points_and_constants": single_points_and_constants, "self_loops": self_loops, "field_types": field_types}

@@ -34,17 +34,22 @@ PTS = {
 }
 for k in ("airybi", "airyaiprime", "airybiprime"):
     PTS[k] = PTS["airyai"]
-out = {"univariate": {}, "bivariate": {}}
-for name, f in F1.items():
-    xs = PTS.get(name, PTS["default"])
-    out["univariate"][name] = [[x, float(f(mp.mpf(x)))] for x in xs]
-# higher polygammas (used by the derivative entries of digamma / trigamma / invdigamma / gamma)
-out["polygamma2"] = [[x, float(mp.polygamma(2, mp.mpf(x)))] for x in PTS["digamma"]]
-out["polygamma3"] = [[x, float(mp.polygamma(3, mp.mpf(x)))] for x in PTS["digamma"]]
-B = [(0.7, 1.3), (2.5, 3.0), (0.05, 4.2), (11.5, 6.1), (30.0, 45.0)]
-out["bivariate"]["beta"] = [[a, b, float(mp.beta(a, b))] for a, b in B]
-out["bivariate"]["logbeta"] = [[a, b, float(mp.log(mp.beta(a, b)))] for a, b in B]
-path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "special_functions.json")
-with open(path, "w") as fh:
-    json.dump(out, fh, indent=0)
-print("wrote", path)
+def main():
+    out = {"univariate": {}, "bivariate": {}}
+    for name, f in F1.items():
+        xs = PTS.get(name, PTS["default"])
+        out["univariate"][name] = [[x, float(f(mp.mpf(x)))] for x in xs]
+    # higher polygammas (used by the derivative entries of digamma / trigamma / invdigamma / gamma)
+    out["polygamma2"] = [[x, float(mp.polygamma(2, mp.mpf(x)))] for x in PTS["digamma"]]
+    out["polygamma3"] = [[x, float(mp.polygamma(3, mp.mpf(x)))] for x in PTS["digamma"]]
+    B = [(0.7, 1.3), (2.5, 3.0), (0.05, 4.2), (11.5, 6.1), (30.0, 45.0)]
+    out["bivariate"]["beta"] = [[a, b, float(mp.beta(a, b))] for a, b in B]
+    out["bivariate"]["logbeta"] = [[a, b, float(mp.log(mp.beta(a, b)))] for a, b in B]
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "special_functions.json")
+    with open(path, "w") as fh:
+        json.dump(out, fh, indent=0)
+    print("wrote", path)
+
+
+if __name__ == "__main__":
+    main()

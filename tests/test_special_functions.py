@@ -101,3 +101,62 @@ def test_special_ops_fold_constants_like_the_reference():
     """A Real argument is evaluated eagerly (register.jl:70): erf(0.5) is a number, not a node."""
     assert abs(G.erf(0.5) - math.erf(0.5)) < 1e-15 and abs(G.beta(2.0, 3.0) - 1.0 / 12.0) < 1e-15
     assert isinstance(G.erf(G.Var(1)), G.Node1) and isinstance(G.beta(G.Var(1), 2.0), G.Node2)
+
+
+def _sweep_inputs(core):
+    meta = core.meta()
+    x = 0.004 * np.random.default_rng(4).uniform(-1.0, 1.0, meta["nvar"])
+    y = np.random.default_rng(5).uniform(0.5, 1.5, meta["ncon"])
+    return x, y
+
+
+def test_oracle_special_sweep_vs_mpmath_derivatives():
+    """f, f', f'' of every SpecialFunctions operator over its sweep: the oracle's cons / Jacobian / Hessian of `op(x + a)`
+    against mpmath's numerical differentiation of the function itself (an independent check of the derivative FORMULAS)."""
+    import importlib.util
+    import mpmath as mp
+    from edge_models import special_sweep, special_sweep_args
+    from oracle.oracle_api import Oracle
+    spec = importlib.util.spec_from_file_location("make_special_golden", os.path.join(ROOT, "tests", "golden", "make_special_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    F1 = gen.F1                                          # same mpmath definitions as the golden generator
+    mp.mp.dps = 30
+    n = 33
+    core = special_sweep(n)
+    o = Oracle.from_core(core)
+    x, y = _sweep_inputs(core)
+    c, j, h = o.cons(x), o.jac_coord(x), o.hess_coord(x, y, 0.0)
+    for kp, name in enumerate(G.SPECIAL_UNIVARIATE):
+        arg = x + special_sweep_args(name, n)
+        for k in range(n):
+            r = kp * n + k
+            t = mp.mpf(float(arg[k]))
+            f0, f1, f2 = (float(mp.diff(F1[name], t, q)) for q in (0, 1, 2))
+            scale = max(abs(f0), abs(f1), abs(f2), 1e-300)
+            ok = abs(c[r] - f0) <= 2e-9 * scale and abs(j[r] - f1) <= 2e-9 * scale and abs(h[r] - y[r] * f2) <= 8e-8 * scale
+            assert ok, (name, float(arg[k]), (c[r], f0), (j[r], f1), (h[r] / y[r], f2))
+
+
+@pytest.mark.gpu
+def test_gpu_special_sweep_matches_oracle(exa):
+    """Device special functions (libdevice + csrc/exb_special.h) over each operator's whole sweep: cons / jac / hess of
+    `op(x + a)` against the oracle, POINT BY POINT relative to that point's own (f, f', f'') scale."""
+    import torch
+    from edge_models import special_sweep, special_sweep_args
+    from oracle.oracle_api import Oracle
+    n = 257
+    core = special_sweep(n)
+    ora, m = Oracle.from_core(core), exa.ExaModel(core)
+    x, y = _sweep_inputs(core)
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    got = [m.cons_nln(dx, m.new(m.ncon)).cpu().numpy(), m.jac_coord(dx, m.new(m.nnzj)).cpu().numpy(),
+           m.hess_coord(dx, dy, m.new(m.nnzh), obj_weight=0.0).cpu().numpy()[: m.ncon]]
+    ref = [ora.cons(x), ora.jac_coord(x), ora.hess_coord(x, y, 0.0)[: ora.ncon]]
+    scale = np.maximum.reduce([np.abs(r) for r in ref]) + 1e-300
+    for g_, r_, what in zip(got, ref, ("cons", "jac", "hess")):
+        err = np.abs(g_ - r_) / scale
+        k = int(np.argmax(err))
+        name = G.SPECIAL_UNIVARIATE[k // n]
+        assert err[k] <= 1e-10, (f"{name} {what}: point {k % n} (arg {special_sweep_args(name, n)[k % n]:.4f}) got {g_[k]!r} "
+                                 f"ref {r_[k]!r} rel err {err[k]:.2e}")
