@@ -166,6 +166,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local)
+    near = None
+    if world > 1:   # one process per GPU: stay on the cores (and memory) next to this GPU before any pinned buffer exists
+        from examodels_jl_b200.parallel import bind_near_gpu
+        near = bind_near_gpu(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     E.build_library()
@@ -327,6 +331,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": f"Luksan-Vlcek N={args.n} per GPU (BASELINE configs[1]), hess_coord! only; nvar={m.nvar} ncon={m.ncon} nnzh={m.nnzh}",
                    "sharding": f"{world} contiguous iterator shards, no collective" if world > 1 else "single GPU",
+                   "cpu_binding": (f"rank 0 bound to {len(near)} cores local to its GPU (NVML affinity)" if near else "none"),
                    "l2": f"per step {alg_bytes / 1e6:.0f} MB of inputs+outputs > L2 ({L2_BYTES / 1e6:.0f} MB); no explicit flush",
                    "inputs": "x = x0 + 0.01 U(-1,1) seed 0; y ~ N(0,1) seed 1; obj_weight = 1"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

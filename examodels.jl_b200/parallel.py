@@ -21,6 +21,33 @@ results are compared at 1e-10, not bitwise.
 from __future__ import annotations
 
 
+def bind_near_gpu(device_index):
+    """Pin the calling process to the CPU cores NVML reports as local to `device_index` (its NUMA node / PCIe root), so
+    that page-locked staging buffers allocated afterwards are first-touched next to the GPU they feed.  With one process
+    per GPU on a multi-socket host this is what keeps the host-buffer entry points (exb_host_*) at PCIe speed instead of
+    crossing the socket interconnect.  Returns the CPU list, or None when NVML / affinity control is unavailable."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            pr = torch.cuda.get_device_properties(device_index)
+            bus = "%08X:%02X:%02X.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def shard_range(n, rank, world):
     """Contiguous shard of an n-point iterator (same rule as exb_create: lo = n*r/W)."""
     return n * rank // world, n * (rank + 1) // world
