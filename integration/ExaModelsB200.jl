@@ -104,7 +104,9 @@ function emit_pattern!(words, bufs, p, kind, base_index)
 end
 
 function ExaModels.build_extension(c::ExaCore{T,VT,B}; prod = false, kwargs...) where {T,VT,B<:B200Backend}
-    # `prod` needs no work here: the sorted structure behind exb_jprod / exb_jtprod / exb_hprod is built on first use
+    # `prod` needs no work here: exb_jprod / exb_jtprod / exb_hprod are fused into the derivative sweep (nothing to build);
+    # `sorted_products = true` selects the reference's COO + sorted-structure SpMV (EXB_FLAG_SORTED_PRODUCTS = 2, bitwise
+    # reproducible), whose structure is built on first use
     # patterns in ADD ORDER: both lists are stored newest-first (src/nlp.jl:536); the shared nnzh
     # counter (f.o2) orders objectives against constraints
     pats = Any[]
@@ -118,7 +120,8 @@ function ExaModels.build_extension(c::ExaCore{T,VT,B}; prod = false, kwargs...) 
         emit_pattern!(words, bufs, p, kind, base)
     end
     words[6] = length(bufs)
-    opt = Ref((Int32(c.backend.device), Int32(c.backend.rank), Int32(c.backend.world), Int32(0), Int64(0)))
+    flags = Int32(get(kwargs, :sorted_products, false) ? 2 : 0)
+    opt = Ref((Int32(c.backend.device), Int32(c.backend.rank), Int32(c.backend.world), flags, Int64(0)))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     ptrs = Ptr{Cvoid}[pointer(b) for b in bufs]
     GC.@preserve bufs check(ccall((:exb_create, LIB), Cint,
