@@ -2,6 +2,7 @@
 // that follow the generated per-pattern kernels, and the build-time sort that prepares them.
 //
 //   exb_fx_compress   <- compress_to_dense   ext/ExaModelsKernelAbstractions.jl:691-697
+//   exb_fx_sum        <- sum(objbuffer)      ext:259
 //   exb_fx_sort_runs  <- sort! + getptr      ext:12-18,44-53,699-715   (build time; CUB radix sort)
 //
 // No atomics: every dense target is owned by one thread which adds its (pre-sorted) slots in a
@@ -71,6 +72,23 @@ __global__ void k_make_keys(const long long* __restrict__ major, const long long
 __global__ void k_decode_keys(const long long* __restrict__ keys, long long mult, long long* major, long long* minor, long long n) {
   const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
   if (t < n) { major[t] = keys[t] / mult; minor[t] = keys[t] % mult; }
+}
+
+// deterministic sum of n partials into out[0]: fixed per-thread strided order + fixed tree
+__global__ void __launch_bounds__(1024) k_sum(const double* __restrict__ part, long long n, double* __restrict__ out) {
+  __shared__ double sm[32];
+  double v = 0.0;
+  for (long long k = threadIdx.x; k < n; k += 1024) v += part[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = sm[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) out[0] = v;
+  }
 }
 
 __global__ void k_fill_ll(long long* p, long long n, long long v) {
@@ -165,6 +183,11 @@ cudaError_t exb_fx_make_keys(const long long* major, const long long* minor, lon
 cudaError_t exb_fx_decode_keys(const long long* keys, long long mult, long long* major, long long* minor, long long n, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   k_decode_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, mult, major, minor, n);
+  return cudaGetLastError();
+}
+
+cudaError_t exb_fx_sum(const double* part, long long n, double* out, cudaStream_t st) {
+  k_sum<<<1, 1024, 0, st>>>(part, n, out);
   return cudaGetLastError();
 }
 

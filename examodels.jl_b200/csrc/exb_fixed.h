@@ -8,6 +8,7 @@ cudaError_t exb_fx_compress(const double* buf, const void* ptr, const void* slot
                             long long nt, double* y, int accumulate, cudaStream_t st);
 cudaError_t exb_fx_pack_runs(void** slot, void** target, void** ptr, long long nslots, long long nruns, long long max_index,
                              int* idx32, int* dense, cudaStream_t st);
+cudaError_t exb_fx_sum(const double* part, long long n, double* out, cudaStream_t st);
 cudaError_t exb_fx_fill(long long* p, long long n, long long v, cudaStream_t st);
 cudaError_t exb_fx_sort_runs(const long long* keys, long long n, long long** slot_out, long long** target_out,
                              long long** ptr_out, long long* nruns_out, long long* nslots_out, cudaStream_t st);

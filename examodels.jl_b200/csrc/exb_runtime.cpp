@@ -264,7 +264,7 @@ struct exb_model {
   std::vector<void*> dev;      // everything cudaMalloc'ed by the handle
   size_t dev_bytes = 0;
   double* d_theta = nullptr;
-  double* d_objpart = nullptr; double* d_obj = nullptr; unsigned* d_counter = nullptr;
+  double* d_objpart = nullptr; double* d_obj = nullptr;
   double* d_gradbuf = nullptr; double* d_conbuf = nullptr;
   // sorted (target, slot) lists: grad (ext:39-46) and constraint augmentation (ext:48-53)
   void *g_slot = nullptr, *g_target = nullptr, *g_ptr = nullptr; long long g_runs = 0; int g_i32 = 0, g_dense = 0;
@@ -665,8 +665,6 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
   rc = dmalloc(m, (void**)&m->d_objpart, (size_t)(m->k[KN_OBJ].nblocks + 1) * 8); if (rc) return rc;
   CU_TRY(m, cudaMemset(m->d_objpart, 0, (size_t)(m->k[KN_OBJ].nblocks + 1) * 8));   // padding blocks never write
   rc = dmalloc(m, (void**)&m->d_obj, 8); if (rc) return rc;
-  rc = dmalloc(m, (void**)&m->d_counter, 8); if (rc) return rc;
-  CU_TRY(m, cudaMemset(m->d_counter, 0, 8));
   rc = dmalloc(m, (void**)&m->d_gradbuf, (size_t)pl.nnzg * 8); if (rc) return rc;
   rc = dmalloc(m, (void**)&m->d_conbuf, (size_t)pl.nconaug * 8); if (rc) return rc;
   // gradient sparsity: (var, slot) sorted by var (ext:39-46)
@@ -868,12 +866,11 @@ int exb_obj_async(exb_model* m, const double* x, double* out_dev, void* stream) 
   EXB_GUARD(m);
   TimeScope ts_(m, CB_OBJ, stream);
   cudaStream_t st = (cudaStream_t)stream;
-  if (!m->k[KN_OBJ].fn || m->k[KN_OBJ].nblocks == 0) {   // no objective term evaluated by this handle
-    CU_TRY(m, cudaMemsetAsync(out_dev, 0, 8, st));
-    return EXB_OK;
-  }
-  ExbCall c{}; c.x = x; c.th = m->d_theta; c.out = out_dev; c.out2 = m->d_objpart; c.counter = m->d_counter;
-  return launch(m, KN_OBJ, c, st);   // value + last-block reduction in one launch (kerf + sum(objbuffer), ext:253-271)
+  ExbCall c{}; c.x = x; c.th = m->d_theta; c.out2 = m->d_objpart;
+  int rc = launch(m, KN_OBJ, c, st); if (rc) return rc;
+  CU_TRY(m, exb_fx_sum(m->d_objpart, m->k[KN_OBJ].nblocks, out_dev, st));
+  m->launches++; m->last_launches++;
+  return EXB_OK;
   EXB_END
 }
 int exb_obj(exb_model* m, const double* x, double* out_host, void* stream) {
