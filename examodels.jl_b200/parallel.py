@@ -122,13 +122,25 @@ class ShardedExaModel:
         for r in range(self.world):
             src = self.dist.get_global_rank(self.group, r) if self.group is not None else r
             jobs += [(vals[lo:hi], src) for lo, hi in self.slices(which, r)]
-        try:      # one NCCL group launch for all (pattern, owner) broadcasts instead of one launch each
-            from torch.distributed.distributed_c10d import _coalescing_manager
-            with _coalescing_manager(group=self.group, device=vals.device, async_ops=True) as cm:
-                for t, src in jobs:
-                    self.dist.broadcast(t, src=src, group=self.group)
-            cm.wait()
-        except Exception:
+        coalesced = False
+        if self.dist.get_backend(self.group) == "nccl":
+            # one NCCL group launch for all (pattern, owner) broadcasts instead of one launch each.  Only attempted on NCCL:
+            # a failed coalescing context on another backend can leave the group in "coalescing" state, in which later
+            # collectives are queued instead of executed.
+            try:
+                from torch.distributed.distributed_c10d import _coalescing_manager
+                with _coalescing_manager(group=self.group, device=vals.device, async_ops=True) as cm:
+                    for t, src in jobs:
+                        self.dist.broadcast(t, src=src, group=self.group)
+                cm.wait()
+                coalesced = True
+            except Exception:
+                try:
+                    from torch.distributed.distributed_c10d import _world
+                    _world.pg_coalesce_state.pop(self.group if self.group is not None else self.dist.group.WORLD, None)
+                except Exception:
+                    pass
+        if not coalesced:
             works = [self.dist.broadcast(t, src=src, group=self.group, async_op=True) for t, src in jobs]
             for w in works:
                 w.wait()

@@ -1074,7 +1074,8 @@ void ora_jprod(void* h, const double* x, const double* v, double* Jv) {
     if (p.kind == KIND_OBJ) continue;
     Work w; w.size(p.t.size());
     Ctx c; c.p = &p; c.X = x; c.TH = m->theta.data(); c.w = &w;
-    for (i64 k = 0; k < p.nitr; k++) {
+    i64 lo, hi; shard_of(*m, p, lo, hi);   // shard mode (test aid): partial product of this shard's points
+    for (i64 k = lo; k < hi; k++) {
       point(c, k); fwd(c, p.root, 1);
       Sink s; std::memset(&s, 0, sizeof s); s.mode = M_JPROD; s.v = v; s.out = Jv; s.row = offset0(c);
       int cnt = 0; rpass1(c, p.root, s, cnt, 1.0);
@@ -1088,7 +1089,8 @@ void ora_jtprod(void* h, const double* x, const double* v, double* Jtv) {
     if (p.kind == KIND_OBJ) continue;
     Work w; w.size(p.t.size());
     Ctx c; c.p = &p; c.X = x; c.TH = m->theta.data(); c.w = &w;
-    for (i64 k = 0; k < p.nitr; k++) {
+    i64 lo, hi; shard_of(*m, p, lo, hi);   // shard mode (test aid): partial product of this shard's points
+    for (i64 k = lo; k < hi; k++) {
       point(c, k); fwd(c, p.root, 1);
       Sink s; std::memset(&s, 0, sizeof s); s.mode = M_JTPROD; s.v = v; s.out = Jtv; s.row = offset0(c);
       int cnt = 0; rpass1(c, p.root, s, cnt, 1.0);
@@ -1102,7 +1104,8 @@ void ora_hprod(void* h, const double* x, const double* y, const double* v, doubl
     if (p.kind != KIND_OBJ && !y) continue;
     Work w; w.size(p.t.size());
     Ctx c; c.p = &p; c.X = x; c.TH = m->theta.data(); c.w = &w;
-    for (i64 k = 0; k < p.nitr; k++) {
+    i64 lo, hi; shard_of(*m, p, lo, hi);   // shard mode (test aid): partial product of this shard's points
+    for (i64 k = lo; k < hi; k++) {
       point(c, k); fwd(c, p.root, 2);
       double adj1 = p.kind == KIND_OBJ ? obj_weight : y[offset0(c) - 1];
       Sink s; std::memset(&s, 0, sizeof s); s.mode = M_HPROD; s.v = v; s.out = Hv;
