@@ -121,3 +121,42 @@ def test_front_end_tree_shapes():
     assert s.inner1.op == "+" and isinstance(s.inner2, G.Var)
     assert x[d] == x[d] and x[d + 1] != x[d]                                       # === on index expressions
     assert x[3].i == 3 and isinstance(x[d].i, G.Node2)                             # nlp.jl:908,922
+
+
+def _generated(core):
+    return E.Plan(core).source().split("generated by exb_plan")[1]
+
+
+def test_index_equality_is_decided_at_build_time_for_affine_maps():
+    """`i == j ? 2adj : adj` (src/hessian.jl:261-266) needs a run-time compare only when the two index expressions can
+    coincide: affine maps of a range iterator are decided by the plan, data-driven indices are not."""
+    import numpy as np
+    from examodels_jl_b200.graph import sin
+
+    def model(body, itr):
+        c = E.ExaCore(); x = c.add_var(64, start=np.linspace(0.1, 0.9, 64))
+        c.add_con(lambda i: body(x, i), itr)
+        return c
+    assert "exb_twice_if_eq" not in _generated(model(lambda x, i: x[i] * x[i + 1], range(1, 30)))          # never equal
+    assert "exb_twice_if_eq" not in _generated(model(lambda x, i: sin(x[i] * x[2 * i + 5]), range(1, 25)))   # i = 2i + 5 has no solution in range
+    assert "exb_twice_if_eq" in _generated(model(lambda x, i: x[i] * x[2 * i - 3], range(1, 30)))          # equal at i = 3
+    assert "exb_twice_if_eq" not in _generated(model(lambda x, i: x[i] * x[2 * i - 3], range(4, 30)))      # ... which is outside this range
+    d = np.zeros(5, dtype=np.dtype([("f", "i8"), ("t", "i8")])); d["f"] = [1, 2, 3, 4, 5]; d["t"] = [2, 2, 4, 4, 6]
+    assert "exb_twice_if_eq" in _generated(model(lambda x, b: x[b.f] * x[b.t], d))                         # data: run-time compare
+
+
+def test_persistent_kernel_is_opt_in_and_needs_windows(monkeypatch):
+    lv = M.luksan_vlcek(50)
+    assert "exb_hessp_g0" not in _generated(lv)
+    monkeypatch.setenv("EXB_TUNE_PERSISTENT", "1")
+    src = _generated(lv)
+    assert "exb_hessp_g0" in src and "XLO = 0, XHI = 2" in src and "XLO = -1, XHI = 0" in src      # LV constraint / objective windows
+    assert "exb_hessp_g0" not in _generated(M.luksan_vlcek_aug(10, 2))                             # data-indexed (product iterator): no window
+    assert "exb_hessp_g0" not in _generated(M.pattern_family(50, 8))
+
+
+def test_fixed_index_variables_bypass_the_window():
+    """A variable at a fixed index (the rocket's step length) is read with ExbX*::ldc, everything else with ::ld."""
+    src = _generated(M.goddard_rocket(20))
+    assert "x.ldc(" in src and "x.ld(" in src
+    assert "x.ldc(" not in _generated(M.luksan_vlcek(20))
