@@ -53,10 +53,19 @@ def build_library(force=False):
     srcs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)
             if f.endswith((".cpp", ".cu", ".cuh", ".hpp", ".h")) and f != "exb_embed.cpp"]
     srcs.append(os.path.join(_HERE, "..", "include", "exa_b200.h"))
-    stale = (not os.path.exists(_LIBPATH)
-             or any(os.path.getmtime(s) > os.path.getmtime(_LIBPATH) for s in srcs))
-    if force or stale:
-        subprocess.check_call(["make", "-s", "-C", _CSRC, "libexa_b200.so"])
+    def stale():
+        return (not os.path.exists(_LIBPATH)
+                or any(os.path.getmtime(s) > os.path.getmtime(_LIBPATH) for s in srcs))
+    if force or stale():
+        # the ranks of one job (torchrun) may all get here at once on a fresh checkout: one builds, the others wait
+        import fcntl
+        with open(os.path.join(_CSRC, ".build.lock"), "w") as lk:
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            try:
+                if force or stale():
+                    subprocess.check_call(["make", "-s", "-C", _CSRC, "libexa_b200.so"])
+            finally:
+                fcntl.flock(lk, fcntl.LOCK_UN)
     return _LIBPATH
 
 
