@@ -17,6 +17,7 @@
 #include <sys/file.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <zlib.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -213,9 +214,48 @@ std::string shq(const std::string& p) {   // single-quote a path for the shell
 
 bool file_exists(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 && st.st_size > 0; }
 
+// Compiled modules are kept gzip-compressed in the cache (`<hash>.cubin.gz`): ~80 % of a cubin built with -lineinfo is the
+// embedded debug PTX text, which compresses 6x, and the cache travels with every snapshot of the tree.  EXB_KEEP_CUBIN=1
+// keeps the raw file next to it (cuobjdump / nvdisasm).
+bool module_cached(const std::string& cubin) { return file_exists(cubin + ".gz") || file_exists(cubin); }
+bool gz_compress_file(const std::string& in, const std::string& out) {
+  std::ifstream f(in, std::ios::binary);
+  std::vector<char> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  if (buf.empty()) return false;
+  const std::string tmp = out + ".tmp" + std::to_string((long)getpid());
+  gzFile g = gzopen(tmp.c_str(), "wb6");
+  if (!g) return false;
+  size_t off = 0; bool ok = true;
+  while (off < buf.size() && ok) {
+    const unsigned n = (unsigned)std::min<size_t>(buf.size() - off, 1u << 24);
+    ok = gzwrite(g, buf.data() + off, n) == (int)n;
+    off += n;
+  }
+  ok = (gzclose(g) == Z_OK) && ok;
+  if (!ok || rename(tmp.c_str(), out.c_str()) != 0) { unlink(tmp.c_str()); return false; }
+  return true;
+}
+bool read_module(const std::string& cubin, std::vector<char>& image) {
+  image.clear();
+  if (file_exists(cubin)) {   // a raw module (EXB_KEEP_CUBIN, or a cache written by an older build) wins
+    std::ifstream f(cubin, std::ios::binary);
+    image.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+    if (!image.empty()) return true;   // (else: another process compressed + removed it meanwhile: read the .gz)
+  }
+  gzFile g = gzopen((cubin + ".gz").c_str(), "rb");
+  if (!g) return false;
+  std::vector<char> chunk(1u << 22);
+  int n;
+  while ((n = gzread(g, chunk.data(), (unsigned)chunk.size())) > 0) image.insert(image.end(), chunk.begin(), chunk.begin() + n);
+  const bool ok = n == 0;
+  gzclose(g);
+  if (!ok) image.clear();
+  return ok && !image.empty();
+}
+
 int compile_plan(exb_plan* p, bool allow_compile) {
   bool all = true;
-  for (auto& v : p->var) all = all && file_exists(v.cubin_path);
+  for (auto& v : p->var) all = all && module_cached(v.cubin_path);
   if (all) { p->from_cache = true; return EXB_OK; }
   if (!allow_compile) return fail(EXB_ERR_COMPILE, "kernel module " + p->cubin_path + " is not cached and EXB_FLAG_NO_COMPILE is set");
   // serialise concurrent builders of the same model (ranks of one job, parallel tests)
@@ -226,7 +266,7 @@ int compile_plan(exb_plan* p, bool allow_compile) {
   std::string cmd;   // the variants compile concurrently: one shell, background jobs, wait
   std::vector<const Variant*> todo;
   for (auto& v : p->var) {
-    if (file_exists(v.cubin_path)) continue;
+    if (module_cached(v.cubin_path)) continue;
     { std::ofstream f(v.cu_path); f << v.source; }
     std::string tmp = v.cubin_path + ".tmp" + std::to_string((long)getpid());
     cmd += "( " + shq(nvcc_path()) + " " + NVCC_FLAGS_CLEAN + " -o " + shq(tmp) + " " + shq(v.cu_path) + " > " + shq(v.cubin_path + ".log") +
@@ -238,7 +278,10 @@ int compile_plan(exb_plan* p, bool allow_compile) {
     int st = system(cmd.c_str());
     (void)st;
     for (const Variant* v : todo) {
-      if (file_exists(v->cubin_path)) continue;
+      if (file_exists(v->cubin_path)) {   // compiled: keep it compressed
+        if (gz_compress_file(v->cubin_path, v->cubin_path + ".gz") && !getenv("EXB_KEEP_CUBIN")) unlink(v->cubin_path.c_str());
+        continue;
+      }
       std::ifstream lf(v->cubin_path + ".log");
       std::stringstream ss; ss << lf.rdbuf();
       std::string msg = ss.str();
@@ -475,9 +518,7 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
   CUresult r = CUDA_SUCCESS;
   for (auto& v : P->var) {
     std::vector<char> image;
-    std::ifstream f(v.cubin_path, std::ios::binary);
-    image.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
-    if (image.empty()) return fail(EXB_ERR_COMPILE, "cannot read " + v.cubin_path);
+    if (!read_module(v.cubin_path, image)) return fail(EXB_ERR_COMPILE, "cannot read " + v.cubin_path + "[.gz]");
     CUmodule mod = nullptr;
     r = g_drv.ModuleLoadData(&mod, image.data());
     if (r != CUDA_SUCCESS) return fail(EXB_ERR_COMPILE, "cuModuleLoadData(" + v.cubin_path + "): " + cu_err(r));

@@ -160,3 +160,26 @@ def test_fixed_index_variables_bypass_the_window():
     src = _generated(M.goddard_rocket(20))
     assert "x.ldc(" in src and "x.ld(" in src
     assert "x.ldc(" not in _generated(M.luksan_vlcek(20))
+
+
+def test_kernel_modules_are_cached_compressed(tmp_path, monkeypatch):
+    """nvcc output is kept as `<hash>.cubin.gz` (the debug PTX text of -lineinfo is ~80 % of a cubin and compresses 6x);
+    the decompressed image is a loadable sm_100a ELF with every callback kernel in it."""
+    import gzip
+    import subprocess
+    monkeypatch.setenv("EXB_CACHE_DIR", str(tmp_path))
+    p = E.Plan(M.luksan_vlcek(30))
+    path = p.compile()
+    assert path.startswith(str(tmp_path)) and not os.path.exists(path) and os.path.exists(path + ".gz")
+    raw = gzip.open(path + ".gz", "rb").read()
+    assert raw[:4] == b"\x7fELF" and len(raw) > 5 * os.path.getsize(path + ".gz") / 2
+    (tmp_path / "m.cubin").write_bytes(raw)
+    out = subprocess.run(["cuobjdump", "-res-usage", str(tmp_path / "m.cubin")], capture_output=True, text=True).stdout
+    for k in ("exb_hess_g0", "exb_jac_g0", "exb_ggrad_g0", "exb_cons_g0", "exb_obj_g0", "exb_hprod_g0"):
+        assert f"Function {k}:" in out
+    again = E.Plan(M.luksan_vlcek(31))          # same source: cache hit on the compressed module, nothing recompiled
+    t0 = os.path.getmtime(path + ".gz")
+    assert again.compile() == path and os.path.getmtime(path + ".gz") == t0
+    monkeypatch.setenv("EXB_KEEP_CUBIN", "1")   # development: keep the raw module next to it
+    q = E.Plan(M.luksan_vlcek(30, order="guide")).compile()
+    assert os.path.exists(q) and os.path.exists(q + ".gz")
