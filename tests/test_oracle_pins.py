@@ -262,3 +262,51 @@ def test_add_par_values():
     c1, c2 = _par_models()
     np.testing.assert_allclose(Oracle.from_core(c1).cons(np.ones(5)), [10.0, 20.0, 30.0])
     np.testing.assert_allclose(Oracle.from_core(c2).cons(np.ones(12)), [1.0, 5.0, 9.0])
+
+
+# ---- nnzj / nnzh hard-coded in the reference's own tests for MOI-built models: test/JuMPTest/JuMPTest.jl ------------------
+def _term_steps(body, nvar=6):
+    """(o1step, o2step) of one pattern as both the oracle and the planner compute them."""
+    import examodels_jl_b200 as E
+    c = E.ExaCore(); x = c.add_var(nvar, start=np.linspace(0.2, 0.9, nvar))
+    c.add_con(lambda i: body(x, i), range(1, 2))
+    o, p = Oracle.from_core(c), E.Plan(c)
+    a, b = o.pattern_info(0), p.pattern_info(0)
+    assert (a["o1step"], a["o2step"]) == (b["o1step"], b["o2step"])
+    return a["o1step"], a["o2step"]
+
+
+def test_jump_suite_hard_coded_counts():
+    """The MOI bridge turns every top-level term of a scalar nonlinear function into its own pattern, so the counts the
+    reference's JuMP tests hard-code are sums of per-term (o1step, o2step) -- reproducible without the bridge itself."""
+    from examodels_jl_b200.graph import cos, exp, sin
+    # JuMPTest.jl:398-405: p - 1.2 vmf^2 - 0.7 vmf vmt cos(vaf - vat) - 0.3 vmf vmt sin(vaf - vat): nnzj 10, nnzh 21
+    terms = [lambda x, i: x[i], lambda x, i: 1.2 * x[i + 1] ** 2,
+             lambda x, i: 0.7 * x[i + 1] * x[i + 2] * cos(x[i + 3] - x[i + 4]),
+             lambda x, i: 0.3 * x[i + 1] * x[i + 2] * sin(x[i + 3] - x[i + 4])]
+    steps = [_term_steps(t) for t in terms]
+    assert steps == [(1, 0), (1, 1), (4, 10), (4, 10)]
+    assert (sum(s[0] for s in steps), sum(s[1] for s in steps)) == (10, 21)
+    assert (4 * 10, 4 * 21) == (40, 84)                                        # :493-494, the same row batched over K = 4
+    # :424-431: sin(x) + x^2 + cos(x - y): nnzj 4, nnzh 5
+    steps = [_term_steps(t) for t in (lambda x, i: sin(x[i]), lambda x, i: x[i] ** 2, lambda x, i: cos(x[i] - x[i + 1]))]
+    assert steps == [(1, 1), (1, 1), (2, 3)] and (sum(s[0] for s in steps), sum(s[1] for s in steps)) == (4, 5)
+    # :446-455: exp(sin(x) + x^2 + cos(x - y)) is ONE term: nnzo 2 (x and y), nnzh 3
+    assert _term_steps(lambda x, i: exp(sin(x[i]) + x[i] ** 2 + cos(x[i] - x[i + 1]))) == (2, 3)
+    # :476-482: sin(z1 z2), sin(z3 z3), sin(z3 z4): nnzj 5, nnzh 7
+    steps = [_term_steps(t) for t in (lambda x, i: sin(x[i] * x[i + 1]), lambda x, i: sin(x[i + 2] * x[i + 2]), lambda x, i: sin(x[i + 2] * x[i + 3]))]
+    assert steps == [(2, 3), (1, 1), (2, 3)] and (sum(s[0] for s in steps), sum(s[1] for s in steps)) == (5, 7)
+
+
+def test_jump_suite_parameter_objective_values():
+    """JuMPTest.jl:458-473: sum(sin(p x_i)) with a Parameter p = 0.4: nnzo 8, nnzh 8, obj and grad in closed form."""
+    import examodels_jl_b200 as E
+    from examodels_jl_b200.graph import sin
+    c = E.ExaCore(); x = c.add_var(8, start=np.zeros(8)); p = c.add_par([0.4])
+    c.add_obj(lambda i: sin(p[1] * x[i]), range(1, 9))
+    o = Oracle.from_core(c)
+    info = o.pattern_info(0)
+    assert (info["o1step"] * 8, info["o2step"] * 8) == (8, 8) and o.nnzh == 8
+    pt = np.linspace(-0.7, 0.7, 8)
+    assert abs(o.obj(pt) - np.sin(0.4 * pt).sum()) < 1e-14
+    np.testing.assert_allclose(o.grad(pt), 0.4 * np.cos(0.4 * pt), rtol=1e-14)
