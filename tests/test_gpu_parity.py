@@ -275,3 +275,28 @@ def test_sharded_host_shims_upload_only_what_the_shard_reads(exa, torch_):
         assert_close(g, og.grad(x), f"host grad shard {r}")
     assert d2h > 0 and tot_d2h == 8 * ora.nnzh
     assert_close(got, ref, "sharded host hess, assembled")
+
+
+def test_reference_ipopt_solution_is_a_kkt_point_on_the_gpu(exa, torch_):
+    """The reference-produced fixture of docs/src/develop.md:84-105 (Ipopt solution + multipliers of LV N=10) through the CUDA
+    path: constraints vanish, grad f + J' lambda = 0, the reduced Lagrangian Hessian is positive definite."""
+    import json
+    import os
+    from examodels_jl_b200 import models as M
+    torch = torch_
+    sol = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "known_answers.json")))["lv10_ipopt_solution"]
+    x, lam = np.array(sol["x"]), np.array(sol["multipliers"])
+    m = exa.ExaModel(M.luksan_vlcek(10, order="guide"))
+    dx, dl = torch.from_numpy(x).cuda(), torch.from_numpy(lam).cuda()
+    jr, jc = m.new(m.nnzj, torch.int64), m.new(m.nnzj, torch.int64); m.jac_structure(jr, jc)
+    J = np.zeros((m.ncon, m.nvar)); np.add.at(J, (jr.cpu().numpy() - 1, jc.cpu().numpy() - 1), m.jac_coord(dx, m.new(m.nnzj)).cpu().numpy())
+    g = m.grad(dx, m.new(m.nvar)).cpu().numpy()
+    c = m.cons_nln(dx, m.new(m.ncon)).cpu().numpy()
+    assert np.abs(c).max() < 1e-10 and np.abs(g + J.T @ lam).max() < 2e-8
+    jt = m.jtprod_nln(dx, dl, m.new(m.nvar)).cpu().numpy()          # the fused J' v kernel gives the same residual
+    assert np.abs(g + jt).max() < 2e-8
+    hr, hc = m.new(m.nnzh, torch.int64), m.new(m.nnzh, torch.int64); m.hess_structure(hr, hc)
+    L = np.zeros((m.nvar, m.nvar)); np.add.at(L, (hr.cpu().numpy() - 1, hc.cpu().numpy() - 1), m.hess_coord(dx, dl, m.new(m.nnzh)).cpu().numpy())
+    H = L + np.tril(L, -1).T
+    Z = np.linalg.svd(J)[2][m.ncon:].T
+    assert np.linalg.eigvalsh(Z.T @ H @ Z).min() > 0.0

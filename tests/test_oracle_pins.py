@@ -310,3 +310,30 @@ def test_jump_suite_parameter_objective_values():
     pt = np.linspace(-0.7, 0.7, 8)
     assert abs(o.obj(pt) - np.sin(0.4 * pt).sum()) < 1e-14
     np.testing.assert_allclose(o.grad(pt), 0.4 * np.cos(0.4 * pt), rtol=1e-14)
+
+
+def _kkt_residuals(cons, grad, jac_vals, jr, jc, nvar, ncon):
+    sol = KA["lv10_ipopt_solution"]
+    lam = np.array(sol["multipliers"])
+    J = np.zeros((ncon, nvar)); np.add.at(J, (np.asarray(jr) - 1, np.asarray(jc) - 1), jac_vals)
+    return float(np.abs(cons).max()), float(np.abs(grad + J.T @ lam).max())
+
+
+@pytest.mark.parametrize("order", ["guide", "bench"])
+def test_reference_ipopt_solution_is_a_kkt_point_of_the_oracle(order):
+    """A fixture PRODUCED BY THE REFERENCE: the Ipopt solution and multipliers of LV N=10 printed in docs/src/develop.md:84-105.
+    At that point the oracle's constraints vanish and grad f + J' lambda = 0 -- which pins cons, grad!, jac_coord! and
+    jac_structure! together against numbers that came out of ExaModels itself (to the precision of an Ipopt solve)."""
+    core = M.luksan_vlcek(10, order=order)
+    o = Oracle.from_core(core)
+    x = np.array(KA["lv10_ipopt_solution"]["x"])
+    jr, jc = o.jac_structure()
+    c_res, kkt_res = _kkt_residuals(o.cons(x), o.grad(x), o.jac_coord(x), jr, jc, o.nvar, o.ncon)
+    assert c_res < 1e-10 and kkt_res < 2e-8, (c_res, kkt_res)
+    # and it is a strict local minimiser on the constraint null space: the reduced Lagrangian Hessian is positive definite
+    hr, hc = o.hess_structure()
+    L = np.zeros((o.nvar, o.nvar)); np.add.at(L, (hr - 1, hc - 1), o.hess_coord(x, np.array(KA["lv10_ipopt_solution"]["multipliers"]), 1.0))
+    H = L + np.tril(L, -1).T
+    J = np.zeros((o.ncon, o.nvar)); np.add.at(J, (jr - 1, jc - 1), o.jac_coord(x))
+    Z = np.linalg.svd(J)[2][o.ncon:].T                      # null-space basis of J (2 columns)
+    assert np.linalg.eigvalsh(Z.T @ H @ Z).min() > 0.0
