@@ -14,9 +14,17 @@
 //      and the raw traversal counts 10 / 21 pinned by
 //     test/JuMPTest/JuMPTest.jl:404-405,
 //   * closed-form cons values of test/NLPTest/conaug_test.jl:86-213,
+//   * every nnzj / nnzh hard-coded in test/JuMPTest/JuMPTest.jl (per-term slot counts),
 //   * derivative tables against finite differences / sympy as in
-//     test/ADTest/ADTest.jl:298-374.
-// No stored numeric derivative vectors exist in the reference tree.
+//     test/ADTest/ADTest.jl:298-374,
+//   * the one numeric fixture the reference itself produced: the Ipopt solution and
+//     multipliers of LV N=10 printed in docs/src/develop.md:84-105, which must be a KKT
+//     point of this restatement (cons = 0, grad f + J' lambda = 0 to the precision of the
+//     solve: pins cons, grad!, jac_coord!, jac_structure! against reference output),
+//   * the SpecialFunctions-extension values against mpmath (the reference's come from
+//     SpecialFunctions.jl, not vendored).
+// No stored numeric derivative VECTORS exist in the reference tree: second-order values
+// are pinned by derivation, exact symbolic differentiation and finite differences.
 //
 // Every function cites the reference file:line it restates (paths relative to
 // /root/reference/).  The recursion is kept literal (one C++ function per Julia
