@@ -50,6 +50,19 @@ def luksan_vlcek(N, order="bench"):
     return c
 
 
+def luksan_vlcek_param(N, theta=(100.0, 1.0)):
+    """docs/src/parameters.md:20-90 of the reference: LV with the penalty coefficient and the offset of the objective as
+    parameters, `θ[1] * (x[i-1]^2 - x[i])^2 + (x[i-1] - θ[2])^2` (objective added first, as there)."""
+    c = ExaCore()
+    th = c.add_par(list(theta))
+    x = c.add_var(N, start=lv_x0(N))
+    c.add_obj(lambda i: th[1] * (x[i - 1] ** 2 - x[i]) ** 2 + (x[i - 1] - th[2]) ** 2, range(2, N + 1))
+    c.add_con(lambda i: (3 * x[i + 1] ** 3 + 2 * x[i + 2] - 5
+                         + sin(x[i + 1] - x[i + 2]) * sin(x[i + 1] + x[i + 2]) + 4 * x[i + 1]
+                         - x[i] * exp(x[i] - x[i + 1]) - 3), range(1, N - 1))
+    return c
+
+
 def luksan_vlcek_aug(N, M=1):
     """test/NLPTest/luksan.jl:17-26."""
     c = ExaCore()

@@ -300,3 +300,36 @@ def test_reference_ipopt_solution_is_a_kkt_point_on_the_gpu(exa, torch_):
     H = L + np.tril(L, -1).T
     Z = np.linalg.svd(J)[2][m.ncon:].T
     assert np.linalg.eigvalsh(Z.T @ H @ Z).min() > 0.0
+
+
+def test_cuda_path_replays_the_reference_ipopt_logs(exa, torch_):
+    """tests/test_oracle_pins.py::test_oracle_replays_the_reference_ipopt_logs_digit_for_digit, through the CUDA path: the
+    three Ipopt runs printed by the reference's documentation build (docs/src/parameters.md) are reproduced digit for digit
+    from exb_obj / exb_grad / exb_cons / exb_jac / exb_hess and the two structure kernels, with the parameters updated in
+    place (exb_set_params) between the runs."""
+    import json
+    import os
+    from examodels_jl_b200 import models as M
+    from util import check_ipopt_run, newton_kkt_replay
+    torch = torch_
+    logs = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ipopt_logs.json")))
+    core = M.luksan_vlcek_param(10)
+    m = exa.ExaModel(core)
+    jr, jc = m.new(m.nnzj, torch.int64), m.new(m.nnzj, torch.int64); m.jac_structure(jr, jc)
+    hr, hc = m.new(m.nnzh, torch.int64), m.new(m.nnzh, torch.int64); m.hess_structure(hr, hc)
+    jr, jc, hr, hc = (t.cpu().numpy() - 1 for t in (jr, jc, hr, hc))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()   # noqa: E731
+
+    def jac(x):
+        J = np.zeros((m.ncon, m.nvar)); np.add.at(J, (jr, jc), m.jac_coord(dev(x), m.new(m.nnzj)).cpu().numpy()); return J
+
+    def hess(x, lam, sigma):
+        L = np.zeros((m.nvar, m.nvar)); np.add.at(L, (hr, hc), m.hess_coord(dev(x), dev(lam), m.new(m.nnzh), obj_weight=sigma).cpu().numpy())
+        return L + np.tril(L, -1).T
+    cb = dict(obj=lambda x: m.obj(dev(x)), grad=lambda x: m.grad(dev(x), m.new(m.nvar)).cpu().numpy(),
+              cons=lambda x: m.cons_nln(dev(x), m.new(m.ncon)).cpu().numpy(), jac=jac, hess=hess)
+    for run in logs["runs"]:
+        assert (m.nnzj, m.nnzh) == (run["nnzj"], run["nnzh"])
+        m.set_params(run["theta"])
+        rows, final, _, _ = newton_kkt_replay(cb, core.meta()["x0"], len(run["iterations"]) - 1)
+        check_ipopt_run(run, rows, final)

@@ -337,3 +337,64 @@ def test_reference_ipopt_solution_is_a_kkt_point_of_the_oracle(order):
     J = np.zeros((o.ncon, o.nvar)); np.add.at(J, (jr - 1, jc - 1), o.jac_coord(x))
     Z = np.linalg.svd(J)[2][o.ncon:].T                      # null-space basis of J (2 columns)
     assert np.linalg.eigvalsh(Z.T @ H @ Z).min() > 0.0
+
+
+def _lv10_parametric():
+    """docs/src/parameters.md:56-90 of the reference."""
+    return M.luksan_vlcek_param(10)
+
+
+def test_reference_ipopt_logs_of_the_parametric_model():
+    """Numbers printed by the reference's own doc build (docs/src/parameters.md): structure counts, the objective at the
+    start point for three parameter settings (parameters changed WITHOUT rebuilding the model), the primal infeasibility at
+    the start, and -- at the solution printed in docs/src/develop.md -- the final objective, constraint violation and the
+    unscaled dual infeasibility of the Ipopt run, which the oracle reproduces to ~1e-13."""
+    g = KA["lv10_parametric_ipopt_logs"]
+    core = _lv10_parametric()
+    o = Oracle.from_core(core)
+    assert (o.nnzj, o.nnzh) == (g["nnzj"], g["nnzh"])
+    x0 = core.meta()["x0"]
+    for key, val in g["obj_at_start"].items():
+        o.set_params([float(t) for t in key.split(",")])
+        assert abs(o.obj(x0) - val) <= 5e-8 * val, (key, o.obj(x0), val)              # printed with 8 significant digits
+    assert abs(np.abs(o.cons(x0)).max() - g["inf_pr_at_start"]) < 0.05                   # printed as 2.48e+01
+    o.set_params([100.0, 1.0])
+    sol = KA["lv10_ipopt_solution"]
+    x, lam = np.array(sol["x"]), np.array(sol["multipliers"])
+    assert abs(o.obj(x) - g["final_objective_theta_100_1"]) <= 1e-12 * g["final_objective_theta_100_1"]
+    jr, jc = o.jac_structure()
+    c_res, kkt_res = _kkt_residuals(o.cons(x), o.grad(x), o.jac_coord(x), jr, jc, o.nvar, o.ncon)
+    assert abs(c_res - g["final_constraint_violation"]) < 5e-14                          # 8.3547e-12 here vs 8.3542e-12 there
+    assert abs(kkt_res - g["final_dual_infeasibility_unscaled"]) < 5e-13                 # 6.31596e-09 here vs 6.31591e-09 there
+
+
+def test_oracle_replays_the_reference_ipopt_logs_digit_for_digit():
+    """The strongest pin available without a Julia toolchain.  The reference's documentation build printed three complete
+    Ipopt runs of the parametric LV N=10 model (docs/src/parameters.md; fixture tests/golden/ipopt_logs.json + generator).
+    The problem has no bounds and the logs show full Newton steps without regularisation, so the printed trajectory is a
+    deterministic function of obj / grad! / cons! / jac_coord! / hess_coord! (with the evolving multipliers) and the two
+    structures: replaying it with the ORACLE's callbacks reproduces every printed digit of every iteration -- objective (8
+    digits), primal / dual infeasibility, step norm -- and the final scaled / unscaled objective to 1e-12, for all three
+    parameter settings (changed without rebuilding the model)."""
+    from util import check_ipopt_run, newton_kkt_replay
+    logs = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ipopt_logs.json")))
+    core = _lv10_parametric()
+    o = Oracle.from_core(core)
+    jr, jc = o.jac_structure(); hr, hc = o.hess_structure()
+
+    def jac(x):
+        J = np.zeros((o.ncon, o.nvar)); np.add.at(J, (jr - 1, jc - 1), o.jac_coord(x)); return J
+
+    def hess(x, lam, sigma):
+        L = np.zeros((o.nvar, o.nvar)); np.add.at(L, (hr - 1, hc - 1), o.hess_coord(x, lam, sigma)); return L + np.tril(L, -1).T
+    cb = dict(obj=o.obj, grad=o.grad, cons=o.cons, jac=jac, hess=hess)
+    xs = []
+    for run in logs["runs"]:
+        assert (o.nnzj, o.nnzh) == (run["nnzj"], run["nnzh"])
+        o.set_params(run["theta"])
+        rows, final, x, lam = newton_kkt_replay(cb, core.meta()["x0"], len(run["iterations"]) - 1)
+        check_ipopt_run(run, rows, final)
+        xs.append((x, lam))
+    # the first run ends at the solution / multipliers printed in docs/src/develop.md:84-105
+    np.testing.assert_allclose(xs[0][0], KA["lv10_ipopt_solution"]["x"], rtol=0, atol=5e-9)
+    np.testing.assert_allclose(xs[0][1], KA["lv10_ipopt_solution"]["multipliers"], rtol=0, atol=5e-8)
