@@ -17,7 +17,11 @@
 //   * every nnzj / nnzh hard-coded in test/JuMPTest/JuMPTest.jl (per-term slot counts),
 //   * derivative tables against finite differences / sympy as in
 //     test/ADTest/ADTest.jl:298-374,
-//   * the one numeric fixture the reference itself produced: the Ipopt solution and
+//   * the Ipopt runs the reference's documentation build printed for the parametric LV N=10
+//     model (docs/src/parameters.md): replaying them with these callbacks reproduces every
+//     printed digit of every iteration (tests/golden/ipopt_logs.json) -- pins all five value
+//     callbacks, both structures and the parameter updates against reference output,
+//   * the Ipopt solution and
 //     multipliers of LV N=10 printed in docs/src/develop.md:84-105, which must be a KKT
 //     point of this restatement (cons = 0, grad f + J' lambda = 0 to the precision of the
 //     solve: pins cons, grad!, jac_coord!, jac_structure! against reference output),
