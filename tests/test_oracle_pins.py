@@ -398,3 +398,13 @@ def test_oracle_replays_the_reference_ipopt_logs_digit_for_digit():
     # the first run ends at the solution / multipliers printed in docs/src/develop.md:84-105
     np.testing.assert_allclose(xs[0][0], KA["lv10_ipopt_solution"]["x"], rtol=0, atol=5e-9)
     np.testing.assert_allclose(xs[0][1], KA["lv10_ipopt_solution"]["multipliers"], rtol=0, atol=5e-8)
+
+
+def test_max_min_ties_and_abs_at_zero_follow_the_reference_tables():
+    """src/functionlist.jl:79-80: on a tie the SECOND argument gets the derivative 1 (`x1 > x2 ? 1 : 0`, `x1 > x2 ? 0 : 1`);
+    :12: d|x| uses signbit, so d|+0| = 1 and d|-0| = -1."""
+    f, y1, y2, *_ = bi(G.OP2_CODE["max"], 0.7, 0.7)
+    assert (f, y1, y2) == (0.7, 0.0, 1.0)
+    f, y1, y2, *_ = bi(G.OP2_CODE["min"], 0.7, 0.7)
+    assert (f, y1, y2) == (0.7, 0.0, 1.0)
+    assert tuple(uni(G.OP1_CODE["abs"], 0.0)[:2]) == (0.0, 1.0) and tuple(uni(G.OP1_CODE["abs"], -0.0)[:2]) == (0.0, -1.0)
