@@ -39,7 +39,9 @@ exb_obj_async exb_grad exb_cons exb_jac_structure64 exb_jac_structure32 exb_jac 
 exb_hess_structure32 exb_hess exb_host_obj exb_host_grad exb_host_cons exb_host_jac exb_host_hess
 exb_host_jac_structure64 exb_host_hess_structure64 exb_shard exb_stats exb_last_error exb_abi_version
 exb_jprod exb_jtprod exb_hprod exb_compressed_dims exb_jac_structure_compressed64 exb_hess_structure_compressed64
-exb_jac_compressed exb_hess_compressed exb_set_timing exb_timings exb_kernel_choice exb_host_bytes""".split()
+exb_jac_compressed exb_hess_compressed exb_set_timing exb_timings exb_kernel_choice exb_host_bytes
+exb_comm_unique_id exb_comm_init exb_comm_attach exb_comm_destroy exb_comm_set_mode exb_comm_gather_coo exb_owned
+exb_comm_stats""".split()
 
 
 class ExbError(RuntimeError):
@@ -181,6 +183,7 @@ class ExaModel:
         (self.nvar, self.ncon, self.nnzj, self.nnzh, self.nobj, self.nnzg, self.nconaug,
          self.npar) = (int(v) for v in d)
         self.npatterns = len(core.patterns)
+        self.has_comm = False
         if self.npar:
             self.set_params(meta["theta"])
 
@@ -337,6 +340,47 @@ class ExaModel:
         """`CompressedNLPModel(m)` (src/utils.jl:425-579): the same model with duplicate COO entries summed."""
         return CompressedExaModel(self)
 
+    # -- multi-GPU: the library's own communicator (include/exa_b200.h "multi-GPU") ---------------------
+    def comm_init(self, group=None, mode="replicate"):
+        """Create the NCCL communicator of this sharded model inside the library.  The 128-byte ncclUniqueId made by rank 0
+        travels through `torch.distributed` (any backend) -- a Julia host would send it over MPI.  Collective."""
+        import torch.distributed as dist
+        ids = [None]
+        if dist.get_rank(group) == 0:
+            buf = C.create_string_buffer(128)
+            _check(lib().exb_comm_unique_id(buf))
+            ids[0] = buf.raw
+        dist.broadcast_object_list(ids, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        _check(lib().exb_comm_init(self.h, C.c_char_p(ids[0])))
+        self.has_comm = True
+        self.comm_set_mode(mode)
+        return self
+
+    def comm_set_mode(self, mode):
+        _check(lib().exb_comm_set_mode(self.h, {"replicate": 0, "owner": 1}[mode]))
+        self.comm_mode = mode
+
+    def comm_destroy(self):
+        _check(lib().exb_comm_destroy(self.h))
+        self.has_comm = False
+
+    def gather_coo(self, which, vals):
+        """Replicate the sharded COO values in place (which = 1: jac, 2: hess)."""
+        n = self.nnzj if which == 1 else self.nnzh
+        _check(lib().exb_comm_gather_coo(self.h, which, self._dev(vals, n), self._stream()))
+        return vals
+
+    def owned(self):
+        """0-based half-open range of the variables this handle owns."""
+        o = np.zeros(2, dtype=np.int64)
+        _check(lib().exb_owned(self.h, _np_ptr(o)))
+        return int(o[0]), int(o[1])
+
+    def comm_stats(self):
+        o = np.zeros(4, dtype=np.int64)
+        _check(lib().exb_comm_stats(self.h, _np_ptr(o)))
+        return dict(zip(("collectives", "last_collectives", "attached", "mode"), (int(v) for v in o)))
+
     # -- sharding / introspection ------------------------------------------------------
     def shard(self, k):
         o = np.zeros(6, dtype=np.int64)
@@ -385,11 +429,13 @@ class CompressedExaModel:
 
     def jac_structure(self, rows, cols):
         i = self.inner
+        assert rows.dtype == cols.dtype == i._torch.int64, "compressed structures are written as int64"
         _check(lib().exb_jac_structure_compressed64(i.h, i._dev(rows, self.nnzj, rows.dtype), i._dev(cols, self.nnzj, cols.dtype), i._stream()))
         return rows, cols
 
     def hess_structure(self, rows, cols):
         i = self.inner
+        assert rows.dtype == cols.dtype == i._torch.int64, "compressed structures are written as int64"
         _check(lib().exb_hess_structure_compressed64(i.h, i._dev(rows, self.nnzh, rows.dtype), i._dev(cols, self.nnzh, cols.dtype), i._stream()))
         return rows, cols
 

@@ -739,10 +739,12 @@ inline std::string gen_pattern(PatternPlan& p, int index, bool windowed) {
       o << "  __device__ static __forceinline__ double g1(const ExbPatArgs& pa, const long long v, const ExbXG x, const double* __restrict__ th) {\n";
       // branch-free: an out-of-range point is replaced by the pattern's first local point and its slot discarded, so the
       // loads of every slot are issued up front (the kernel is latency-bound: ~10 flops per 8-byte word)
-      o << "    double acc = 0.0;\n    if (pa.n > 0) {\n";
+      // the kernel partitions VARIABLES (a sharded handle owns a contiguous range of them), so every point of the pattern
+      // is eligible: [0, nfull), not the handle's point shard
+      o << "    double acc = 0.0;\n    if (pa.nfull > 0) {\n";
       for (int j : ord) {
-        o << "      { const long long kg = v - (" << Gen::ilit(p.shift1[(size_t)j]) << ") - pa.start; const bool in = kg >= pa.k0 && kg < pa.k0 + pa.n;\n"
-          << "        double s[" << a1 << "]; d1(pa, in ? kg : pa.k0, x, th, s); acc += in ? s[" << j << "] : 0.0; }\n";
+        o << "      { const long long kg = v - (" << Gen::ilit(p.shift1[(size_t)j]) << ") - pa.start; const bool in = kg >= 0 && kg < pa.nfull;\n"
+          << "        double s[" << a1 << "]; d1(pa, in ? kg : 0, x, th, s); acc += in ? s[" << j << "] : 0.0; }\n";
       }
       o << "    }\n";
       o << "    return acc;\n  }\n";

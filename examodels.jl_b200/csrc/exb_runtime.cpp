@@ -13,6 +13,7 @@
 #include <cuda.h>
 #include <cuda_runtime_api.h>
 #include <dlfcn.h>
+#include <nccl.h>   // types only: the library is dlopen'ed (see Nccl below)
 #include <fcntl.h>
 #include <sys/file.h>
 #include <sys/stat.h>
@@ -27,6 +28,7 @@
 #include <mutex>
 #include <sstream>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/exa_b200.h"
@@ -120,6 +122,45 @@ std::string cu_err(CUresult r) {
   const char* s = nullptr;
   if (g_drv.GetErrorString) g_drv.GetErrorString(r, &s);
   return s ? s : "CUDA driver error " + std::to_string((int)r);
+}
+
+// ---- NCCL entry points, dlopen'ed at the first exb_comm_* call: libexa_b200.so has no link-time dependency on NCCL, and a
+// process that already loaded a copy (torch's bundled libnccl.so.2) shares it instead of loading a second one --------------
+struct Nccl {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommCount)(const ncclComm_t, int*) = nullptr;
+  ncclResult_t (*CommUserRank)(const ncclComm_t, int*) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false; std::string why;
+};
+Nccl g_nccl;
+std::once_flag g_nccl_once;
+bool load_nccl() {
+  std::call_once(g_nccl_once, [] {
+    void* h = nullptr;
+    std::vector<std::string> names;
+    if (const char* e = getenv("EXB_NCCL_LIB")) names.push_back(e);
+    names.push_back("libnccl.so.2"); names.push_back("libnccl.so");
+    for (auto& n : names) if ((h = dlopen(n.c_str(), RTLD_NOW | RTLD_NOLOAD))) break;    // a copy already in the process wins
+    if (!h) for (auto& n : names) if ((h = dlopen(n.c_str(), RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!h) { g_nccl.why = "libnccl.so.2 not found (set EXB_NCCL_LIB)"; return; }
+    auto sym = [&](const char* n, auto& f) { f = (std::remove_reference_t<decltype(f)>)dlsym(h, n); return f != nullptr; };
+    g_nccl.ok = sym("ncclGetUniqueId", g_nccl.GetUniqueId) && sym("ncclCommInitRank", g_nccl.CommInitRank) &&
+                sym("ncclCommDestroy", g_nccl.CommDestroy) && sym("ncclCommCount", g_nccl.CommCount) &&
+                sym("ncclCommUserRank", g_nccl.CommUserRank) && sym("ncclAllReduce", g_nccl.AllReduce) &&
+                sym("ncclBroadcast", g_nccl.Broadcast) && sym("ncclAllGather", g_nccl.AllGather) &&
+                sym("ncclGroupStart", g_nccl.GroupStart) && sym("ncclGroupEnd", g_nccl.GroupEnd) &&
+                sym("ncclGetErrorString", g_nccl.GetErrorString);
+    if (!g_nccl.ok) g_nccl.why = "NCCL library lacks a required entry point";
+  });
+  return g_nccl.ok;
 }
 
 enum { KN_HESS, KN_JAC, KN_SGRAD, KN_GGRAD, KN_CONS, KN_OBJ, KN_JSTRUCT64, KN_JSTRUCT32, KN_GSTRUCT64, KN_HSTRUCT64, KN_HSTRUCT32, KN_AUGROW, KN_JPROD, KN_JTPROD, KN_HPROD, KN_COUNT };
@@ -320,6 +361,7 @@ struct exb_model {
   double *d_jacbuf = nullptr, *d_hessbuf = nullptr;
   std::vector<long long> lo, hi;   // local point range per pattern
   long long x_lo = 0, x_hi = 0;    // [x_lo, x_hi): the part of x this handle's points can read (the host shims upload only that)
+  long long v_lo = 0, v_hi = 0;    // [v_lo, v_hi): the variables this handle owns (0-based; all of them unless sharded)
   long long last_h2d = 0, last_d2h = 0;   // bytes moved by the last exb_host_* call
   // host shims
   cudaStream_t hstream = nullptr, hstream2 = nullptr;
@@ -327,6 +369,10 @@ struct exb_model {
   double *hx = nullptr, *hy = nullptr, *hout = nullptr; size_t hx_n = 0, hy_n = 0, hout_n = 0;
   double *dx = nullptr, *dy = nullptr, *dout = nullptr; size_t dx_n = 0, dy_n = 0, dout_n = 0;
   long long launches = 0, last_launches = 0;
+  // multi-GPU: a communicator over the `world` handles of one sharded model (exb_comm_*); with it the reducing callbacks
+  // complete themselves on the caller's stream
+  ncclComm_t comm = nullptr; bool comm_owned = false; int comm_mode = EXB_COMM_REPLICATE;
+  long long collectives = 0, last_collectives = 0;
   // per-callback device timing (the TimedNLPModel role, src/utils.jl:271-408): CUDA events around each callback
   bool timing = false;
   struct Pending { int cb; cudaEvent_t e0, e1; };
@@ -550,7 +596,7 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
     memset(&a, 0, sizeof a);
     const long long n = p.ir.nitr;
     m->lo[k] = n * m->rank / m->world; m->hi[k] = n * (m->rank + 1) / m->world;
-    a.n = m->hi[k] - m->lo[k]; a.k0 = m->lo[k];
+    a.n = m->hi[k] - m->lo[k]; a.k0 = m->lo[k]; a.nfull = n;
     a.start = p.ir.range_start;
     a.o0 = p.o0; a.o1 = p.o1; a.o2 = p.o2; a.aux = p.oa;
     for (size_t d = 0; d < p.ir.dims.size() && d < EXB_MAXD; d++) a.dim[d] = p.ir.dims[d];
@@ -577,7 +623,19 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       }
       if (p.xr_fixed) { xl = std::min<long long>(xl, p.flo - 1); xh = std::max<long long>(xh, p.fhi); }
     }
-    if (all || xl < 0 || xh > pl.m.nvar) { xl = 0; xh = pl.m.nvar; }
+    // variables are partitioned too: rank r OWNS [nvar r / W, nvar (r + 1) / W).  The owner-computes gradient kernel
+    // (exb_ggrad_body) writes exactly the owned range, evaluating whichever points touch it (x is replicated), so the
+    // gradient of a shift-indexed objective needs NO exchange between ranks at all
+    m->v_lo = pl.m.nvar * m->rank / m->world; m->v_hi = pl.m.nvar * (m->rank + 1) / m->world;
+    for (size_t k = 0; k < np && !all; k++) {
+      const exb::PatternPlan& p = pl.pats[k];
+      if (!p.gather1 || m->world == 1 || m->v_hi <= m->v_lo) continue;
+      if (!p.xr_ok) { all = true; break; }
+      const long long w = p.xr_shift ? p.rhi - p.rlo : 0;   // a variable's points read x within this distance of it
+      xl = std::min<long long>(xl, m->v_lo - w); xh = std::max<long long>(xh, m->v_hi + w);
+    }
+    if (all) { xl = 0; xh = pl.m.nvar; }
+    xl = std::max<long long>(xl, 0); xh = std::min<long long>(xh, pl.m.nvar);
     if (xh < xl) { xl = 0; xh = 0; }
     m->x_lo = xl; m->x_hi = xh;
   }
@@ -623,7 +681,7 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       int rc = dmalloc(m, &d_args, args.size() * sizeof(ExbPatArgs)); if (rc) return rc;
       CU_TRY(m, cudaMemcpy(d_args, args.data(), args.size() * sizeof(ExbPatArgs), cudaMemcpyHostToDevice));
       L.g.pat = (const ExbPatArgs*)d_args; L.g.chunk = nullptr; L.g.np = (int)lst.size(); L.g.shift = 0;
-      L.nblocks = (unsigned)((pl.m.nvar + BLK * EXB_GVPT - 1) / (BLK * EXB_GVPT));
+      L.nblocks = (unsigned)((m->v_hi - m->v_lo + BLK * EXB_GVPT - 1) / (BLK * EXB_GVPT));
       L.smem = 0;
       continue;
     }
@@ -750,6 +808,7 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
 void free_model(exb_model* m) {
   if (!m) return;
   DeviceGuard dg(m->device);
+  if (m->comm && m->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
   for (void* p : m->dev) cudaFree(p);
   for (CUmodule mod : m->mods) if (mod && g_drv.ModuleUnload) g_drv.ModuleUnload(mod);
   if (m->hx) cudaFreeHost(m->hx);
@@ -784,6 +843,64 @@ int ensure_host(exb_model* m, double** h, size_t* hn, double** d, size_t* dn, si
   return EXB_OK;
 }
 
+
+// ---- collectives of a sharded model, issued on the caller's stream through the handle's communicator ------
+#define NC_TRY(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) return fail(EXB_ERR_CUDA, std::string(#x) + ": " + g_nccl.GetErrorString(r_)); } while (0)
+bool comm_on(const exb_model* m) { return m->comm != nullptr && m->world > 1; }
+int comm_allreduce(exb_model* m, double* buf, long long n, cudaStream_t st) {
+  if (n <= 0) return EXB_OK;
+  NC_TRY(g_nccl.AllReduce(buf, buf, (size_t)n, ncclDouble, ncclSum, m->comm, st));
+  m->collectives++; m->last_collectives++;
+  return EXB_OK;
+}
+struct Seg { int rank; long long lo, hi; };
+// in-place all-gather of ragged contiguous segments (rank seg.rank holds buf[lo, hi)): one NCCL group of broadcasts
+int comm_allgatherv(exb_model* m, double* buf, const std::vector<Seg>& segs, cudaStream_t st) {
+  bool any = false;
+  for (auto& g : segs) any = any || g.hi > g.lo;
+  if (!any) return EXB_OK;
+  NC_TRY(g_nccl.GroupStart());
+  for (auto& g : segs)
+    if (g.hi > g.lo) {
+      ncclResult_t r = g_nccl.Broadcast(buf + g.lo, buf + g.lo, (size_t)(g.hi - g.lo), ncclDouble, g.rank, m->comm, st);
+      if (r != ncclSuccess) { g_nccl.GroupEnd(); return fail(EXB_ERR_CUDA, std::string("ncclBroadcast: ") + g_nccl.GetErrorString(r)); }
+    }
+  NC_TRY(g_nccl.GroupEnd());
+  m->collectives++; m->last_collectives++;
+  return EXB_OK;
+}
+// variables are owned in equal contiguous ranges [nvar r / W, nvar (r + 1) / W)
+int comm_allgather_vars(exb_model* m, double* g, cudaStream_t st) {
+  const long long nvar = m->plan->pl.m.nvar; const int W = m->world;
+  if (nvar % W == 0) {
+    const long long cnt = nvar / W;
+    NC_TRY(g_nccl.AllGather(g + cnt * m->rank, g, (size_t)cnt, ncclDouble, m->comm, st));
+    m->collectives++; m->last_collectives++;
+    return EXB_OK;
+  }
+  std::vector<Seg> segs;
+  for (int r = 0; r < W; r++) segs.push_back({r, nvar * r / W, nvar * (r + 1) / W});
+  return comm_allgatherv(m, g, segs, st);
+}
+// rows of the base constraints are owned with their points: pattern k, rank r -> [o0 + n r / W, o0 + n (r + 1) / W)
+void row_segments(const exb_model* m, std::vector<Seg>& segs) {
+  const exb::Plan& pl = m->plan->pl;
+  for (auto& p : pl.pats)
+    if (p.ir.kind == exb::KIND_CON)
+      for (int r = 0; r < m->world; r++) segs.push_back({r, p.o0 + p.ir.nitr * r / m->world, p.o0 + p.ir.nitr * (r + 1) / m->world});
+}
+// c / Jv of a sharded handle: own base rows + own augmentation terms, zero elsewhere
+int comm_finish_rows(exb_model* m, double* c, cudaStream_t st) {
+  if (!comm_on(m)) return EXB_OK;
+  const exb::Plan& pl = m->plan->pl;
+  if (pl.nconaug > 0) return comm_allreduce(m, c, pl.ncon, st);   // augmentation terms land in arbitrary rows: sum the shards
+  if (m->comm_mode == EXB_COMM_OWNER) return EXB_OK;              // every rank already holds the rows of its own points
+  std::vector<Seg> segs;
+  row_segments(m, segs);
+  if (segs.size() > 512) return comm_allreduce(m, c, pl.ncon, st);
+  return comm_allgatherv(m, c, segs, st);
+}
+
 }  // namespace
 
 enum { CB_OBJ = 0, CB_GRAD, CB_CONS, CB_JAC, CB_HESS, CB_JPROD, CB_JTPROD, CB_HPROD };
@@ -800,7 +917,7 @@ struct TimeScope {   // records an event pair on the caller's stream when timing
     m->pending.push_back({cb, e0, e1});
   }
 };
-#define EXB_GUARD(m) if (!(m) || !(m)->plan) return fail(EXB_ERR_HANDLE, "invalid handle"); DeviceGuard dg_((m)->device); (m)->last_launches = 0
+#define EXB_GUARD(m) if (!(m) || !(m)->plan) return fail(EXB_ERR_HANDLE, "invalid handle"); DeviceGuard dg_((m)->device); (m)->last_launches = 0; (m)->last_collectives = 0
 #define EXB_BEGIN try {
 #define EXB_END } catch (const std::exception& e) { return fail(EXB_ERR_INTERNAL, e.what()); } catch (...) { return fail(EXB_ERR_INTERNAL, "unknown exception"); }
 
@@ -911,6 +1028,7 @@ int exb_obj_async(exb_model* m, const double* x, double* out_dev, void* stream) 
   int rc = launch(m, KN_OBJ, c, st); if (rc) return rc;
   CU_TRY(m, exb_fx_sum(m->d_objpart, m->k[KN_OBJ].nblocks, out_dev, st));
   m->launches++; m->last_launches++;
+  if (comm_on(m)) return comm_allreduce(m, out_dev, 1, st);   // partial sums of the shards (ext:253-271 has one device); 8 bytes
   return EXB_OK;
   EXB_END
 }
@@ -932,16 +1050,24 @@ int exb_grad(exb_model* m, const double* x, double* g, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const exb::Plan& pl = m->plan->pl;
   ExbCall c{}; c.x = x; c.th = m->d_theta; c.out = m->d_gradbuf;
-  const bool gathered = m->k[KN_GGRAD].nblocks > 0;
-  if (gathered) {   // shift-indexed objective patterns: one thread per variable writes g[v] (0 where untouched)
-    ExbCall cg{}; cg.x = x; cg.th = m->d_theta; cg.out = g; cg.nout = pl.m.nvar;
+  const bool gathered = !pl.k_ggrad.empty();
+  // fill!(g, 0) (ext:317): needed when some variable has no objective term -- and on a sharded handle, whose g must be zero
+  // outside what it computes so that the shards add up
+  if (m->world > 1 || (!gathered && !(m->g_dense && m->g_runs == pl.m.nvar))) CU_TRY(m, cudaMemsetAsync(g, 0, (size_t)pl.m.nvar * 8, st));
+  if (gathered) {   // shift-indexed objective patterns: one thread per OWNED variable writes g[v] (0 where untouched)
+    ExbCall cg{}; cg.x = x; cg.th = m->d_theta; cg.out = g; cg.v0 = m->v_lo; cg.nout = m->v_hi - m->v_lo;
     int rc = launch(m, KN_GGRAD, cg, st); if (rc) return rc;
   }
   int rc = launch(m, KN_SGRAD, c, st); if (rc) return rc;                        // kerg, ext:669-679
-  // fill!(g, 0) (ext:317) is only needed when some variable has no objective term; otherwise every g[v] is assigned
-  if (!gathered && !(m->g_dense && m->g_runs == pl.m.nvar)) CU_TRY(m, cudaMemsetAsync(g, 0, (size_t)pl.m.nvar * 8, st));
-  CU_TRY(m, exb_fx_compress(m->d_gradbuf, m->g_ptr, m->g_slot, m->g_target, m->g_i32, m->g_runs, g, gathered ? 1 : 0, st));   // ext:691-697
+  CU_TRY(m, exb_fx_compress(m->d_gradbuf, m->g_ptr, m->g_slot, m->g_target, m->g_i32, m->g_runs, g, (gathered || m->world > 1) ? 1 : 0, st));   // ext:691-697
   if (m->g_runs > 0) { m->launches++; m->last_launches++; }
+  if (comm_on(m)) {
+    // slot-kernel patterns leave partial sums over this shard's points anywhere in g: sum the shards.  A model whose
+    // objective patterns are all owner-computed has every g[v] exact on the rank that owns v: nothing to reduce, and
+    // nothing to send at all unless the caller wants g replicated
+    if (!pl.k_sgrad.empty()) return comm_allreduce(m, g, pl.m.nvar, st);
+    if (m->comm_mode == EXB_COMM_REPLICATE) return comm_allgather_vars(m, g, st);
+  }
   return EXB_OK;
   EXB_END
 }
@@ -958,7 +1084,7 @@ int exb_cons(exb_model* m, const double* x, double* cvals, void* stream) {
   int rc = launch(m, KN_CONS, c, st); if (rc) return rc;                         // kerf + kerf2, ext:681-688
   CU_TRY(m, exb_fx_compress(m->d_conbuf, m->a_ptr, m->a_slot, m->a_target, m->a_i32, m->a_runs, cvals, 1, st));   // ext:691-697
   if (m->a_runs > 0) { m->launches++; m->last_launches++; }
-  return EXB_OK;
+  return comm_finish_rows(m, cvals, st);
   EXB_END
 }
 
@@ -1104,7 +1230,7 @@ int exb_jprod(exb_model* m, const double* x, const double* v, double* Jv, void* 
     int rc = launch(m, KN_JPROD, c, st); if (rc) return rc;
     CU_TRY(m, exb_fx_compress(m->d_conbuf, m->a_ptr, m->a_slot, m->a_target, m->a_i32, m->a_runs, Jv, 1, st));
     if (m->a_runs > 0) { m->launches++; m->last_launches++; }
-    return EXB_OK;
+    return comm_finish_rows(m, Jv, st);
   }
   int rc = ensure_sorted(m, 1); if (rc) return rc;
   rc = exb_jac(m, x, m->d_jacbuf, stream); if (rc) return rc;
@@ -1121,7 +1247,8 @@ int exb_jtprod(exb_model* m, const double* x, const double* v, double* Jtv, void
   if (!m->sorted_products) {
     CU_TRY(m, cudaMemsetAsync(Jtv, 0, (size_t)pl.m.nvar * 8, st));
     ExbCall c{}; c.x = x; c.v = v; c.th = m->d_theta; c.out = Jtv;
-    return launch(m, KN_JTPROD, c, st);
+    int rc = launch(m, KN_JTPROD, c, st); if (rc) return rc;
+    return comm_on(m) ? comm_allreduce(m, Jtv, pl.m.nvar, st) : EXB_OK;   // partial products of the shards
   }
   int rc = ensure_sorted(m, 1); if (rc) return rc;
   rc = exb_jac(m, x, m->d_jacbuf, stream); if (rc) return rc;
@@ -1138,7 +1265,8 @@ int exb_hprod(exb_model* m, const double* x, const double* y, const double* v, d
   if (!m->sorted_products) {
     CU_TRY(m, cudaMemsetAsync(Hv, 0, (size_t)pl.m.nvar * 8, st));
     ExbCall c{}; c.x = x; c.y = y; c.v = v; c.th = m->d_theta; c.sigma = obj_weight; c.out = Hv;
-    return launch(m, KN_HPROD, c, st);
+    int rc = launch(m, KN_HPROD, c, st); if (rc) return rc;
+    return comm_on(m) ? comm_allreduce(m, Hv, pl.m.nvar, st) : EXB_OK;
   }
   int rc = ensure_sorted(m, 1); if (rc) return rc;
   rc = exb_hess(m, x, y, obj_weight, m->d_hessbuf, stream); if (rc) return rc;
@@ -1404,6 +1532,82 @@ int exb_host_hess_structure64(exb_model* m, int64_t* rows, int64_t* cols) {
   EXB_BEGIN EXB_GUARD(m); return host_structure(m, KN_HSTRUCT64, m->plan->pl.nnzh, rows, cols); EXB_END
 }
 
+// ---- multi-GPU: the communicator of a sharded model (include/exa_b200.h) ----------------------------------------------------
+int exb_comm_unique_id(void* id128) {
+  EXB_BEGIN
+  if (!id128) return fail(EXB_ERR_ARG, "null argument");
+  if (!load_nccl()) return fail(EXB_ERR_CUDA, "NCCL unavailable: " + g_nccl.why);
+  ncclUniqueId id;
+  NC_TRY(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(id) == EXB_COMM_ID_BYTES, "ncclUniqueId size");
+  memcpy(id128, &id, sizeof id);
+  return EXB_OK;
+  EXB_END
+}
+int exb_comm_init(exb_model* m, const void* id128) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  if (!id128) return fail(EXB_ERR_ARG, "null argument");
+  if (m->comm) return fail(EXB_ERR_ARG, "the handle already has a communicator");
+  if (!load_nccl()) return fail(EXB_ERR_CUDA, "NCCL unavailable: " + g_nccl.why);
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  NC_TRY(g_nccl.CommInitRank(&m->comm, m->world, id, m->rank));
+  m->comm_owned = true;
+  return EXB_OK;
+  EXB_END
+}
+int exb_comm_attach(exb_model* m, void* nccl_comm) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  if (!nccl_comm) return fail(EXB_ERR_ARG, "null communicator");
+  if (m->comm) return fail(EXB_ERR_ARG, "the handle already has a communicator");
+  if (!load_nccl()) return fail(EXB_ERR_CUDA, "NCCL unavailable: " + g_nccl.why);
+  int n = 0, r = -1;
+  NC_TRY(g_nccl.CommCount((ncclComm_t)nccl_comm, &n));
+  NC_TRY(g_nccl.CommUserRank((ncclComm_t)nccl_comm, &r));
+  if (n != m->world || r != m->rank) return fail(EXB_ERR_ARG, "communicator rank / size differ from the handle's shard");
+  m->comm = (ncclComm_t)nccl_comm; m->comm_owned = false;
+  return EXB_OK;
+  EXB_END
+}
+int exb_comm_destroy(exb_model* m) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  if (m->comm && m->comm_owned) g_nccl.CommDestroy(m->comm);
+  m->comm = nullptr; m->comm_owned = false;
+  return EXB_OK;
+  EXB_END
+}
+int exb_comm_set_mode(exb_model* m, int mode) {
+  if (!m) return fail(EXB_ERR_HANDLE, "invalid handle");
+  if (mode != EXB_COMM_REPLICATE && mode != EXB_COMM_OWNER) return fail(EXB_ERR_ARG, "unknown mode");
+  m->comm_mode = mode;
+  return EXB_OK;
+}
+// replicate the sharded COO values (which = 1: jac, 2: hess): every rank broadcasts the slices it wrote
+int exb_comm_gather_coo(exb_model* m, int which, double* vals, void* stream) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  if (which != 1 && which != 2) return fail(EXB_ERR_ARG, "which must be 1 (jac) or 2 (hess)");
+  if (m->world == 1) return EXB_OK;
+  if (!m->comm) return fail(EXB_ERR_ARG, "no communicator: call exb_comm_init first");
+  const exb::Plan& pl = m->plan->pl;
+  std::vector<Seg> segs;
+  for (auto& p : pl.pats) {
+    if (which == 1 && p.ir.kind == exb::KIND_OBJ) continue;
+    const long long o = which == 1 ? p.o1 : p.o2, stp = which == 1 ? p.o1step : p.o2step;
+    for (int r = 0; r < m->world; r++) segs.push_back({r, o + stp * (p.ir.nitr * r / m->world), o + stp * (p.ir.nitr * (r + 1) / m->world)});
+  }
+  return comm_allgatherv(m, vals, segs, (cudaStream_t)stream);
+  EXB_END
+}
+int exb_owned(const exb_model* m, int64_t* o) {
+  if (!m || !o) return fail(EXB_ERR_HANDLE, "invalid handle");
+  o[0] = m->v_lo; o[1] = m->v_hi;
+  return EXB_OK;
+}
+
 int exb_shard(const exb_model* m, int k, int64_t* o) {
   if (!m || !o) return fail(EXB_ERR_HANDLE, "invalid handle");
   if (k < 0 || (size_t)k >= m->plan->pl.pats.size()) return fail(EXB_ERR_ARG, "pattern index out of range");
@@ -1456,6 +1660,11 @@ int exb_kernel_choice(const exb_model* m, int callback, int64_t* o) {
   o[1] = L.use_p >= 0 ? 1 : 0;
   o[2] = L.use_p >= 0 ? (int64_t)L.pgrid[(size_t)L.use_p] : (int64_t)L.nblocks;
   o[3] = kn == KN_GGRAD ? 1 : 0;
+  return EXB_OK;
+}
+int exb_comm_stats(const exb_model* m, int64_t* o) {
+  if (!m || !o) return fail(EXB_ERR_HANDLE, "invalid handle");
+  o[0] = m->collectives; o[1] = m->last_collectives; o[2] = m->comm ? 1 : 0; o[3] = m->comm_mode;
   return EXB_OK;
 }
 int exb_stats(const exb_model* m, int64_t* o) {

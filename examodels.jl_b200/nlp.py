@@ -482,3 +482,52 @@ def _emit_pattern(p: _Pattern, bufs):
     w.append(root)
     w += [0, 0]  # ncomp1, ncomp2 (not supplied: recomputed by the probe)
     return w
+
+
+def window_core(core: ExaCore, windows):
+    """The same model with every pattern's iterator restricted to the points `[a_k, b_k)` (0-based, one pair per
+    pattern, in add order); variables, parameters and expression trees are shared.  Because a pattern's slots depend
+    on its own data point only, callback outputs of the windowed model are the corresponding slices of the full
+    model's -- the size-independent property bench.py and the full-size tests use to check a huge model against the
+    oracle on a sample (`window_slices` gives the index maps).  Models with constraint augmentations are not supported
+    (their row indices refer to the base constraint's full dims)."""
+    w = ExaCore(minimize=core.minimize, name=core.name)
+    w.nvar, w.npar = core.nvar, core.npar
+    w.x0, w.lvar, w.uvar, w.theta = core.x0, core.lvar, core.uvar, core.theta
+    w.vars, w.pars = core.vars, core.pars
+    assert len(windows) == len(core.patterns)
+    for p, (a, b) in zip(core.patterns, windows):
+        assert p.kind != KIND_AUG, "window_core: augmentation patterns are not supported"
+        a, b = max(0, int(a)), min(p.nitr, int(b))
+        b = max(a, b)
+        if p.itr.range is not None:
+            it = Iterator(range(p.itr.range.start + a, p.itr.range.start + b))
+        else:
+            it = Iterator(np.ascontiguousarray(p.itr.array[a:b]))
+        q = _Pattern(p.kind, p.tree, it, size=it.sizes)
+        if p.kind == KIND_OBJ:
+            w.nobj += len(it)
+        else:
+            q.offset = w.ncon
+            w.ncon += len(it)
+            z = np.zeros(len(it))
+            w.y0.append(z); w.lcon.append(z); w.ucon.append(z)
+        w._push(q)
+    return w
+
+
+def window_slices(full_info, win_info, windows):
+    """Index maps between a full model and its `window_core`: for each pattern k with window [a, b) returns a dict with
+    `rows` / `jac` / `hess` = (slice in the full model's c / jac / hess vector, slice in the windowed model's).
+    `full_info[k]`, `win_info[k]` are `Plan.pattern_info(k)` dicts of the two models."""
+    out = []
+    for f, s, (a, b) in zip(full_info, win_info, windows):
+        a = max(0, int(a)); b = max(a, min(f["nitr"], int(b)))
+        n = b - a
+        d = {"n": n}
+        d["hess"] = (slice(f["o2"] + f["o2step"] * a, f["o2"] + f["o2step"] * b), slice(s["o2"], s["o2"] + s["o2step"] * n))
+        if f["kind"] == KIND_CON:
+            d["rows"] = (slice(f["o0"] + a, f["o0"] + b), slice(s["o0"], s["o0"] + n))
+            d["jac"] = (slice(f["o1"] + f["o1step"] * a, f["o1"] + f["o1step"] * b), slice(s["o1"], s["o1"] + s["o1step"] * n))
+        out.append(d)
+    return out

@@ -14,6 +14,11 @@ SURVEY.md §8e over torch.distributed (NCCL over NVLink on the GPU box, gloo in 
                the fused product kernels of a shard return its partial product -> all_reduce(SUM) over ncon / nvar
   structures   computed replicated (each rank evaluates every point once, at build time).
 
+When the rank-local evaluator carries the library's own NCCL communicator (`ExaModel.comm_init`, the C ABI's
+exb_comm_*), every reducing callback completes itself inside the library on the caller's stream and this class only
+forwards; the torch.distributed collectives below are the host-side fallback (gloo in the CPU tests, or a host that
+prefers to own the communication).
+
 The reference has no multi-device path at all (single device, ext/ExaModelsKernelAbstractions.jl);
 this layer is new.  Summation order across ranks differs from the single-GPU order, so sharded
 results are compared at 1e-10, not bitwise.
@@ -64,6 +69,7 @@ class ShardedExaModel:
         self.local, self.gather = local, gather
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         assert (local.rank, local.world) == (self.rank, self.world), "local evaluator shard != process rank"
+        self.abi = bool(getattr(local, "has_comm", False))   # collectives run inside libexa_b200.so
         # patterns: list of dicts with kind, nitr, o1, o2, o1step, o2step (Plan.pattern_info)
         self.patterns = patterns
         for a in ("nvar", "ncon", "nnzj", "nnzh"):
@@ -72,34 +78,41 @@ class ShardedExaModel:
     # -- reductions -------------------------------------------------------------------
     def obj(self, x):
         import torch
+        if self.abi:
+            return self.local.obj(x)
         t = torch.tensor([self.local.obj(x)], dtype=torch.float64, device=x.device)
         self.dist.all_reduce(t, group=self.group)
         return float(t.item())
 
     def grad(self, x, g):
         self.local.grad(x, g)
-        self.dist.all_reduce(g, group=self.group)
+        if not self.abi:
+            self.dist.all_reduce(g, group=self.group)
         return g
 
     def cons_nln(self, x, c):
         self.local.cons_nln(x, c)
-        self.dist.all_reduce(c, group=self.group)
+        if not self.abi:
+            self.dist.all_reduce(c, group=self.group)
         return c
 
     # -- matrix-free products: partial products of the shards add up ----------------------
     def jprod_nln(self, x, v, Jv):
         self.local.jprod_nln(x, v, Jv)
-        self.dist.all_reduce(Jv, group=self.group)
+        if not self.abi:
+            self.dist.all_reduce(Jv, group=self.group)
         return Jv
 
     def jtprod_nln(self, x, v, Jtv):
         self.local.jtprod_nln(x, v, Jtv)
-        self.dist.all_reduce(Jtv, group=self.group)
+        if not self.abi:
+            self.dist.all_reduce(Jtv, group=self.group)
         return Jtv
 
     def hprod(self, x, y, v, Hv, obj_weight=1.0):
         self.local.hprod(x, y, v, Hv, obj_weight=obj_weight)
-        self.dist.all_reduce(Hv, group=self.group)
+        if not self.abi:
+            self.dist.all_reduce(Hv, group=self.group)
         return Hv
 
     # -- sharded COO outputs -------------------------------------------------------------
@@ -118,32 +131,17 @@ class ShardedExaModel:
     def _replicate(self, vals, which):
         if not self.gather or self.world == 1:
             return vals
+        if self.abi:
+            return self.local.gather_coo(which, vals)
         jobs = []
         for r in range(self.world):
             src = self.dist.get_global_rank(self.group, r) if self.group is not None else r
             jobs += [(vals[lo:hi], src) for lo, hi in self.slices(which, r)]
-        coalesced = False
-        if self.dist.get_backend(self.group) == "nccl":
-            # one NCCL group launch for all (pattern, owner) broadcasts instead of one launch each.  Only attempted on NCCL:
-            # a failed coalescing context on another backend can leave the group in "coalescing" state, in which later
-            # collectives are queued instead of executed.
-            try:
-                from torch.distributed.distributed_c10d import _coalescing_manager
-                with _coalescing_manager(group=self.group, device=vals.device, async_ops=True) as cm:
-                    for t, src in jobs:
-                        self.dist.broadcast(t, src=src, group=self.group)
-                cm.wait()
-                coalesced = True
-            except Exception:
-                try:
-                    from torch.distributed.distributed_c10d import _world
-                    _world.pg_coalesce_state.pop(self.group if self.group is not None else self.dist.group.WORLD, None)
-                except Exception:
-                    pass
-        if not coalesced:
-            works = [self.dist.broadcast(t, src=src, group=self.group, async_op=True) for t, src in jobs]
-            for w in works:
-                w.wait()
+        # host-side fallback (no communicator inside the library): one broadcast per (pattern, owner).  The sequence of
+        # collectives is the same on every rank by construction; no try / except around live collectives.
+        works = [self.dist.broadcast(t, src=src, group=self.group, async_op=True) for t, src in jobs]
+        for w in works:
+            w.wait()
         return vals
 
     def jac_coord(self, x, vals):

@@ -125,7 +125,7 @@ int exb_create(const void* ir, size_t ir_bytes, const void* const* host_data, in
                const exb_options* opt, exb_model** out);
 int exb_destroy(exb_model* m);
 int exb_dims(const exb_model* m, int64_t* out8);
-/* theta: DEVICE pointer to npar doubles (copied; set_value!, src/nlp.jl:1217-1287) */
+/* theta: pointer to npar doubles, DEVICE or HOST (cudaMemcpyDefault; copied; set_value!, src/nlp.jl:1217-1287) */
 int exb_set_params(exb_model* m, const double* theta, void* stream);
 
 /* ---- callbacks: all pointers are DEVICE pointers, stream is a cudaStream_t ---- */
@@ -182,6 +182,44 @@ int exb_host_jac(exb_model* m, const double* x, double* vals);
 int exb_host_hess(exb_model* m, const double* x, const double* y, double obj_weight, double* vals);
 int exb_host_jac_structure64(exb_model* m, int64_t* rows, int64_t* cols);
 int exb_host_hess_structure64(exb_model* m, int64_t* rows, int64_t* cols);
+
+/* ---- multi-GPU: one handle per GPU, each evaluating shard `rank` of `world` (exb_options) ---------------------------
+ * The reference has a single device (ext/ExaModelsKernelAbstractions.jl:212-547); this is the path BASELINE.json's north
+ * star adds: "NCCL over NVLink only to allreduce the scalar objective/gradient overlaps and to sum duplicated COO entries".
+ * A communicator over the `world` handles is either created here from an ncclUniqueId that the host distributes by any
+ * means it has (MPI, a socket, torch.distributed): rank 0 calls exb_comm_unique_id, every rank calls exb_comm_init with the
+ * same 128 bytes (collective, like ncclCommInitRank) -- or borrowed from the host (exb_comm_attach, an ncclComm_t whose rank /
+ * size equal the handle's).  NCCL is dlopen'ed (libnccl.so.2; EXB_NCCL_LIB overrides), there is no link-time dependency.
+ *
+ * With a communicator the reducing callbacks complete themselves on the caller's stream, with no host synchronisation:
+ *   exb_obj / exb_obj_async   partial sums -> ncclAllReduce of ONE double (8 bytes)
+ *   exb_grad                  variables are owned in contiguous ranges [nvar r / W, nvar (r + 1) / W) (exb_owned).  Objective
+ *                             patterns with shift-indexed variables are owner-computed PER VARIABLE (x is replicated), so a
+ *                             rank's g is exact on the range it owns and NOTHING is exchanged -- not even the halo; REPLICATE
+ *                             mode then all-gathers the ranges.  Models with other objective patterns (slots scattered by
+ *                             iterator data) fall back to ncclAllReduce over nvar.
+ *   exb_cons / exb_jprod      base rows are owned with their points (exb_shard); REPLICATE mode all-gathers them (one NCCL
+ *                             group of broadcasts).  Augmentation terms land in arbitrary rows -> ncclAllReduce over ncon.
+ *   exb_jtprod / exb_hprod    partial products -> ncclAllReduce over nvar
+ *   exb_jac / exb_hess        every rank writes contiguous, disjoint slices per pattern (exb_shard): no collective;
+ *                             exb_comm_gather_coo replicates them when the consumer is not sharded.
+ * Summation order across ranks differs from the single-GPU order: compare at 1e-10, not bitwise.  Without a communicator a
+ * sharded handle returns its partial results (zero outside what it computes) and the host reduces them itself. */
+#define EXB_COMM_ID_BYTES 128
+#define EXB_COMM_REPLICATE 0 /* default: obj, g, c, Jv, Jtv, Hv are complete on every rank after the call */
+#define EXB_COMM_OWNER 1     /* sharded consumer: g is valid on the owned variables, c / Jv on the rows of the own points
+                                (at least; results that had to be all-reduced are complete everywhere) */
+int exb_comm_unique_id(void* id128);
+int exb_comm_init(exb_model* m, const void* id128);
+int exb_comm_attach(exb_model* m, void* nccl_comm);
+int exb_comm_destroy(exb_model* m);
+int exb_comm_set_mode(exb_model* m, int mode);
+/* which = 1: jac, 2: hess -- in-place replication of the sharded COO values */
+int exb_comm_gather_coo(exb_model* m, int which, double* vals, void* stream);
+/* out[0..1] = 0-based half-open range of the variables this handle owns */
+int exb_owned(const exb_model* m, int64_t* out2);
+/* out[0] = collectives issued since creation, out[1] = by the last callback, out[2] = 1 if a communicator is attached, out[3] = mode */
+int exb_comm_stats(const exb_model* m, int64_t* out4);
 
 /* ---- sharding / introspection ------------------------------------------- */
 /* For pattern k: out[0..5] = lo hi (0-based local point range of this rank)

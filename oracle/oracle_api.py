@@ -34,8 +34,53 @@ def lib():
         L.ora_obj.restype = C.c_double
         for name in ("ora_destroy", "ora_dims", "ora_set_params"):
             getattr(L, name).restype = None
+        L.ora_emit_source.restype = C.c_void_p
+        L.ora_emit_source.argtypes = [C.c_void_p]
+        L.ora_free.argtypes = [C.c_void_p]
+        L.ora_free.restype = None
         _LIB = L
     return _LIB
+
+
+class CompiledOracle:
+    """The per-pattern straight-line port emitted by the oracle itself (exa_oracle.cpp `ora_emit_source`) and compiled
+    with the interpreter's own flags: the stand-in for the native code Julia generates for src/hessian.jl:681-712.
+    Values are bit-identical to the interpreter's.  TEST / BASELINE INFRASTRUCTURE ONLY."""
+
+    def __init__(self, ora):
+        import hashlib
+        L = lib()
+        ptr = L.ora_emit_source(ora.h)
+        src = C.string_at(ptr).decode()
+        L.ora_free(ptr)
+        self.source = src
+        gen = os.path.join(_HERE, "_gen")
+        os.makedirs(gen, exist_ok=True)
+        with open(os.path.join(_HERE, "ora_tables.hpp"), "rb") as f:
+            tag = hashlib.sha1(src.encode() + f.read()).hexdigest()[:16]
+        so, cpp = os.path.join(gen, f"ora_{tag}.so"), os.path.join(gen, f"ora_{tag}.cpp")
+        if not os.path.exists(so):
+            with open(cpp, "w") as f:
+                f.write(src)
+            tmp = so + f".tmp{os.getpid()}"
+            subprocess.check_call(["/usr/bin/g++", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-pthread", "-fPIC", "-std=c++17",
+                                   "-fext-numeric-literals", "-w", "-I", _HERE, "-shared", "-o", tmp, cpp])
+            os.replace(tmp, so)
+        self.so = so
+        self.lib = C.CDLL(so)
+        self.lib.cmp_hess.restype = None
+        self.ora = ora
+        self._data = (C.c_void_p * max(1, len(ora._bufs)))(*[b.ctypes.data for b in ora._bufs])
+
+    def hess_coord(self, x, y=None, obj_weight=1.0, out=None):
+        o = self.ora
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = None if y is None else np.ascontiguousarray(y, dtype=np.float64)
+        out = np.empty(o.nnzh, dtype=np.float64) if out is None else out
+        th = o._theta if getattr(o, "_theta", None) is not None else np.zeros(max(1, o.npar))
+        self.lib.cmp_hess(_p(x), _p(y), _p(th), C.c_double(obj_weight), _p(out), self._data,
+                          C.c_int(getattr(o, "_threads", 1)), C.c_int(getattr(o, "_rank", 0)), C.c_int(getattr(o, "_world", 1)))
+        return out
 
 
 def _p(a):
@@ -72,11 +117,17 @@ class Oracle:
         except Exception:
             pass
 
+    def compile(self):
+        """g++-compiled straight-line form of this model's hess_coord! (see CompiledOracle)."""
+        return CompiledOracle(self)
+
     def set_threads(self, n):
+        self._threads = int(n)
         lib().ora_set_threads(self.h, int(n))
 
     def set_shard(self, rank, world):
         """Test aid: evaluate only shard `rank` of `world` of every pattern's iterator."""
+        self._rank, self._world = int(rank), int(world)
         lib().ora_set_shard(self.h, int(rank), int(world))
 
     @staticmethod
@@ -86,6 +137,7 @@ class Oracle:
     def set_params(self, theta):
         t = np.ascontiguousarray(theta, dtype=np.float64)
         assert t.size == self.npar
+        self._theta = t
         lib().ora_set_params(self.h, _p(t))
 
     def npatterns(self):

@@ -1,6 +1,8 @@
-"""Sharded evaluation on real GPU handles: two ranks (NCCL over two GPUs when the box has them, else both ranks
-on GPU 0 with gloo), each an `ExaModel(core, rank=r, world=2)`, completed by the collectives of
-examodels.jl_b200/parallel.py, against the unsharded oracle."""
+"""Sharded evaluation on real GPU handles: two ranks, each an `ExaModel(core, rank=r, world=2)`, against the unsharded
+oracle.  On a box with >= 2 GPUs: NCCL, and the collectives are exercised three ways -- on the host side
+(examodels.jl_b200/parallel.py over torch.distributed), inside the library through its own communicator (exb_comm_*, replicate
+mode), and in owner mode (sharded consumer).  On a 1-GPU box both ranks share GPU 0 and only the host-side form runs, over
+gloo (NCCL refuses two ranks on one device)."""
 import os
 import socket
 import sys
@@ -36,30 +38,64 @@ def _worker(rank, world, port, which, q):
         pats = [plan.pattern_info(k) for k in range(plan.npatterns())]
         full = Oracle.from_core(core)
         local = E.ExaModel(core, device=dev, rank=rank, world=world)
-        sm = ShardedExaModel(local, pats, gather=True)
         x = core.meta()["x0"] + 0.01 * np.random.default_rng(0).uniform(-1, 1, full.nvar)
         y = np.random.default_rng(1).standard_normal(full.ncon)
         dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
-        ref = full.obj(x)
-        assert abs(sm.obj(dx) - ref) <= 1e-10 * max(1.0, abs(ref))
-        assert_close(sm.grad(dx, local.new(local.nvar)).cpu().numpy(), full.grad(x), "grad")
-        assert_close(sm.cons_nln(dx, local.new(local.ncon)).cpu().numpy(), full.cons(x), "cons")
-        assert_close(sm.jac_coord(dx, local.new(local.nnzj).fill_(float("nan"))).cpu().numpy(), full.jac_coord(x), "jac")
-        assert_close(sm.hess_coord(dx, dy, local.new(local.nnzh).fill_(float("nan")), obj_weight=0.5).cpu().numpy(),
-                     full.hess_coord(x, y, 0.5), "hess")
         v = torch.from_numpy(np.random.default_rng(2).standard_normal(full.nvar)).cuda()
         w = torch.from_numpy(np.random.default_rng(3).standard_normal(full.ncon)).cuda()
-        assert_close(sm.jprod_nln(dx, v, local.new(local.ncon)).cpu().numpy(), full.jprod(x, v.cpu().numpy()), "jprod")
-        assert_close(sm.jtprod_nln(dx, w, local.new(local.nvar)).cpu().numpy(), full.jtprod(x, w.cpu().numpy()), "jtprod")
-        assert_close(sm.hprod(dx, dy, v, local.new(local.nvar), obj_weight=0.5).cpu().numpy(), full.hprod(x, y, v.cpu().numpy(), 0.5), "hprod")
-        # sharded output left in place: only this rank's slices are written
-        sm.gather = False
-        h = sm.hess_coord(dx, dy, local.new(local.nnzh).fill_(float("nan")), obj_weight=0.5).cpu().numpy()
-        mine = np.zeros(local.nnzh, dtype=bool)
-        for lo, hi in sm.slices(2, rank):
-            mine[lo:hi] = True
-        assert not np.isnan(h[mine]).any() and np.isnan(h[~mine]).all()
-        assert_close(h[mine], full.hess_coord(x, y, 0.5)[mine], "hess shard")
+        nan = float("nan")
+
+        def checks(sm):
+            ref = full.obj(x)
+            assert abs(sm.obj(dx) - ref) <= 1e-10 * max(1.0, abs(ref))
+            assert_close(sm.grad(dx, local.new(local.nvar).fill_(nan)).cpu().numpy(), full.grad(x), "grad")
+            assert_close(sm.cons_nln(dx, local.new(local.ncon).fill_(nan)).cpu().numpy(), full.cons(x), "cons")
+            assert_close(sm.jac_coord(dx, local.new(local.nnzj).fill_(nan)).cpu().numpy(), full.jac_coord(x), "jac")
+            assert_close(sm.hess_coord(dx, dy, local.new(local.nnzh).fill_(nan), obj_weight=0.5).cpu().numpy(),
+                         full.hess_coord(x, y, 0.5), "hess")
+            assert_close(sm.jprod_nln(dx, v, local.new(local.ncon).fill_(nan)).cpu().numpy(), full.jprod(x, v.cpu().numpy()), "jprod")
+            assert_close(sm.jtprod_nln(dx, w, local.new(local.nvar).fill_(nan)).cpu().numpy(), full.jtprod(x, w.cpu().numpy()), "jtprod")
+            assert_close(sm.hprod(dx, dy, v, local.new(local.nvar).fill_(nan), obj_weight=0.5).cpu().numpy(), full.hprod(x, y, v.cpu().numpy(), 0.5), "hprod")
+            # sharded output left in place: only this rank's slices are written
+            sm.gather = False
+            h = sm.hess_coord(dx, dy, local.new(local.nnzh).fill_(nan), obj_weight=0.5).cpu().numpy()
+            mine = np.zeros(local.nnzh, dtype=bool)
+            for lo, hi in sm.slices(2, rank):
+                mine[lo:hi] = True
+            assert not np.isnan(h[mine]).any() and np.isnan(h[~mine]).all()
+            assert_close(h[mine], full.hess_coord(x, y, 0.5)[mine], "hess shard")
+            sm.gather = True
+
+        # (1) collectives on the host side (torch.distributed): the handle returns partial results
+        sm = ShardedExaModel(local, pats, gather=True)
+        assert not sm.abi
+        checks(sm)
+        if backend == "nccl":
+            # (2) the library's own NCCL communicator (exb_comm_init): every reducing callback completes itself
+            local.comm_init(mode="replicate")
+            sm = ShardedExaModel(local, pats, gather=True)
+            assert sm.abi
+            checks(sm)
+            st = local.comm_stats()
+            assert st["attached"] == 1 and st["collectives"] >= 7
+            # (3) owner mode, the sharded consumer: g on the owned variables, c on the rows of the own points
+            local.comm_set_mode("owner")
+            lo, hi = local.owned()
+            assert (lo, hi) == (full.nvar * rank // world, full.nvar * (rank + 1) // world)
+            g = local.grad(dx, local.new(local.nvar).fill_(nan)).cpu().numpy()
+            assert_close(g[lo:hi], full.grad(x)[lo:hi], "grad (owned variables)")
+            if which == "lv":   # shift-indexed objective: owner-computed per variable, nothing is exchanged
+                assert local.comm_stats()["last_collectives"] == 0
+            c = local.cons_nln(dx, local.new(local.ncon).fill_(nan)).cpu().numpy()
+            cref = full.cons(x)
+            for k, pt in enumerate(pats):
+                if pt["kind"] == 1:
+                    sh = local.shard(k)
+                    assert_close(c[pt["o0"] + sh["lo"]:pt["o0"] + sh["hi"]], cref[pt["o0"] + sh["lo"]:pt["o0"] + sh["hi"]], "cons (own rows)")
+            if which == "lv":
+                assert local.comm_stats()["last_collectives"] == 0
+            assert abs(local.obj(dx) - full.obj(x)) <= 1e-10 * max(1.0, abs(full.obj(x)))
+            local.comm_destroy()
         q.put((rank, "ok"))
     except Exception:  # pragma: no cover
         import traceback
