@@ -41,7 +41,8 @@ exb_host_jac_structure64 exb_host_hess_structure64 exb_shard exb_stats exb_last_
 exb_jprod exb_jtprod exb_hprod exb_compressed_dims exb_jac_structure_compressed64 exb_hess_structure_compressed64
 exb_jac_compressed exb_hess_compressed exb_set_timing exb_timings exb_kernel_choice exb_host_bytes
 exb_comm_unique_id exb_comm_init exb_comm_attach exb_comm_destroy exb_comm_set_mode exb_comm_gather_coo exb_owned
-exb_comm_stats""".split()
+exb_comm_stats exb_compressed_shard exb_jac_structure_compressed32 exb_hess_structure_compressed32
+exb_host_jac_compressed exb_host_hess_compressed exb_plan_tile exb_eval""".split()
 
 
 class ExbError(RuntimeError):
@@ -132,6 +133,12 @@ class Plan:
         o = np.zeros(max(1, info["ncomp1" if which == 1 else "ncomp2"]), dtype=np.int64)
         _check(lib().exb_plan_comp(self.h, k, which, _np_ptr(o)))
         return o[: info["ncomp1" if which == 1 else "ncomp2"]]
+
+    def tile_info(self):
+        """Fused duplicate-free Hessian (column-tile kernel): applicability and closed-form unique count."""
+        o = np.zeros(4, dtype=np.int64)
+        _check(lib().exb_plan_tile(self.h, _np_ptr(o)))
+        return {"fused": bool(o[0]), "nnzh_unique": int(o[1]), "distances": int(o[2]), "halo": int(o[3])}
 
     def source(self):
         src, n = C.c_char_p(), C.c_size_t()
@@ -270,6 +277,16 @@ class ExaModel:
             _check(lib().exb_host_hess(self.h, self._host(x, self.nvar), yp, w, self._host(vals, self.nnzh)))
         return vals
 
+    def eval_all(self, x, y, obj_out, g, c, jac, hess, obj_weight=1.0, mask=31):
+        """obj + grad! + cons! + jac_coord! + hess_coord! at the same x from ONE sweep (exb_eval): every data point is
+        evaluated once.  `obj_out` is a 1-element CUDA tensor (no synchronisation).  `mask` selects callbacks (bit 0 obj,
+        1 grad, 2 cons, 3 jac, 4 hess); outputs that are not requested may be None."""
+        def p(t, n):
+            return None if t is None else self._dev(t, n)
+        _check(lib().exb_eval(self.h, C.c_uint(mask), self._dev(x, self.nvar), p(y, self.ncon), C.c_double(float(obj_weight)),
+                              p(obj_out, 1), p(g, self.nvar), p(c, self.ncon), p(jac, self.nnzj), p(hess, self.nnzh), self._stream()))
+        return obj_out, g, c, jac, hess
+
     def _structure(self, which, n, rows, cols):
         torch = self._torch
         if _is_torch(rows):
@@ -339,6 +356,22 @@ class ExaModel:
     def compressed(self):
         """`CompressedNLPModel(m)` (src/utils.jl:425-579): the same model with duplicate COO entries summed."""
         return CompressedExaModel(self)
+
+    def host_hess_compressed(self, x, y, vals, obj_weight=1.0):
+        """Duplicate-free `hess_coord!` with HOST buffers (exb_host_hess_compressed): the D2H copy carries the unique entries only."""
+        yp = None if y is None else self._host(y, self.ncon)
+        _check(lib().exb_host_hess_compressed(self.h, self._host(x, self.nvar), yp, C.c_double(float(obj_weight)), _np_ptr(vals)))
+        return vals
+
+    def host_jac_compressed(self, x, vals):
+        _check(lib().exb_host_jac_compressed(self.h, self._host(x, self.nvar), _np_ptr(vals)))
+        return vals
+
+    def compressed_shard(self):
+        """(lo, hi, fused): range of the duplicate-free Hessian values this handle writes; fused = emitted by one launch."""
+        o = np.zeros(3, dtype=np.int64)
+        _check(lib().exb_compressed_shard(self.h, _np_ptr(o)))
+        return int(o[0]), int(o[1]), bool(o[2])
 
     # -- multi-GPU: the library's own communicator (include/exa_b200.h "multi-GPU") ---------------------
     def comm_init(self, group=None, mode="replicate"):
@@ -417,35 +450,54 @@ class ExaModel:
 
 class CompressedExaModel:
     """Duplicate-free COO view of an `ExaModel`: unique (row, col) coordinates in the reference's order
-    (sorted by (col, row), src/utils.jl:478-487,509-510), duplicate values summed (`_compress!`, :564-571)."""
+    (sorted by (col, row), src/utils.jl:478-487,509-510), duplicate values summed (`_compress!`, :564-571).
+    The Hessian of a shift-indexed model is emitted duplicate-free by ONE launch (`fused_hess`); see include/exa_b200.h."""
 
     def __init__(self, inner):
         self.inner = inner
-        nj, nh = C.c_int64(), C.c_int64()
-        _check(lib().exb_compressed_dims(inner.h, C.byref(nj), C.byref(nh)))
-        self.nvar, self.ncon, self.nnzj, self.nnzh = inner.nvar, inner.ncon, int(nj.value), int(nh.value)
+        nh = C.c_int64()
+        _check(lib().exb_compressed_dims(inner.h, None, C.byref(nh)))
+        self.nvar, self.ncon, self.nnzh = inner.nvar, inner.ncon, int(nh.value)
+        self._nnzj = None
+        self.hess_lo, self.hess_hi, self.fused_hess = inner.compressed_shard()
         for a in ("obj", "grad", "cons_nln", "cons", "new"):
             setattr(self, a, getattr(inner, a))
 
-    def jac_structure(self, rows, cols):
+    @property
+    def nnzj(self):
+        if self._nnzj is None:
+            nj = C.c_int64()
+            _check(lib().exb_compressed_dims(self.inner.h, C.byref(nj), None))
+            self._nnzj = int(nj.value)
+        return self._nnzj
+
+    def _structure(self, which, n, rows, cols):
         i = self.inner
-        assert rows.dtype == cols.dtype == i._torch.int64, "compressed structures are written as int64"
-        _check(lib().exb_jac_structure_compressed64(i.h, i._dev(rows, self.nnzj, rows.dtype), i._dev(cols, self.nnzj, cols.dtype), i._stream()))
+        torch = i._torch
+        assert rows.dtype == cols.dtype and rows.dtype in (torch.int64, torch.int32), "structures are int64 or int32 tensors"
+        f = getattr(lib(), f"exb_{which}_structure_compressed{64 if rows.dtype == torch.int64 else 32}")
+        _check(f(i.h, i._dev(rows, n, rows.dtype), i._dev(cols, n, cols.dtype), i._stream()))
         return rows, cols
 
+    def jac_structure(self, rows, cols):
+        return self._structure("jac", self.nnzj, rows, cols)
+
     def hess_structure(self, rows, cols):
-        i = self.inner
-        assert rows.dtype == cols.dtype == i._torch.int64, "compressed structures are written as int64"
-        _check(lib().exb_hess_structure_compressed64(i.h, i._dev(rows, self.nnzh, rows.dtype), i._dev(cols, self.nnzh, cols.dtype), i._stream()))
-        return rows, cols
+        return self._structure("hess", self.nnzh, rows, cols)
 
     def jac_coord(self, x, vals):
         i = self.inner
-        _check(lib().exb_jac_compressed(i.h, i._dev(x, self.nvar), i._dev(vals, self.nnzj), i._stream()))
+        if _is_torch(x):
+            _check(lib().exb_jac_compressed(i.h, i._dev(x, self.nvar), i._dev(vals, self.nnzj), i._stream()))
+        else:
+            i.host_jac_compressed(x, i._host(vals, self.nnzj) and vals)
         return vals
 
     def hess_coord(self, x, y, vals, obj_weight=1.0):
         i = self.inner
-        yp = None if y is None else i._dev(y, self.ncon)
-        _check(lib().exb_hess_compressed(i.h, i._dev(x, self.nvar), yp, C.c_double(float(obj_weight)), i._dev(vals, self.nnzh), i._stream()))
+        if _is_torch(x):
+            yp = None if y is None else i._dev(y, self.ncon)
+            _check(lib().exb_hess_compressed(i.h, i._dev(x, self.nvar), yp, C.c_double(float(obj_weight)), i._dev(vals, self.nnzh), i._stream()))
+        else:
+            i.host_hess_compressed(x, y, i._host(vals, self.nnzh) and vals, obj_weight=obj_weight)
         return vals

@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define EXB_TYPES_ONLY 1
+#include "exb_device.cuh"   // ExbTile
 #include "exb_fixed.h"
 
 namespace {
@@ -89,6 +91,18 @@ __global__ void __launch_bounds__(1024) k_sum(const double* __restrict__ part, l
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     if (threadIdx.x == 0) out[0] = v;
   }
+}
+
+// (row, col) of the duplicate-free Hessian of a shift-indexed model, in (col, row) order: one thread per column
+// (see ExbTile; the values come from exb_tile_body in the generated module)
+template <typename I>
+__global__ void k_tile_structure(const ExbTile t, I* __restrict__ rows, I* __restrict__ cols) {
+  const long long c = t.c_lo + (long long)blockIdx.x * 256 + threadIdx.x;
+  if (c >= t.c_hi) return;
+  long long p = 0;
+  for (int r = 0; r < t.D; r++) { long long v = c - t.lo[r]; v = v < 0 ? 0 : v; p += v > t.len[r] ? t.len[r] : v; }
+  for (int r = 0; r < t.D; r++)
+    if (c >= t.lo[r] && c < t.lo[r] + t.len[r]) { rows[p] = (I)(c + t.dist[r]); cols[p] = (I)c; p++; }
 }
 
 __global__ void k_fill_ll(long long* p, long long n, long long v) {
@@ -183,6 +197,21 @@ cudaError_t exb_fx_make_keys(const long long* major, const long long* minor, lon
 cudaError_t exb_fx_decode_keys(const long long* keys, long long mult, long long* major, long long* minor, long long n, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   k_decode_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, mult, major, minor, n);
+  return cudaGetLastError();
+}
+
+cudaError_t exb_fx_tile_structure(const void* tile, void* rows, void* cols, int idx32, cudaStream_t st) {
+  const ExbTile& t = *(const ExbTile*)tile;
+  if (t.c_hi <= t.c_lo) return cudaSuccess;
+  const unsigned grid = (unsigned)((t.c_hi - t.c_lo + 255) / 256);
+  if (idx32) k_tile_structure<int><<<grid, 256, 0, st>>>(t, (int*)rows, (int*)cols);
+  else k_tile_structure<long long><<<grid, 256, 0, st>>>(t, (long long*)rows, (long long*)cols);
+  return cudaGetLastError();
+}
+
+cudaError_t exb_fx_narrow(const long long* in, int* out, long long n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  k_narrow<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
   return cudaGetLastError();
 }
 

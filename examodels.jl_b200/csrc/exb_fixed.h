@@ -17,3 +17,6 @@ cudaError_t exb_fx_spmv(const double* buf, const void* ptr, const void* slot, co
 cudaError_t exb_fx_gather(const long long* src, const void* slot, int idx32, void* out, long long n, cudaStream_t st);
 cudaError_t exb_fx_make_keys(const long long* major, const long long* minor, long long mult, long long* keys, long long n, cudaStream_t st);
 cudaError_t exb_fx_decode_keys(const long long* keys, long long mult, long long* major, long long* minor, long long n, cudaStream_t st);
+// tile: const ExbTile* (exb_device.cuh); rows / cols: int64 (idx32 = 0) or int32 device arrays
+cudaError_t exb_fx_tile_structure(const void* tile, void* rows, void* cols, int idx32, cudaStream_t st);
+cudaError_t exb_fx_narrow(const long long* in, int* out, long long n, cudaStream_t st);

@@ -49,6 +49,7 @@ struct PatternPlan {
   i64 oa = 0;                  // aug: first conbuffer slot (ConstraintAugmentation.oa)
   i64 ob = 0;                  // obj: first objbuffer slot
   int ppt0 = 1, ppt1 = 1, ppt2 = 1;   // points per thread in the value / first-order / second-order kernels
+  int ppte = 1;                       // ... and in the fused evaluation kernel (exb_eval_g0)
   std::vector<int> leaf1;      // representative Var IR node per first-order slot
   std::vector<std::pair<int, int>> leaf2;
   // owner-computes gradient (see gen_pattern, g1): every first-order slot's variable index is `t + shift1[j]` with
@@ -63,6 +64,13 @@ struct PatternPlan {
   // (1-based); xr_ok = false: indices come from iterator data, anything may be read
   bool xr_ok = false, xr_shift = false, xr_fixed = false;
   i64 rlo = 0, rhi = 0, flo = 0, fhi = 0;
+  // column-tile kernels (exb_tile_body, duplicate-free Hessian): every variable of the pattern is `t + const`, t the value of
+  // a range iterator.  Second-order slot j is the lower-triangle entry (c + t2_d[j], c) in column c = t + t2_cb[j]; t2_r[j] is
+  // the rank of t2_d[j] in the model's sorted set of distinct row - column distances (Plan::hd)
+  bool tile_ok = false;
+  std::vector<i64> t2_cb, t2_d;
+  std::vector<int> t2_r;
+  i64 t_cbmin = 0, t_cbmax = 0;
 };
 
 struct Plan {
@@ -72,8 +80,13 @@ struct Plan {
   std::string source;  // generated module (without the device header)
   std::string error;
   // pattern lists per kernel (indices into pats), fixed at generation time
-  std::vector<int> k_hess, k_jac, k_sgrad, k_ggrad, k_cons, k_obj, k_aug;
+  std::vector<int> k_hess, k_jac, k_sgrad, k_ggrad, k_cons, k_obj, k_aug, k_eval;
   bool hess_windowed = false;  // every Hessian pattern has an x window: the persistent kernel exb_hessp_g0 is generated too
+  // duplicate-free Hessian emitted directly (exb_hessc_g0): possible when every pattern with second-order slots is tile_ok
+  bool tile_ok = false;
+  std::vector<i64> hd;         // distinct row - column distances of the model's Hessian entries, ascending
+  std::vector<i64> h_lo, h_len;   // per distance: the ONE interval of (1-based) columns in which the entry exists
+  int tile_halo = 0, tile_ppt = 2;   // tile_ppt: columns per thread (EXB_TUNE_TILE_PPT)
   bool idx32 = false;          // every index (variables, points, slots) fits 31 bits: address arithmetic in 32 bits
   int block = 128, minb = 16;  // launch shape of the generated kernels (tuning knobs: EXB_TUNE_BLOCK / EXB_TUNE_MINB)
 };
@@ -619,6 +632,27 @@ inline void emit_eval_fn(std::ostringstream& o, const std::string& name, const s
   }
   o << "  }\n";
 }
+// Fused evaluation of one point: value, first-order slots (adjoint 1) and second-order slots (adjoint a0) from ONE forward
+// sweep (exb_eval_block).  Same fast / slow split as emit_eval_fn.
+inline void emit_eval3_fn(std::ostringstream& o, const std::string& params, const std::string& args, int n1, int n2, const Body& B,
+                          const std::vector<std::string>& tail) {
+  const std::string outs = ", double& v, double (&s1)[" + std::to_string(n1) + "], double (&s2)[" + std::to_string(n2) + "]";
+  o << "  template <bool SLOW, class XA> __device__ static __forceinline__ void d012_t(" << params << outs << ", bool& bad) {\n";
+  for (auto& l : B.lines) o << "    " << l << "\n";
+  for (auto& l : tail) o << "    " << l << "\n";
+  o << "  }\n";
+  const bool fast = body_uses_fast(B);
+  if (fast)
+    o << "  template <class XA> __device__ static __noinline__ void d012_slow(" << params << ", double* __restrict__ so) { bool bad = false; double v; double s1[" << n1
+      << "], s2[" << n2 << "]; d012_t<true>(" << args << ", v, s1, s2, bad); so[0] = v; for (int j = 0; j < " << n1 << "; j++) so[1 + j] = s1[j]; for (int j = 0; j < "
+      << n2 << "; j++) so[" << 1 + n1 << " + j] = s2[j]; }\n";
+  o << "  template <class XA> __device__ static __forceinline__ void d012(" << params << outs << ") {\n    bool bad = false;\n";
+  o << "    d012_t<false>(" << args << ", v, s1, s2, bad);\n";
+  if (fast)
+    o << "    if (bad) { double q[" << 1 + n1 + n2 << "]; d012_slow(" << args << ", q); v = q[0]; for (int j = 0; j < " << n1 << "; j++) s1[j] = q[1 + j]; for (int j = 0; j < "
+      << n2 << "; j++) s2[j] = q[" << 1 + n1 << " + j]; }\n";
+  o << "  }\n";
+}
 // Points per thread: cheap bodies are dominated by the per-block prologue / tile-store epilogue, so they get
 // several points per thread (also more loads in flight per thread); heavy bodies keep one.
 inline int body_weight(const Body& B) {
@@ -670,7 +704,26 @@ inline void compute_xrange(PatternPlan& p) {
   }
 }
 
-inline std::string gen_pattern(PatternPlan& p, int index, bool windowed) {
+// shift analysis for the column-tile kernels (see PatternPlan::tile_ok)
+inline void compute_tile(PatternPlan& p) {
+  p.tile_ok = p.ir.itr_kind == ITR_RANGE && p.ir.kind != KIND_AUG;
+  p.t2_cb.clear(); p.t2_d.clear(); p.t2_r.clear();
+  if (p.o2step == 0) return;
+  bool first = true;
+  for (int j = 0; j < p.o2step && p.tile_ok; j++) {
+    i64 ca, ka, cb, kb;
+    const int na = (int)p.ir.nodes[(size_t)p.leaf2[(size_t)j].first].a, nb = (int)p.ir.nodes[(size_t)p.leaf2[(size_t)j].second].a;
+    if (!affine_index(p.ir, na, ca, ka) || !affine_index(p.ir, nb, cb, kb) || ca != 1 || cb != 1) { p.tile_ok = false; break; }
+    const i64 lo = std::min(ka, kb), d = std::max(ka, kb) - lo;
+    p.t2_cb.push_back(lo); p.t2_d.push_back(d);
+    if (first || lo < p.t_cbmin) p.t_cbmin = lo;
+    if (first || lo > p.t_cbmax) p.t_cbmax = lo;
+    first = false;
+  }
+  if (p.tile_ok && p.t_cbmax - p.t_cbmin > 64) p.tile_ok = false;   // halo of re-evaluated points per tile
+}
+
+inline std::string gen_pattern(PatternPlan& p, int index, bool windowed, const std::vector<i64>* hd = nullptr, int tile_stride = 0) {
   std::ostringstream o;
   const int ns1 = p.o1step, ns2 = p.o2step;
   const int a1 = ns1 > 0 ? ns1 : 1, a2 = ns2 > 0 ? ns2 : 1;
@@ -761,6 +814,52 @@ inline std::string gen_pattern(PatternPlan& p, int index, bool windowed) {
     }
     emit_eval_fn(o, "d2", A + ", const XA x, const double* __restrict__ th, const double a0", "pa, kg, x, th, a0", a2, B, tail);
     p.ppt2 = ppt_for(body_weight(B), a2);
+  }
+  {  // d012 (exb_eval: one sweep for cons! / obj + jac_coord! / grad! slots + hess_coord! slots; src/nlp.jl:1827-1940 evaluates the
+     // same tree three to five times at the same x)
+    Body B; Gen g(p, B, 2);
+    NV& r = g.fwd(p.ir.root);
+    std::vector<std::string> tail;
+    tail.push_back("v = " + r.x.s + ";");
+    if (ns1 > 0) {
+      g.comp = &p.comp1; g.slot.assign((size_t)ns1, K(0)); g.cnt = 0;
+      g.rpass1(p.ir.root, K(1));
+      for (int j = 0; j < ns1; j++) tail.push_back("s1[" + std::to_string(j) + "] = " + g.slot[(size_t)j].s + ";");
+    }
+    if (ns2 > 0) {
+      g.comp = &p.comp2; g.slot.assign((size_t)ns2, K(0)); g.cnt = 0;
+      g.hrpass0(p.ir.root, Sym("a0"), K(0));
+      for (int j = 0; j < ns2; j++) tail.push_back("s2[" + std::to_string(j) + "] = " + g.slot[(size_t)j].s + ";");
+    }
+    emit_eval3_fn(o, A + ", const XA x, const double* __restrict__ th, const double a0", "pa, kg, x, th, a0", a1, a2, B, tail);
+    p.ppte = ppt_for(body_weight(B), a1 + a2);
+    o << "  static constexpr int PPTE = " << p.ppte << "; static constexpr bool G1 = " << (p.gather1 ? "true" : "false") << ";\n";
+  }
+  if (hd != nullptr && ns2 > 0 && p.tile_ok) {
+    // Column-tile form (exb_tile_body): the block stages the second-order slots of the points around its tile of columns in
+    // shared memory (`raw`, point-major, TSTRIDE words per point); the thread that owns column c then sums every slot that
+    // lands in column c -- slot j of the point whose range value is c - CB_j -- into acc[rank of the entry's row - column
+    // distance].  The additions run in ascending point, then slot order: the order in which `_compress!` (utils.jl:564-571)
+    // meets the duplicates of one coordinate in the sorted list.
+    std::vector<int> ord((size_t)ns2);
+    for (int j = 0; j < ns2; j++) ord[(size_t)j] = j;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return p.t2_cb[(size_t)a] > p.t2_cb[(size_t)b]; });
+    o << "  static constexpr bool TILE = true; static constexpr int TSTRIDE = " << tile_stride << "; static constexpr long long CBMIN = " << p.t_cbmin
+      << ", CBMAX = " << p.t_cbmax << ";\n";
+    // rp = the staged slots of the point whose range value equals the column (local point ql): slot j of the point CB_j
+    // earlier sits at the compile-time offset j - CB_j * TSTRIDE from it.  CHECK = false: interior tile, every point exists.
+    o << "  template <bool CHECK> __device__ static __forceinline__ void hgather(const double* __restrict__ rp, const int ql, const int qlo, const int qhi, double (&acc)["
+      << hd->size() << "]) {\n";
+    for (int j : ord) {
+      const int r = p.t2_r[(size_t)j];
+      const long long off = (long long)j - (long long)p.t2_cb[(size_t)j] * tile_stride;
+      o << "    if (!CHECK || (ql - (" << p.t2_cb[(size_t)j] << ") >= qlo && ql - (" << p.t2_cb[(size_t)j] << ") < qhi)) acc[" << r << "] += rp[" << off << "];\n";
+    }
+    o << "  }\n";
+  } else {
+    o << "  static constexpr bool TILE = false; static constexpr int TSTRIDE = 1; static constexpr long long CBMIN = 0, CBMAX = 0;\n";
+    if (hd != nullptr)
+      o << "  template <bool CHECK> __device__ static __forceinline__ void hgather(const double* __restrict__, const int, const int, const int, double (&)[" << hd->size() << "]) {}\n";
   }
   {  // s1: variable index per first-order slot (jacobian.jl:69-83)
     Body B; Gen g(p, B, 0);
@@ -861,7 +960,47 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes) {
     for (auto& p : pl.pats) { compute_window(p); compute_xrange(p); if (p.o2step > 0) { any = true; pl.hess_windowed = pl.hess_windowed && p.win; } }
     pl.hess_windowed = pl.hess_windowed && any;
   }
-  for (size_t k = 0; k < pl.pats.size(); k++) o << gen_pattern(pl.pats[k], (int)k, pl.hess_windowed && pl.pats[k].win);
+  {  // duplicate-free Hessian through the column-tile kernel: every pattern with second-order slots must be shift-indexed, and
+     // every row - column distance must exist in ONE interval of columns (else: the sorted gather of exb_runtime.cpp)
+    bool any = false; pl.tile_ok = true;
+    for (auto& p : pl.pats) { compute_tile(p); if (p.o2step > 0) { any = true; pl.tile_ok = pl.tile_ok && p.tile_ok; } }
+    pl.tile_ok = pl.tile_ok && any && getenv("EXB_NO_TILE") == nullptr;
+    if (const char* e = getenv("EXB_TUNE_TILE_PPT")) { int v = atoi(e); if (v >= 1 && v <= 8) pl.tile_ppt = v; }
+    if (pl.tile_ok) {
+      for (auto& p : pl.pats) for (i64 d : p.t2_d) pl.hd.push_back(d);
+      std::sort(pl.hd.begin(), pl.hd.end());
+      pl.hd.erase(std::unique(pl.hd.begin(), pl.hd.end()), pl.hd.end());
+      if (pl.hd.size() > 16) pl.tile_ok = false;
+    }
+    if (pl.tile_ok) {
+      const size_t D = pl.hd.size();
+      std::vector<std::vector<std::pair<i64, i64>>> iv(D);
+      for (auto& p : pl.pats) {
+        p.t2_r.clear();
+        for (size_t j = 0; j < p.t2_d.size(); j++) {
+          const int r = (int)(std::lower_bound(pl.hd.begin(), pl.hd.end(), p.t2_d[j]) - pl.hd.begin());
+          p.t2_r.push_back(r);
+          if (p.ir.nitr > 0) iv[(size_t)r].push_back({p.ir.range_start + p.t2_cb[j], p.ir.range_start + p.ir.nitr - 1 + p.t2_cb[j]});
+        }
+        if (p.o2step > 0) pl.tile_halo = std::max(pl.tile_halo, (int)(p.t_cbmax - p.t_cbmin));
+      }
+      pl.h_lo.assign(D, 1); pl.h_len.assign(D, 0);
+      for (size_t r = 0; r < D && pl.tile_ok; r++) {
+        auto& v = iv[r];
+        if (v.empty()) continue;
+        std::sort(v.begin(), v.end());
+        i64 lo = v[0].first, hi = v[0].second;
+        for (size_t q = 1; q < v.size(); q++) { if (v[q].first > hi + 1) { pl.tile_ok = false; break; } hi = std::max(hi, v[q].second); }
+        if (lo < 1 || hi > pl.m.nvar) pl.tile_ok = false;
+        pl.h_lo[r] = lo; pl.h_len[r] = hi - lo + 1;
+      }
+    }
+    if (!pl.tile_ok) { pl.hd.clear(); pl.h_lo.clear(); pl.h_len.clear(); }
+  }
+  for (size_t k = 0; k < pl.pats.size(); k++) {
+    int stride = pl.pats[k].o2step | 1;   // odd word stride: conflict-free 64-bit shared-memory accesses
+    o << gen_pattern(pl.pats[k], (int)k, pl.hess_windowed && pl.pats[k].win, pl.tile_ok ? &pl.hd : nullptr, stride);
+  }
   // kernel pattern lists
   for (size_t k = 0; k < pl.pats.size(); k++) {
     const PatternPlan& p = pl.pats[k];
@@ -869,6 +1008,7 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes) {
     if (p.ir.kind == KIND_OBJ) { pl.k_obj.push_back((int)k); if (p.o1step > 0) (p.gather1 ? pl.k_ggrad : pl.k_sgrad).push_back((int)k); }
     else { pl.k_cons.push_back((int)k); if (p.o1step > 0) pl.k_jac.push_back((int)k); }
     if (p.ir.kind == KIND_AUG) pl.k_aug.push_back((int)k);
+    pl.k_eval.push_back((int)k);   // every pattern has a value
   }
   auto kern = [&](const char* name, const char* body, const std::vector<int>& v, const char* targ) {
     if (v.empty()) return;
@@ -876,7 +1016,12 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes) {
       << body << "<" << targ << plist(v) << ">(g, c); }\n";
   };
   kern("exb_hess_g0", "exb_hess_body", pl.k_hess, "");
+  if (pl.tile_ok) {
+    o << "extern \"C\" __global__ void __launch_bounds__(EXB_BLOCK, EXB_MINB) exb_hessc_g0(const ExbGroup g, const ExbCall c, const ExbTile t) { "
+      << "exb_tile_body<" << pl.hd.size() << ", " << pl.tile_ppt << ", " << plist(pl.k_hess) << ">(g, c, t); }\n";
+  }
   if (pl.hess_windowed) kern("exb_hessp_g0", "exb_hessp_body", pl.k_hess, "");
+  kern("exb_eval_g0", "exb_eval_body", pl.k_eval, "");
   kern("exb_jac_g0", "exb_d1_body", pl.k_jac, "");
   kern("exb_sgrad_g0", "exb_d1_body", pl.k_sgrad, "");
   kern("exb_ggrad_g0", "exb_ggrad_body", pl.k_ggrad, "");

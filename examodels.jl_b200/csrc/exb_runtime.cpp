@@ -163,10 +163,10 @@ bool load_nccl() {
   return g_nccl.ok;
 }
 
-enum { KN_HESS, KN_JAC, KN_SGRAD, KN_GGRAD, KN_CONS, KN_OBJ, KN_JSTRUCT64, KN_JSTRUCT32, KN_GSTRUCT64, KN_HSTRUCT64, KN_HSTRUCT32, KN_AUGROW, KN_JPROD, KN_JTPROD, KN_HPROD, KN_COUNT };
+enum { KN_HESS, KN_JAC, KN_SGRAD, KN_GGRAD, KN_CONS, KN_OBJ, KN_JSTRUCT64, KN_JSTRUCT32, KN_GSTRUCT64, KN_HSTRUCT64, KN_HSTRUCT32, KN_AUGROW, KN_JPROD, KN_JTPROD, KN_HPROD, KN_HESSC, KN_EVAL, KN_COUNT };
 const char* KNAME[KN_COUNT] = {"exb_hess_g0", "exb_jac_g0", "exb_sgrad_g0", "exb_ggrad_g0", "exb_cons_g0", "exb_obj_g0", "exb_jstruct64_g0",
                                "exb_jstruct32_g0", "exb_gstruct64_g0", "exb_hstruct64_g0", "exb_hstruct32_g0", "exb_augrow_g0",
-                               "exb_jprod_g0", "exb_jtprod_g0", "exb_hprod_g0"};
+                               "exb_jprod_g0", "exb_jtprod_g0", "exb_hprod_g0", "exb_hessc_g0", "exb_eval_g0"};
 
 }  // namespace
 
@@ -185,12 +185,13 @@ struct exb_plan {
   bool from_cache = false;
   const std::vector<int>& list(int kn) const {
     switch (kn) {
-      case KN_HESS: case KN_HSTRUCT64: case KN_HSTRUCT32: case KN_HPROD: return pl.k_hess;
+      case KN_HESS: case KN_HSTRUCT64: case KN_HSTRUCT32: case KN_HPROD: case KN_HESSC: return pl.k_hess;
       case KN_JAC: case KN_JSTRUCT64: case KN_JSTRUCT32: case KN_JPROD: case KN_JTPROD: return pl.k_jac;
       case KN_SGRAD: case KN_GSTRUCT64: return pl.k_sgrad;
       case KN_GGRAD: return pl.k_ggrad;
       case KN_CONS: return pl.k_cons;
       case KN_OBJ: return pl.k_obj;
+      case KN_EVAL: return pl.k_eval;
       default: return pl.k_aug;
     }
   }
@@ -212,6 +213,7 @@ struct Launch {          // one generated kernel, ready to launch
   ExbGroup gp{};                      // the persistent kernel's own block -> pattern table
   std::vector<ExbChunk> hchunk;       // host copy of the chunk table (windowed launches of the pipelined host shims)
   std::vector<int> ppt, ns;           // per listed pattern: points per thread, slots per point
+  bool is_tile = false; ExbTile tile{};   // column-tile kernel (exb_tile_body): third kernel parameter
 };
 
 int make_plan(const void* ir, size_t bytes, exb_plan** out) {
@@ -349,6 +351,7 @@ struct exb_model {
   size_t dev_bytes = 0;
   double* d_theta = nullptr;
   double* d_objpart = nullptr; double* d_obj = nullptr;
+  double* d_objpart_e = nullptr; long long n_objpart_e = 0;   // objective partials of the fused evaluation kernel
   double* d_gradbuf = nullptr; double* d_conbuf = nullptr;
   // sorted (target, slot) lists: grad (ext:39-46) and constraint augmentation (ext:48-53)
   void *g_slot = nullptr, *g_target = nullptr, *g_ptr = nullptr; long long g_runs = 0; int g_i32 = 0, g_dense = 0;
@@ -357,7 +360,8 @@ struct exb_model {
   struct Sorted { void *slot = nullptr, *other = nullptr, *target = nullptr, *ptr = nullptr; long long runs = 0, nslots = 0; int i32 = 0, dense = 0;
                   long long *urows = nullptr, *ucols = nullptr; };
   Sorted jrow, jcol, hrow, hcol, jcmp, hcmp;
-  bool prod_ready = false, cmp_ready = false;
+  bool prod_ready = false, cmp_ready = false, cmpj_ready = false;
+  bool hess_tile = false;   // duplicate-free Hessian straight from the column-tile kernel (exb_hessc_g0): no sorted list, no raw buffer
   double *d_jacbuf = nullptr, *d_hessbuf = nullptr;
   std::vector<long long> lo, hi;   // local point range per pattern
   long long x_lo = 0, x_hi = 0;    // [x_lo, x_hi): the part of x this handle's points can read (the host shims upload only that)
@@ -404,7 +408,8 @@ int launch_fn(exb_model* m, int kn, CUfunction fn, const ExbCall& c, cudaStream_
   Launch& L = m->k[kn];
   ExbGroup g = L.g;
   ExbCall cc = c;
-  void* params[2] = {&g, &cc};
+  ExbTile tt = L.tile;
+  void* params[3] = {&g, &cc, &tt};   // the third parameter exists in the column-tile kernels only
   CUresult r = g_drv.LaunchKernel(fn, L.nblocks, 1, 1, (unsigned)m->plan->pl.block, 1, 1, L.smem, (CUstream)st, params, nullptr);
   if (r != CUDA_SUCCESS) return fail(EXB_ERR_CUDA, std::string("launch of ") + KNAME[kn] + ": " + cu_err(r));
   m->launches++; m->last_launches++;
@@ -611,6 +616,16 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       }
     }
   }
+  {  // fused evaluation kernel (exb_eval_g0): an objective pattern's blocks leave their partial sums at aux + block number
+    long long base = 0;
+    for (size_t k = 0; k < np; k++) {
+      const exb::PatternPlan& p = pl.pats[k];
+      if (p.ir.kind != exb::KIND_OBJ) continue;
+      pa[k].aux = base;
+      base += (pa[k].n + (long long)pl.block * p.ppte - 1) / ((long long)pl.block * p.ppte);
+    }
+    m->n_objpart_e = base;
+  }
   {  // the part of x the local points can read: shifts of range values and fixed indices are known to the plan
     long long xl = pl.m.nvar, xh = 0; bool all = false;
     for (size_t k = 0; k < np && !all; k++) {
@@ -652,6 +667,7 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
   for (int kn = 0; kn < KN_COUNT; kn++) {
     const std::vector<int>& lst = P->list(kn);
     if (lst.empty()) continue;
+    if (kn == KN_HESSC && !pl.tile_ok) continue;
     Launch& L = m->k[kn];
     for (CUmodule mod : m->mods) {
       CUfunction fn = nullptr;
@@ -659,7 +675,7 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       if (r != CUDA_SUCCESS) return fail(EXB_ERR_COMPILE, std::string("kernel ") + KNAME[kn] + " missing from module: " + cu_err(r));
       L.cand.push_back(fn);
     }
-    const bool tunable = kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD || kn == KN_GGRAD || kn == KN_CONS || kn == KN_OBJ;
+    const bool tunable = kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD || kn == KN_GGRAD || kn == KN_CONS || kn == KN_OBJ || kn == KN_HESSC || kn == KN_EVAL;
     L.best = (!tunable || L.cand.size() == 1) ? 0 : tuned[kn];
     L.fn = L.cand[L.best >= 0 ? (size_t)L.best : 0];
     const long long BLK = P->pl.block;
@@ -670,11 +686,37 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       args[q] = pa[(size_t)lst[q]];
       const exb::PatternPlan& p = pl.pats[(size_t)lst[q]];
       const bool k2 = kn == KN_HESS || kn == KN_HPROD, k1 = kn == KN_JAC || kn == KN_SGRAD || kn == KN_JPROD || kn == KN_JTPROD, k0 = kn == KN_CONS || kn == KN_OBJ;
-      const int ppt = k2 ? p.ppt2 : k1 ? p.ppt1 : k0 ? p.ppt0 : 1;
+      const int ppt = kn == KN_EVAL ? p.ppte : k2 ? p.ppt2 : k1 ? p.ppt1 : k0 ? p.ppt0 : 1;
       nb[q] = (args[q].n + BLK * ppt - 1) / (BLK * ppt);
       tot += nb[q]; if (nb[q] > maxnb) maxnb = nb[q];
-      int ns = k2 ? p.o2step : k1 ? p.o1step : 1;
+      int ns = kn == KN_EVAL ? p.o1step + p.o2step : k2 ? p.o2step : k1 ? p.o1step : 1;
       if (ns <= EXB_TILE_MAX_NS && ns * ppt > maxns) maxns = ns * ppt;   // tile words per thread
+    }
+    if (kn == KN_HESSC) {   // one block per tile of T consecutive COLUMNS of the owned range (exb_tile_body), no block -> pattern map
+      void* d_args = nullptr;
+      int rc = dmalloc(m, &d_args, args.size() * sizeof(ExbPatArgs)); if (rc) return rc;
+      CU_TRY(m, cudaMemcpy(d_args, args.data(), args.size() * sizeof(ExbPatArgs), cudaMemcpyHostToDevice));
+      L.g.pat = (const ExbPatArgs*)d_args; L.g.chunk = nullptr; L.g.np = (int)lst.size(); L.g.shift = 0;
+      ExbTile& t = L.tile; memset(&t, 0, sizeof t);
+      L.is_tile = true;
+      t.c_lo = m->v_lo + 1; t.c_hi = m->v_hi + 1;
+      t.T = (int)BLK * pl.tile_ppt - pl.tile_halo; t.D = (int)pl.hd.size();
+      if (t.T < 32) continue;   // halo too wide for this block shape: the sorted gather stays in charge
+      size_t words = (size_t)t.T * (size_t)t.D;
+      for (int r = 0; r < t.D; r++) { t.lo[r] = pl.h_lo[(size_t)r]; t.len[r] = pl.h_len[(size_t)r]; t.dist[r] = pl.hd[(size_t)r]; }
+      for (int pi : lst) {
+        const exb::PatternPlan& p = pl.pats[(size_t)pi];
+        words = std::max(words, (size_t)(t.T + (p.t_cbmax - p.t_cbmin)) * (size_t)(p.o2step | 1));
+      }
+      L.nblocks = (unsigned)((t.c_hi - t.c_lo + t.T - 1) / t.T);
+      L.smem = (unsigned)(8 * ((words + 1) & ~(size_t)1));
+      if (L.smem > 48u * 1024u)
+        for (CUfunction fn : L.cand) {
+          r = g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)L.smem);
+          if (r != CUDA_SUCCESS) return fail(EXB_ERR_CUDA, std::string("cuFuncSetAttribute(max dynamic smem): ") + cu_err(r));
+        }
+      m->hess_tile = true;
+      continue;
     }
     if (kn == KN_GGRAD) {   // one thread per VARIABLE (exb_ggrad_body), no block -> pattern map; runs even when this shard has no points (g = 0)
       void* d_args = nullptr;
@@ -705,7 +747,7 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       L.ppt.push_back(kn == KN_HESS ? p.ppt2 : (kn == KN_JAC || kn == KN_SGRAD) ? p.ppt1 : (kn == KN_CONS || kn == KN_OBJ) ? p.ppt0 : 1);
       L.ns.push_back(kn == KN_HESS ? p.o2step : (kn == KN_JAC || kn == KN_SGRAD) ? p.o1step : 1);
     }
-    L.smem = (kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD) ? (maxns > 1 ? (unsigned)(BLK * maxns * 8) : 16u) : 0u;
+    L.smem = (kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD || kn == KN_EVAL) ? (maxns > 1 ? (unsigned)(BLK * maxns * 8) : 16u) : 0u;
     if (L.smem > 48u * 1024u)   // tiles of patterns with many slots per point: opt in to large dynamic shared memory
       for (CUfunction fn : L.cand) {
         r = g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)L.smem);
@@ -764,6 +806,8 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
   rc = dmalloc(m, (void**)&m->d_objpart, (size_t)(m->k[KN_OBJ].nblocks + 1) * 8); if (rc) return rc;
   CU_TRY(m, cudaMemset(m->d_objpart, 0, (size_t)(m->k[KN_OBJ].nblocks + 1) * 8));   // padding blocks never write
   rc = dmalloc(m, (void**)&m->d_obj, 8); if (rc) return rc;
+  rc = dmalloc(m, (void**)&m->d_objpart_e, (size_t)(m->n_objpart_e + 1) * 8); if (rc) return rc;
+  CU_TRY(m, cudaMemset(m->d_objpart_e, 0, (size_t)(m->n_objpart_e + 1) * 8));
   rc = dmalloc(m, (void**)&m->d_gradbuf, (size_t)pl.nnzg * 8); if (rc) return rc;
   rc = dmalloc(m, (void**)&m->d_conbuf, (size_t)pl.nconaug * 8); if (rc) return rc;
   // gradient sparsity: (var, slot) sorted by var (ext:39-46)
@@ -955,6 +999,13 @@ int exb_plan_comp(const exb_plan* p, int k, int which, int64_t* o) {
   for (size_t q = 0; q < c.size(); q++) o[q] = c[q];
   return EXB_OK;
 }
+int exb_plan_tile(const exb_plan* p, int64_t* o) {
+  if (!p || !o) return fail(EXB_ERR_HANDLE, "invalid handle");
+  const exb::Plan& pl = p->pl;
+  o[0] = pl.tile_ok ? 1 : 0; o[1] = 0; o[2] = (int64_t)pl.hd.size(); o[3] = pl.tile_halo;
+  for (long long v : pl.h_len) o[1] += v;
+  return EXB_OK;
+}
 int exb_plan_source(const exb_plan* p, const char** src, size_t* len) {
   if (!p || !src) return fail(EXB_ERR_HANDLE, "invalid handle");
   *src = p->full_source.c_str();
@@ -1043,22 +1094,23 @@ int exb_obj(exb_model* m, const double* x, double* out_host, void* stream) {
   EXB_END
 }
 
-int exb_grad(exb_model* m, const double* x, double* g, void* stream) {
-  EXB_BEGIN
-  EXB_GUARD(m);
-  TimeScope ts_(m, CB_GRAD, stream);
-  cudaStream_t st = (cudaStream_t)stream;
+// grad! = [fill] + owner-computed patterns (exb_ggrad_g0) + slot patterns (exb_sgrad_g0 -> gradbuffer -> segmented sum) + the
+// sharded model's collective.  slots_ready: the gradient buffer was already filled by the fused evaluation kernel.
+static int grad_impl(exb_model* m, const double* x, double* g, cudaStream_t st, bool slots_ready) {
   const exb::Plan& pl = m->plan->pl;
   ExbCall c{}; c.x = x; c.th = m->d_theta; c.out = m->d_gradbuf;
   const bool gathered = !pl.k_ggrad.empty();
   // fill!(g, 0) (ext:317): needed when some variable has no objective term -- and on a sharded handle, whose g must be zero
   // outside what it computes so that the shards add up
-  if (m->world > 1 || (!gathered && !(m->g_dense && m->g_runs == pl.m.nvar))) CU_TRY(m, cudaMemsetAsync(g, 0, (size_t)pl.m.nvar * 8, st));
+  // (not when the shards never need adding: a communicator is attached and every objective pattern is owner-computed)
+  const bool owner_only = comm_on(m) && pl.k_sgrad.empty() && gathered;
+  if ((m->world > 1 && !owner_only) || (m->world == 1 && !gathered && !(m->g_dense && m->g_runs == pl.m.nvar)))
+    CU_TRY(m, cudaMemsetAsync(g, 0, (size_t)pl.m.nvar * 8, st));
   if (gathered) {   // shift-indexed objective patterns: one thread per OWNED variable writes g[v] (0 where untouched)
     ExbCall cg{}; cg.x = x; cg.th = m->d_theta; cg.out = g; cg.v0 = m->v_lo; cg.nout = m->v_hi - m->v_lo;
     int rc = launch(m, KN_GGRAD, cg, st); if (rc) return rc;
   }
-  int rc = launch(m, KN_SGRAD, c, st); if (rc) return rc;                        // kerg, ext:669-679
+  if (!slots_ready) { int rc = launch(m, KN_SGRAD, c, st); if (rc) return rc; }  // kerg, ext:669-679
   CU_TRY(m, exb_fx_compress(m->d_gradbuf, m->g_ptr, m->g_slot, m->g_target, m->g_i32, m->g_runs, g, (gathered || m->world > 1) ? 1 : 0, st));   // ext:691-697
   if (m->g_runs > 0) { m->launches++; m->last_launches++; }
   if (comm_on(m)) {
@@ -1069,22 +1121,38 @@ int exb_grad(exb_model* m, const double* x, double* g, void* stream) {
     if (m->comm_mode == EXB_COMM_REPLICATE) return comm_allgather_vars(m, g, st);
   }
   return EXB_OK;
+}
+int exb_grad(exb_model* m, const double* x, double* g, void* stream) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  TimeScope ts_(m, CB_GRAD, stream);
+  return grad_impl(m, x, g, (cudaStream_t)stream, false);
   EXB_END
 }
 
+// cons! = [fill] + value kernel (base rows assigned, augmentation terms into conbuffer) + segmented sum of the augmentation
+// terms + the sharded model's collective
+static int cons_prepare(exb_model* m, double* cvals, cudaStream_t st) {
+  const exb::Plan& pl = m->plan->pl;
+  // a sharded handle owns only part of the base rows: zero the rest so that ranks can be summed (not needed when a
+  // communicator is attached and there is no augmentation: rows are then owned, or all-gathered, never added)
+  if (m->world > 1 && !(comm_on(m) && pl.nconaug == 0)) CU_TRY(m, cudaMemsetAsync(cvals, 0, (size_t)pl.ncon * 8, st));
+  return EXB_OK;
+}
+static int cons_finish(exb_model* m, double* cvals, cudaStream_t st) {
+  CU_TRY(m, exb_fx_compress(m->d_conbuf, m->a_ptr, m->a_slot, m->a_target, m->a_i32, m->a_runs, cvals, 1, st));   // ext:691-697
+  if (m->a_runs > 0) { m->launches++; m->last_launches++; }
+  return comm_finish_rows(m, cvals, st);
+}
 int exb_cons(exb_model* m, const double* x, double* cvals, void* stream) {
   EXB_BEGIN
   EXB_GUARD(m);
   TimeScope ts_(m, CB_CONS, stream);
   cudaStream_t st = (cudaStream_t)stream;
-  const exb::Plan& pl = m->plan->pl;
-  // a sharded handle owns only part of the base rows: zero the rest so that ranks can be summed
-  if (m->world > 1) CU_TRY(m, cudaMemsetAsync(cvals, 0, (size_t)pl.ncon * 8, st));
+  int rc = cons_prepare(m, cvals, st); if (rc) return rc;
   ExbCall c{}; c.x = x; c.th = m->d_theta; c.out = cvals; c.out2 = m->d_conbuf;
-  int rc = launch(m, KN_CONS, c, st); if (rc) return rc;                         // kerf + kerf2, ext:681-688
-  CU_TRY(m, exb_fx_compress(m->d_conbuf, m->a_ptr, m->a_slot, m->a_target, m->a_i32, m->a_runs, cvals, 1, st));   // ext:691-697
-  if (m->a_runs > 0) { m->launches++; m->last_launches++; }
-  return comm_finish_rows(m, cvals, st);
+  rc = launch(m, KN_CONS, c, st); if (rc) return rc;                             // kerf + kerf2, ext:681-688
+  return cons_finish(m, cvals, st);
   EXB_END
 }
 
@@ -1103,6 +1171,48 @@ int exb_hess(exb_model* m, const double* x, const double* y, double obj_weight, 
   TimeScope ts_(m, CB_HESS, stream);
   ExbCall c{}; c.x = x; c.y = y; c.th = m->d_theta; c.sigma = obj_weight; c.out = vals;
   return launch(m, KN_HESS, c, (cudaStream_t)stream);
+  EXB_END
+}
+
+// One sweep for several callbacks at the same x (the composition of src/nlp.jl:1827-1940).  With every bit of `mask` set each
+// data point is evaluated ONCE by exb_eval_g0 (value + first-order + second-order slots; csrc/exb_device.cuh exb_eval_block):
+// c / conbuffer, the objective's block partials, jac, the gradient slots and hess are written by that one launch; what
+// follows are the same small finishing steps the separate callbacks have (fixed-order sum of the partials, owner-computed
+// gradient, segmented sums, the sharded model's collectives).  Any other mask runs the requested callbacks one by one.
+// Outputs are the same words the separate callbacks write (same generated code for every slot).
+int exb_eval(exb_model* m, unsigned mask, const double* x, const double* y, double obj_weight, double* obj_dev, double* g, double* cvals,
+             double* jac, double* hess, void* stream) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  cudaStream_t st = (cudaStream_t)stream;
+  const exb::Plan& pl = m->plan->pl;
+  if ((mask & EXB_EVAL_OBJ) && !obj_dev) return fail(EXB_ERR_ARG, "exb_eval: obj requested but obj_dev is NULL");
+  if (((mask & EXB_EVAL_GRAD) && !g) || ((mask & EXB_EVAL_CONS) && !cvals && pl.ncon > 0) || ((mask & EXB_EVAL_JAC) && !jac && pl.nnzj > 0) ||
+      ((mask & EXB_EVAL_HESS) && !hess && pl.nnzh > 0))
+    return fail(EXB_ERR_ARG, "exb_eval: a requested output is NULL");
+  static const bool no_fused = getenv("EXB_NO_FUSED_EVAL") != nullptr;
+  const bool fused = mask == EXB_EVAL_ALL && !no_fused && m->k[KN_EVAL].fn && m->k[KN_EVAL].nblocks > 0;
+  if (!fused) {
+    int rc = EXB_OK;
+    long long nl = 0, nc = 0;   // the callbacks reset the per-call counters: keep the totals of this call
+    auto acc = [&]() { nl += m->last_launches; nc += m->last_collectives; };
+    if (!rc && (mask & EXB_EVAL_OBJ)) { rc = exb_obj_async(m, x, obj_dev, stream); acc(); }
+    if (!rc && (mask & EXB_EVAL_GRAD)) { rc = exb_grad(m, x, g, stream); acc(); }
+    if (!rc && (mask & EXB_EVAL_CONS)) { rc = exb_cons(m, x, cvals, stream); acc(); }
+    if (!rc && (mask & EXB_EVAL_JAC)) { rc = exb_jac(m, x, jac, stream); acc(); }
+    if (!rc && (mask & EXB_EVAL_HESS)) { rc = exb_hess(m, x, y, obj_weight, hess, stream); acc(); }
+    m->last_launches = nl; m->last_collectives = nc;
+    return rc;
+  }
+  int rc = cons_prepare(m, cvals, st); if (rc) return rc;
+  ExbCall c{}; c.x = x; c.y = y; c.th = m->d_theta; c.sigma = obj_weight; c.out = hess;
+  c.e_jac = jac; c.e_c = cvals; c.e_gb = m->d_gradbuf; c.e_cb = m->d_conbuf; c.e_obj = m->d_objpart_e;
+  rc = launch(m, KN_EVAL, c, st); if (rc) return rc;
+  CU_TRY(m, exb_fx_sum(m->d_objpart_e, m->n_objpart_e, obj_dev, st));
+  m->launches++; m->last_launches++;
+  if (comm_on(m)) { rc = comm_allreduce(m, obj_dev, 1, st); if (rc) return rc; }
+  rc = grad_impl(m, x, g, st, true); if (rc) return rc;
+  return cons_finish(m, cvals, st);
   EXB_END
 }
 
@@ -1161,20 +1271,23 @@ int build_sorted(exb_model* m, const long long* keys, long long n, long long max
 
 int structure_raw(exb_model* m, int kn, void* rows, void* cols, cudaStream_t st);   // defined below
 
-int ensure_buffers(exb_model* m) {
+int ensure_buffers(exb_model* m, int passes = 3) {
   const exb::Plan& pl = m->plan->pl;
-  if (!m->d_jacbuf) { int rc = dmalloc(m, (void**)&m->d_jacbuf, (size_t)pl.nnzj * 8); if (rc) return rc; }
-  if (!m->d_hessbuf) { int rc = dmalloc(m, (void**)&m->d_hessbuf, (size_t)pl.nnzh * 8); if (rc) return rc; }
+  if ((passes & 1) && !m->d_jacbuf) { int rc = dmalloc(m, (void**)&m->d_jacbuf, (size_t)pl.nnzj * 8); if (rc) return rc; }
+  if ((passes & 2) && !m->d_hessbuf) { int rc = dmalloc(m, (void**)&m->d_hessbuf, (size_t)pl.nnzh * 8); if (rc) return rc; }
   return EXB_OK;
 }
 
-// which: 1 = products (row- and column-sorted), 2 = compressed (sorted by (col, row))
-int ensure_sorted(exb_model* m, int which) {
-  if (m->world != 1) return fail(EXB_ERR_ARG, "matrix-free products / compressed COO are not available on sharded handles");
-  if ((which == 1 && m->prod_ready) || (which == 2 && m->cmp_ready)) return EXB_OK;
+// which: 1 = products (row- and column-sorted), 2 = compressed (sorted by (col, row)); passes: bit 0 Jacobian, bit 1 Hessian
+int ensure_sorted(exb_model* m, int which, int passes = 3) {
+  if (m->world != 1) return fail(EXB_ERR_ARG, "the sorted-structure forms (EXB_FLAG_SORTED_PRODUCTS products, duplicate-free COO of models that are not "
+                                              "shift-indexed) are not available on sharded handles");
+  if (which == 1) { if (m->prod_ready) return EXB_OK; passes = 3; }
+  if (which == 2) { if (m->cmpj_ready) passes &= ~1; if (m->cmp_ready) passes &= ~2; if (!passes) return EXB_OK; }
   const exb::Plan& pl = m->plan->pl;
-  int rc = ensure_buffers(m); if (rc) return rc;
+  int rc = ensure_buffers(m, passes); if (rc) return rc;
   for (int pass = 0; pass < 2; pass++) {   // 0: Jacobian, 1: Hessian
+    if (!(passes & (1 << pass))) continue;
     const long long n = pass == 0 ? pl.nnzj : pl.nnzh;
     const long long nrow = pass == 0 ? pl.ncon : pl.m.nvar, ncol = pl.m.nvar;
     if (n == 0) continue;
@@ -1200,7 +1313,8 @@ int ensure_sorted(exb_model* m, int which) {
     cudaFree(rows); cudaFree(cols); cudaFree(keys);
     if (rc) return rc;
   }
-  if (which == 1) m->prod_ready = true; else m->cmp_ready = true;
+  if (which == 1) m->prod_ready = true;
+  else { if (passes & 1) m->cmpj_ready = true; if (passes & 2) m->cmp_ready = true; }
   return EXB_OK;
 }
 
@@ -1224,7 +1338,7 @@ int exb_jprod(exb_model* m, const double* x, const double* v, double* Jv, void* 
   cudaStream_t st = (cudaStream_t)stream;
   const exb::Plan& pl = m->plan->pl;
   if (!m->sorted_products) {
-    CU_TRY(m, cudaMemsetAsync(Jv, 0, (size_t)pl.ncon * 8, st));
+    if (!(comm_on(m) && pl.nconaug == 0)) CU_TRY(m, cudaMemsetAsync(Jv, 0, (size_t)pl.ncon * 8, st));
     if (pl.nconaug > 0) CU_TRY(m, cudaMemsetAsync(m->d_conbuf, 0, (size_t)pl.nconaug * 8, st));
     ExbCall c{}; c.x = x; c.v = v; c.th = m->d_theta; c.out = Jv; c.out2 = m->d_conbuf;
     int rc = launch(m, KN_JPROD, c, st); if (rc) return rc;
@@ -1276,33 +1390,83 @@ int exb_hprod(exb_model* m, const double* x, const double* y, const double* v, d
   EXB_END
 }
 
+// Duplicate-free COO.  Hessian of a shift-indexed model (Plan::tile_ok): ONE generated launch (exb_hessc_g0) writes the unique
+// entries with their duplicates summed -- no raw values, no sorted list, and the structure / count are closed forms of the
+// pattern shifts; available on sharded handles (a rank writes the contiguous range of entries of the columns it owns).
+// Everything else: the reference's scheme -- raw COO values, then a segmented sum through the (col, row)-sorted list.
+static long long tile_unique(const exb_model* m) { long long n = 0; for (long long v : m->plan->pl.h_len) n += v; return n; }
+static long long tile_before(const ExbTile& t, long long c) {
+  long long p = 0;
+  for (int r = 0; r < t.D; r++) { long long v = c - t.lo[r]; v = v < 0 ? 0 : v; p += v > t.len[r] ? t.len[r] : v; }
+  return p;
+}
 int exb_compressed_dims(exb_model* m, int64_t* nj, int64_t* nh) {
   EXB_BEGIN
   EXB_GUARD(m);
-  int rc = ensure_sorted(m, 2); if (rc) return rc;
-  if (nj) *nj = m->jcmp.runs;
-  if (nh) *nh = m->hcmp.runs;
+  if (nh) {
+    if (m->hess_tile) *nh = tile_unique(m);
+    else { int rc = ensure_sorted(m, 2, 2); if (rc) return rc; *nh = m->hcmp.runs; }
+  }
+  if (nj) { int rc = ensure_sorted(m, 2, 1); if (rc) return rc; *nj = m->jcmp.runs; }
   return EXB_OK;
   EXB_END
 }
-static int cmp_structure(exb_model* m, const exb_model::Sorted& S, int64_t* rows, int64_t* cols, void* stream) {
+// out[0..1] = 0-based half-open range of the duplicate-free Hessian values a (sharded) handle writes; out[2] = 1 when the
+// Hessian comes straight from the column-tile kernel (one launch, no sorted list)
+int exb_compressed_shard(exb_model* m, int64_t* out3) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  if (!out3) return fail(EXB_ERR_ARG, "null argument");
+  if (m->hess_tile) {
+    const ExbTile& t = m->k[KN_HESSC].tile;
+    out3[0] = tile_before(t, t.c_lo); out3[1] = tile_before(t, t.c_hi); out3[2] = 1;
+    return EXB_OK;
+  }
+  int rc = ensure_sorted(m, 2, 2); if (rc) return rc;
+  out3[0] = 0; out3[1] = m->hcmp.runs; out3[2] = 0;
+  return EXB_OK;
+  EXB_END
+}
+static int cmp_structure(exb_model* m, const exb_model::Sorted& S, void* rows, void* cols, int idx32, void* stream) {
+  if (S.runs == 0) return EXB_OK;
   if (!rows || !cols) return fail(EXB_ERR_ARG, "null rows / cols");
-  if (S.runs > 0) {
+  if (idx32) {
+    CU_TRY(m, exb_fx_narrow(S.urows, (int*)rows, S.runs, (cudaStream_t)stream));
+    CU_TRY(m, exb_fx_narrow(S.ucols, (int*)cols, S.runs, (cudaStream_t)stream));
+  } else {
     CU_TRY(m, cudaMemcpyAsync(rows, S.urows, (size_t)S.runs * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     CU_TRY(m, cudaMemcpyAsync(cols, S.ucols, (size_t)S.runs * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   }
   return EXB_OK;
 }
+static int hess_structure_cmp(exb_model* m, void* rows, void* cols, int idx32, void* stream) {
+  if (m->hess_tile) {   // closed form of the pattern shifts; the whole structure, also on a sharded handle
+    if (!rows || !cols) return fail(EXB_ERR_ARG, "null rows / cols");
+    ExbTile t = m->k[KN_HESSC].tile;
+    t.c_lo = 1; t.c_hi = m->plan->pl.m.nvar + 1;
+    CU_TRY(m, exb_fx_tile_structure(&t, rows, cols, idx32, (cudaStream_t)stream));
+    m->launches++; m->last_launches++;
+    return EXB_OK;
+  }
+  int rc = ensure_sorted(m, 2, 2); if (rc) return rc;
+  return cmp_structure(m, m->hcmp, rows, cols, idx32, stream);
+}
 int exb_jac_structure_compressed64(exb_model* m, int64_t* rows, int64_t* cols, void* stream) {
-  EXB_BEGIN EXB_GUARD(m); int rc = ensure_sorted(m, 2); if (rc) return rc; return cmp_structure(m, m->jcmp, rows, cols, stream); EXB_END
+  EXB_BEGIN EXB_GUARD(m); int rc = ensure_sorted(m, 2, 1); if (rc) return rc; return cmp_structure(m, m->jcmp, rows, cols, 0, stream); EXB_END
+}
+int exb_jac_structure_compressed32(exb_model* m, int32_t* rows, int32_t* cols, void* stream) {
+  EXB_BEGIN EXB_GUARD(m); int rc = ensure_sorted(m, 2, 1); if (rc) return rc; return cmp_structure(m, m->jcmp, rows, cols, 1, stream); EXB_END
 }
 int exb_hess_structure_compressed64(exb_model* m, int64_t* rows, int64_t* cols, void* stream) {
-  EXB_BEGIN EXB_GUARD(m); int rc = ensure_sorted(m, 2); if (rc) return rc; return cmp_structure(m, m->hcmp, rows, cols, stream); EXB_END
+  EXB_BEGIN EXB_GUARD(m); return hess_structure_cmp(m, rows, cols, 0, stream); EXB_END
+}
+int exb_hess_structure_compressed32(exb_model* m, int32_t* rows, int32_t* cols, void* stream) {
+  EXB_BEGIN EXB_GUARD(m); return hess_structure_cmp(m, rows, cols, 1, stream); EXB_END
 }
 int exb_jac_compressed(exb_model* m, const double* x, double* vals, void* stream) {
   EXB_BEGIN
   EXB_GUARD(m);
-  int rc = ensure_sorted(m, 2); if (rc) return rc;
+  int rc = ensure_sorted(m, 2, 1); if (rc) return rc;
   rc = exb_jac(m, x, m->d_jacbuf, stream); if (rc) return rc;
   const exb_model::Sorted& S = m->jcmp;
   CU_TRY(m, exb_fx_compress(m->d_jacbuf, S.ptr, S.slot, S.target, S.i32, S.runs, vals, 0, (cudaStream_t)stream));   // ker_compress!, ext:1295-1303
@@ -1313,7 +1477,12 @@ int exb_jac_compressed(exb_model* m, const double* x, double* vals, void* stream
 int exb_hess_compressed(exb_model* m, const double* x, const double* y, double obj_weight, double* vals, void* stream) {
   EXB_BEGIN
   EXB_GUARD(m);
-  int rc = ensure_sorted(m, 2); if (rc) return rc;
+  if (m->hess_tile) {
+    TimeScope ts_(m, CB_HESS, stream);
+    ExbCall c{}; c.x = x; c.y = y; c.th = m->d_theta; c.sigma = obj_weight; c.out = vals;
+    return launch(m, KN_HESSC, c, (cudaStream_t)stream);
+  }
+  int rc = ensure_sorted(m, 2, 2); if (rc) return rc;
   rc = exb_hess(m, x, y, obj_weight, m->d_hessbuf, stream); if (rc) return rc;
   const exb_model::Sorted& S = m->hcmp;
   CU_TRY(m, exb_fx_compress(m->d_hessbuf, S.ptr, S.slot, S.target, S.i32, S.runs, vals, 0, (cudaStream_t)stream));
@@ -1508,6 +1677,22 @@ int exb_host_hess(exb_model* m, const double* x, const double* y, double obj_wei
   const double* yy = y;
   { EXB_BEGIN EXB_GUARD(m); bool done = false; int prc = host_coo_pipelined(m, KN_HESS, x, y, obj_weight, out, &done); if (prc || done) return prc; EXB_END }
   EXB_HOST_VEC(pl.nnzh, slices(m, 2), exb_hess(m, m->dx, y ? m->dy : nullptr, obj_weight, m->dout, m->hstream))
+}
+// duplicate-free forms with host buffers: the D2H copy carries the unique entries only (LV: 2N - 1 instead of 9N - 15 doubles)
+int exb_host_jac_compressed(exb_model* m, const double* x, double* out) {
+  const double* yy = nullptr;
+  long long nj = 0;
+  { EXB_BEGIN EXB_GUARD(m); int rc0 = ensure_sorted(m, 2, 1); if (rc0) return rc0; nj = m->jcmp.runs; EXB_END }
+  EXB_HOST_VEC(nj, whole(nj), exb_jac_compressed(m, m->dx, m->dout, m->hstream))
+}
+int exb_host_hess_compressed(exb_model* m, const double* x, const double* y, double obj_weight, double* out) {
+  const double* yy = y;
+  int64_t sh[3] = {0, 0, 0};
+  { int rc0 = exb_compressed_shard(m, sh); if (rc0) return rc0; }
+  long long nh = 0;
+  { int64_t t = 0; int rc0 = exb_compressed_dims(m, nullptr, &t); if (rc0) return rc0; nh = t; }
+  std::vector<std::pair<long long, long long>> mine = {{(long long)sh[0], (long long)sh[1]}};
+  EXB_HOST_VEC(nh, mine, exb_hess_compressed(m, m->dx, y ? m->dy : nullptr, obj_weight, m->dout, m->hstream))
 }
 static int host_structure(exb_model* m, int kn, long long n, int64_t* rows, int64_t* cols) {
   int rc = host_stream(m); if (rc) return rc;

@@ -110,6 +110,9 @@ int exb_plan_npatterns(const exb_plan* p);
 int exb_plan_pattern(const exb_plan* p, int k, int64_t* out9);
 /* which = 1: comp1 (Compressor of the gradient/Jacobian pass), 2: comp2 (Hessian) */
 int exb_plan_comp(const exb_plan* p, int k, int which, int64_t* out);
+/* out[0] = 1 if the duplicate-free Hessian is emitted by the fused column-tile kernel (shift-indexed model), out[1] = its
+ * number of unique entries (closed form), out[2] = distinct row - column distances, out[3] = halo points per tile */
+int exb_plan_tile(const exb_plan* p, int64_t* out4);
 /* generated CUDA C++ of the model's kernel module; *len excludes the NUL */
 int exb_plan_source(const exb_plan* p, const char** src, size_t* len);
 /* path of the compiled module for this plan (hash of source + flags) */
@@ -150,6 +153,21 @@ int exb_hess_structure32(exb_model* m, int32_t* rows, int32_t* cols, void* strea
 int exb_hess(exb_model* m, const double* x, const double* y, double obj_weight, double* vals,
              void* stream);
 
+/* ---- several callbacks from ONE sweep (the composition of src/nlp.jl:1827-1940: a solver asks for obj, grad!, cons!, jac_coord!
+ * and hess_coord! at the same x, and the reference walks every pattern's tree once per callback).  mask = EXB_EVAL_ALL: every
+ * data point is evaluated once by one generated launch (exb_eval_g0) that writes c, jac, hess, the gradient slots and the
+ * objective's partial sums; the small finishing steps of the separate callbacks follow (fixed-order sum, owner-computed
+ * gradient, segmented sums, collectives of a sharded model).  Any other mask: the requested callbacks one by one.  Outputs not
+ * requested may be NULL; *obj_dev is a DEVICE double (no synchronisation); y == NULL is the objective-only Hessian form. */
+#define EXB_EVAL_OBJ 1u
+#define EXB_EVAL_GRAD 2u
+#define EXB_EVAL_CONS 4u
+#define EXB_EVAL_JAC 8u
+#define EXB_EVAL_HESS 16u
+#define EXB_EVAL_ALL 31u
+int exb_eval(exb_model* m, unsigned mask, const double* x, const double* y, double obj_weight, double* obj_dev, double* g, double* c,
+             double* jac, double* hess, void* stream);
+
 /* ---- matrix-free products: jprod_nln! / jtprod_nln! / hprod! (src/nlp.jl:1882-1978; device form
  * ext/ExaModelsKernelAbstractions.jl:353-511, `ExaModel(c; prod = true)`).  Default: fused into the derivative sweep --
  * every point multiplies its first- / second-order slots (still in registers) with v; jprod assigns / segment-sums rows
@@ -163,11 +181,25 @@ int exb_hprod(exb_model* m, const double* x, const double* y, const double* v, d
               void* stream);                                                                 /* Hv[nvar]  */
 
 /* ---- duplicate-free COO: the CompressedNLPModel role (src/utils.jl:425-579 | ext:1290-1319) ----
- * Unique (row, col) coordinates in the reference's order (sorted by (col, row)); values of duplicates are
- * summed in ascending slot order.  Built on first use.  Not available on sharded handles. */
-int exb_compressed_dims(exb_model* m, int64_t* nnzj_unique, int64_t* nnzh_unique);
+ * Unique (row, col) coordinates in the reference's order (sorted by (col, row)); values of duplicates are summed in
+ * ascending slot order (the order `_compress!`, utils.jl:564-571, meets them in the stably sorted list).
+ *   Hessian of a SHIFT-INDEXED model (every variable of every pattern with second-order slots is `range value + const`: LV,
+ *   any banded / stencil model): FUSED -- one generated launch (exb_hessc_g0, csrc/exb_device.cuh exb_tile_body) evaluates the
+ *   points around a tile of columns, sums the slots that share a coordinate in shared memory / registers and writes each
+ *   unique entry once (LV: 2N - 1 doubles instead of 9N - 15, and no second pass).  Structure and count are closed forms of
+ *   the pattern shifts: no sort, no nnzh-sized buffer.  Works on sharded handles: a rank owns a contiguous range of columns
+ *   (exb_owned), hence a contiguous range of the unique entries (exb_compressed_shard); duplicates that straddle two shards
+ *   need no exchange because the owner evaluates both contributing points (x, y are replicated).
+ *   Anything else (Jacobian; models indexed through iterator data or with fixed-index variables): the reference's scheme --
+ *   raw COO values into a buffer owned by the handle, then a segmented sum through the pre-sorted list, built on first use;
+ *   not available on sharded handles. */
+int exb_compressed_dims(exb_model* m, int64_t* nnzj_unique, int64_t* nnzh_unique);   /* either pointer may be NULL */
+/* out[0..1] = 0-based half-open range of the duplicate-free Hessian values this handle writes, out[2] = 1 if fused */
+int exb_compressed_shard(exb_model* m, int64_t* out3);
 int exb_jac_structure_compressed64(exb_model* m, int64_t* rows, int64_t* cols, void* stream);
+int exb_jac_structure_compressed32(exb_model* m, int32_t* rows, int32_t* cols, void* stream);
 int exb_hess_structure_compressed64(exb_model* m, int64_t* rows, int64_t* cols, void* stream);
+int exb_hess_structure_compressed32(exb_model* m, int32_t* rows, int32_t* cols, void* stream);
 int exb_jac_compressed(exb_model* m, const double* x, double* vals, void* stream);
 int exb_hess_compressed(exb_model* m, const double* x, const double* y, double obj_weight, double* vals,
                         void* stream);
@@ -180,6 +212,9 @@ int exb_host_grad(exb_model* m, const double* x, double* g);
 int exb_host_cons(exb_model* m, const double* x, double* c);
 int exb_host_jac(exb_model* m, const double* x, double* vals);
 int exb_host_hess(exb_model* m, const double* x, const double* y, double obj_weight, double* vals);
+/* duplicate-free forms: the D2H copy carries the unique entries only */
+int exb_host_jac_compressed(exb_model* m, const double* x, double* vals);
+int exb_host_hess_compressed(exb_model* m, const double* x, const double* y, double obj_weight, double* vals);
 int exb_host_jac_structure64(exb_model* m, int64_t* rows, int64_t* cols);
 int exb_host_hess_structure64(exb_model* m, int64_t* rows, int64_t* cols);
 

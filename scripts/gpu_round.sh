@@ -18,7 +18,7 @@ case ",$sections," in *,configs,*)
 for s in ${sections//,/ }; do
   case $s in ncu:*)
     for cb in $(echo ${s#ncu:} | tr '+' ' '); do
-      timeout 300 ncu --set full --clock-control none --import-source on -k regex:"exb_(hess|ggrad|sgrad|cons|jac|obj)_g0" -s 10 -c 1 -f -o gpurun_out/${tag}_prof_$cb python scripts/prof_one.py lv $cb > gpurun_out/${tag}_ncu_$cb.log 2>&1
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:"exb_(hess|hessc|eval|ggrad|sgrad|cons|jac|obj)_g0" -s 10 -c 1 -f -o gpurun_out/${tag}_prof_$cb python scripts/prof_one.py lv $cb > gpurun_out/${tag}_ncu_$cb.log 2>&1
     done;; esac
 done
 ls -la gpurun_out | tail -12
