@@ -42,7 +42,7 @@ exb_jprod exb_jtprod exb_hprod exb_compressed_dims exb_jac_structure_compressed6
 exb_jac_compressed exb_hess_compressed exb_set_timing exb_timings exb_kernel_choice exb_host_bytes
 exb_comm_unique_id exb_comm_init exb_comm_attach exb_comm_destroy exb_comm_set_mode exb_comm_gather_coo exb_owned
 exb_comm_stats exb_compressed_shard exb_jac_structure_compressed32 exb_hess_structure_compressed32
-exb_host_jac_compressed exb_host_hess_compressed exb_plan_tile exb_eval""".split()
+exb_host_jac_compressed exb_host_hess_compressed exb_plan_tile exb_eval exb_plan_create_data""".split()
 
 
 class ExbError(RuntimeError):
@@ -106,7 +106,8 @@ class Plan:
     def __init__(self, core):
         self.ir, self.bufs = core.to_ir()
         self.h = C.c_void_p()
-        _check(lib().exb_plan_create(self.ir, C.c_size_t(len(self.ir)), None, C.byref(self.h)))
+        arr = (C.c_void_p * max(1, len(self.bufs)))(*[b.ctypes.data for b in self.bufs])
+        _check(lib().exb_plan_create_data(self.ir, C.c_size_t(len(self.ir)), arr, len(self.bufs), None, C.byref(self.h)))
         d = np.zeros(8, dtype=np.int64)
         _check(lib().exb_plan_dims(self.h, _np_ptr(d)))
         (self.nvar, self.ncon, self.nnzj, self.nnzh, self.nobj, self.nnzg, self.nconaug,

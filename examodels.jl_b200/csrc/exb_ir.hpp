@@ -41,6 +41,10 @@ struct PatternIR {
   std::vector<int> idx_roots; std::vector<i64> dims;
   std::vector<IRNode> nodes; int root = -1;
   std::vector<i64> comp1_given, comp2_given;
+  // data hints (not part of the IR; filled from the iterator data by detect_iota when the host passes it): integer field f of an
+  // AoS iterator holds iota0[f] + k at point k (k = 0, 1, ...) -- the `i` column of an array of NamedTuples built from 1:n
+  std::vector<char> iota; std::vector<i64> iota0;
+  bool has_iota() const { for (char c : iota) if (c) return true; return false; }
 };
 
 struct ModelIR {
@@ -57,6 +61,7 @@ inline bool parse_ir(const void* ir, size_t bytes, ModelIR& m, std::string& err)
   if (rd() != 0x0031425845LL) { err = "bad IR magic"; return false; }
   if (rd() != 1) { err = "unsupported IR version"; return false; }
   m.nvar = rd(); m.npar = rd();
+  if (m.nvar < 0 || m.npar < 0) { err = "negative nvar / npar"; return false; }
   i64 npat = rd(); m.ndatabufs = (int)rd();
   if (npat < 0 || npat > (1 << 20)) { err = "bad pattern count"; return false; }
   m.pats.resize((size_t)npat);
@@ -64,6 +69,7 @@ inline bool parse_ir(const void* ir, size_t bytes, ModelIR& m, std::string& err)
     PatternIR& p = m.pats[pi];
     p.kind = (int)rd(); p.nitr = rd(); p.itr_kind = (int)rd(); p.range_start = rd();
     p.databuf = (int)rd(); p.stride = rd();
+    if (p.itr_kind == ITR_AOS) p.range_start = 0;   // point numbers of an AoS iterator start at 0 (see affine_index)
     i64 nf = rd();
     if (!ok || nf < 0 || nf > 4096) { err = "bad field count"; return false; }
     p.fields.resize((size_t)nf);
@@ -102,8 +108,42 @@ inline bool parse_ir(const void* ir, size_t bytes, ModelIR& m, std::string& err)
     }
     if (p.itr_kind == ITR_AOS && (p.databuf < 0 || p.databuf >= m.ndatabufs)) { err = "bad data buffer index"; return false; }
     if (p.nitr < 0) { err = "negative iterator length"; return false; }
+    if (p.itr_kind != ITR_RANGE && p.itr_kind != ITR_AOS) { err = "unknown iterator kind"; return false; }
+    for (auto& f : p.fields) {
+      if (f.type < FT_I64 || f.type > FT_F32) { err = "unknown field type"; return false; }
+      const i64 sz = (f.type == FT_I64 || f.type == FT_F64) ? 8 : 4;
+      if (p.itr_kind == ITR_AOS && (f.off < 0 || f.off + sz > p.stride)) { err = "field offset outside the iterator element"; return false; }
+    }
+    for (auto& n : p.nodes) {
+      if (n.tag == T_DATA_SELF && p.itr_kind != ITR_RANGE) { err = "DATA_SELF on a non-range iterator"; return false; }
+      if (n.tag == T_DATA_FIELD && p.itr_kind != ITR_AOS) { err = "DATA_FIELD on a range iterator"; return false; }
+    }
   }
   return true;
+}
+
+// An integer field whose values are v0, v0 + 1, v0 + 2, ... makes an AoS pattern as good as a range pattern: indices built
+// from it are affine in the point number, so index relations, x windows, owner-computed gradients and the duplicate-free
+// Hessian are decided at build time, and the column is never loaded (or even uploaded).
+inline void detect_iota(ModelIR& m, const void* const* host_data, int n_data) {
+  for (auto& p : m.pats) {
+    p.iota.assign(p.fields.size(), 0); p.iota0.assign(p.fields.size(), 0);
+    if (p.itr_kind != ITR_AOS || !host_data || p.databuf < 0 || p.databuf >= n_data || !host_data[p.databuf] || p.nitr < 1) continue;
+    const unsigned char* base = (const unsigned char*)host_data[p.databuf];
+    for (size_t f = 0; f < p.fields.size(); f++) {
+      const Field& fd = p.fields[f];
+      if (fd.type != FT_I64 && fd.type != FT_I32) continue;
+      auto at = [&](i64 k) -> i64 {
+        const unsigned char* q = base + (size_t)k * (size_t)p.stride + fd.off;
+        if (fd.type == FT_I64) { int64_t t; std::memcpy(&t, q, 8); return t; }
+        int32_t t; std::memcpy(&t, q, 4); return t;
+      };
+      const i64 v0 = at(0);
+      bool ok = v0 > -(1LL << 40) && v0 < (1LL << 40);
+      for (i64 k = 1; k < p.nitr && ok; k++) ok = at(k) == v0 + k;
+      if (ok) { p.iota[f] = 1; p.iota0[f] = v0; }
+    }
+  }
 }
 
 }  // namespace exb

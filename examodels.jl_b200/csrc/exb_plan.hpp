@@ -71,6 +71,9 @@ struct PatternPlan {
   std::vector<i64> t2_cb, t2_d;
   std::vector<int> t2_r;
   i64 t_cbmin = 0, t_cbmax = 0;
+  // same for the gradient (exb_tile_body in gradient mode): first-order slot j of an objective pattern lands in variable t + shift1[j]
+  bool tgrad = false;
+  i64 g_cbmin = 0, g_cbmax = 0;
 };
 
 struct Plan {
@@ -80,13 +83,14 @@ struct Plan {
   std::string source;  // generated module (without the device header)
   std::string error;
   // pattern lists per kernel (indices into pats), fixed at generation time
-  std::vector<int> k_hess, k_jac, k_sgrad, k_ggrad, k_cons, k_obj, k_aug, k_eval;
+  std::vector<int> k_hess, k_jac, k_sgrad, k_ggrad, k_cons, k_obj, k_aug, k_eval, k_tgrad;
   bool hess_windowed = false;  // every Hessian pattern has an x window: the persistent kernel exb_hessp_g0 is generated too
   // duplicate-free Hessian emitted directly (exb_hessc_g0): possible when every pattern with second-order slots is tile_ok
   bool tile_ok = false;
   std::vector<i64> hd;         // distinct row - column distances of the model's Hessian entries, ascending
   std::vector<i64> h_lo, h_len;   // per distance: the ONE interval of (1-based) columns in which the entry exists
-  int tile_halo = 0, tile_ppt = 2;   // tile_ppt: columns per thread (EXB_TUNE_TILE_PPT)
+  int tile_halo = 0, tile_ppt = 3;   // tile_ppt: columns per thread (EXB_TUNE_TILE_PPT; measured on LV: 2 -> 0.147, 3 -> 0.142, 4 -> 0.150 ms)
+  int tgrad_halo = 0, tgrad_ppt = 4;   // gradient mode of the tile kernel (exb_gradt_g0)
   bool idx32 = false;          // every index (variables, points, slots) fits 31 bits: address arithmetic in 32 bits
   int block = 128, minb = 16;  // launch shape of the generated kernels (tuning knobs: EXB_TUNE_BLOCK / EXB_TUNE_MINB)
 };
@@ -144,7 +148,8 @@ inline bool ir_equal(const PatternIR& p, int a, int b) {   // Julia `===` on imm
   return false;
 }
 
-// Integer index expression as an affine function of the iterator value t (DATA_SELF): value = coef * t + cst.
+// Integer index expression as an affine function of t: value = coef * t + cst, where t is the iterator VALUE of a range pattern
+// (DATA_SELF) or the POINT NUMBER of an AoS pattern with iota columns (range_start is 0 there, so the two coincide in `pa.start + kg`).
 // Only the integer `+ - *` that index expressions are made of (nlp.jl:900-926,2012-2015); anything else -> false.
 inline bool affine_index(const PatternIR& p, int n, i64& coef, i64& cst) {
   const IRNode& q = p.nodes[(size_t)n];
@@ -152,6 +157,9 @@ inline bool affine_index(const PatternIR& p, int n, i64& coef, i64& cst) {
   switch (q.tag) {
     case T_CONST_I: case T_VAL: coef = 0; cst = q.payload; return small(cst);
     case T_DATA_SELF: coef = 1; cst = 0; return true;
+    case T_DATA_FIELD:   // an iota column (detect_iota): value = point number + iota0, like a range whose start is iota0
+      if ((size_t)q.a < p.iota.size() && p.iota[(size_t)q.a]) { coef = 1; cst = p.iota0[(size_t)q.a]; return true; }
+      return false;
     case T_OP1: {
       i64 a, b;
       if (!affine_index(p, (int)q.a, a, b)) return false;
@@ -174,10 +182,11 @@ inline bool affine_index(const PatternIR& p, int n, i64& coef, i64& cst) {
   return false;
 }
 // Can two variable index expressions be decided equal / unequal for EVERY data point?  1 always equal, 0 never, -1 unknown.
+inline bool shiftable(const PatternIR& p) { return p.itr_kind == ITR_RANGE || p.has_iota(); }
 inline int index_relation(const PatternIR& p, int a, int b) {
   if (ir_equal(p, a, b)) return 1;
   i64 c1, k1, c2, k2;
-  if (p.itr_kind == ITR_RANGE && affine_index(p, a, c1, k1) && affine_index(p, b, c2, k2)) {
+  if (shiftable(p) && affine_index(p, a, c1, k1) && affine_index(p, b, c2, k2)) {
     if (c1 == c2) return k1 == k2 ? 1 : 0;
     // (c1 - c2) t = k2 - k1 has at most one integer solution: only decidable when it has none
     const i64 dc = c1 - c2, dk = k2 - k1;
@@ -297,7 +306,9 @@ struct Gen {
       case T_CONST_F: { double v; std::memcpy(&v, &q.payload, 8); r.lit = true; r.x = K(v); r.rs = dlit(v); } break;
       case T_DATA_SELF: r.rs = B.tmp("long long", "pa.start + kg"); break;
       case T_DATA_FIELD:
-        if (r.is_int) r.rs = B.tmp("long long", "exb_ld_i(pa, " + std::to_string(q.a) + ", EXB_IX(kg))");
+        if (r.is_int && (size_t)q.a < p.ir.iota.size() && p.ir.iota[(size_t)q.a])   // iota column: never loaded
+          r.rs = B.tmp("long long", "kg + " + ilit(p.ir.iota0[(size_t)q.a]));
+        else if (r.is_int) r.rs = B.tmp("long long", "exb_ld_i(pa, " + std::to_string(q.a) + ", EXB_IX(kg))");
         else r.rs = B.tmp("double", "exb_ld_f(pa, " + std::to_string(q.a) + ", EXB_IX(kg))");
         break;
       case T_PAR: { NV& ix = real((int)q.a); r.rs = B.tmp("double", "__ldg(th + EXB_IX(" + ix.rs + " - 1))"); } break;  // graph.jl:310-311
@@ -672,7 +683,7 @@ inline int ppt_for(int weight, int ns) {
 
 // x window of a pattern (see PatternPlan::win)
 inline void compute_window(PatternPlan& p) {
-  p.win = p.ir.itr_kind == ITR_RANGE && p.ir.kind != KIND_AUG && p.o2step > 0;
+  p.win = shiftable(p.ir) && p.ir.kind != KIND_AUG && p.o2step > 0;
   bool first = true;
   for (size_t q = 0; q < p.ir.nodes.size() && p.win; q++) {
     if (p.ir.nodes[q].tag != T_VAR) continue;
@@ -692,7 +703,7 @@ inline void compute_xrange(PatternPlan& p) {
     if (p.ir.nodes[q].tag != T_VAR) continue;
     i64 cf, ct;
     if (!affine_index(p.ir, (int)p.ir.nodes[q].a, cf, ct)) { p.xr_ok = false; break; }
-    if (cf == 1 && p.ir.itr_kind == ITR_RANGE) {
+    if (cf == 1 && shiftable(p.ir)) {
       if (!p.xr_shift || ct < p.rlo) p.rlo = ct;
       if (!p.xr_shift || ct > p.rhi) p.rhi = ct;
       p.xr_shift = true;
@@ -706,7 +717,7 @@ inline void compute_xrange(PatternPlan& p) {
 
 // shift analysis for the column-tile kernels (see PatternPlan::tile_ok)
 inline void compute_tile(PatternPlan& p) {
-  p.tile_ok = p.ir.itr_kind == ITR_RANGE && p.ir.kind != KIND_AUG;
+  p.tile_ok = shiftable(p.ir) && p.ir.kind != KIND_AUG;
   p.t2_cb.clear(); p.t2_d.clear(); p.t2_r.clear();
   if (p.o2step == 0) return;
   bool first = true;
@@ -775,7 +786,7 @@ inline std::string gen_pattern(PatternPlan& p, int index, bool windowed, const s
     // re-evaluated o1step times keep the slot + compress path.
     p.gather1 = false; p.shift1.clear();
     static const int gmax = getenv("EXB_TUNE_GATHER_W") ? atoi(getenv("EXB_TUNE_GATHER_W")) : 300;
-    if (p.ir.kind == KIND_OBJ && p.ir.itr_kind == ITR_RANGE && ns1 > 0 && body_weight(B) * ns1 <= gmax) {
+    if (p.ir.kind == KIND_OBJ && shiftable(p.ir) && ns1 > 0 && body_weight(B) * ns1 <= gmax) {
       bool ok = true;
       for (int j = 0; j < ns1 && ok; j++) {
         i64 cf, ct;
@@ -783,6 +794,38 @@ inline std::string gen_pattern(PatternPlan& p, int index, bool windowed, const s
         p.shift1.push_back(ct);
       }
       p.gather1 = ok;
+    }
+    {  // tile gradient: every first-order slot of an objective pattern addresses x[t + const] (any body weight)
+      p.tgrad = false;
+      if (p.ir.kind == KIND_OBJ && shiftable(p.ir) && ns1 > 0 && getenv("EXB_NO_TGRAD") == nullptr) {
+        bool ok = true; std::vector<i64> sh;
+        for (int j = 0; j < ns1 && ok; j++) {
+          i64 cf, ct;
+          ok = affine_index(p.ir, (int)p.ir.nodes[(size_t)p.leaf1[(size_t)j]].a, cf, ct) && cf == 1;
+          sh.push_back(ct);
+        }
+        if (ok) {
+          p.g_cbmin = *std::min_element(sh.begin(), sh.end()); p.g_cbmax = *std::max_element(sh.begin(), sh.end());
+          p.tgrad = p.g_cbmax - p.g_cbmin <= 64;
+          if (p.tgrad) { p.shift1 = sh; p.gather1 = false; }   // the tile kernel takes the pattern over from the per-variable kernel
+        }
+      }
+      if (p.tgrad) {
+        const int ts1 = ns1 | 1;
+        std::vector<int> ord((size_t)ns1);
+        for (int j = 0; j < ns1; j++) ord[(size_t)j] = j;
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return p.shift1[(size_t)a] > p.shift1[(size_t)b]; });
+        o << "  static constexpr bool TGRAD = true; static constexpr int TS1 = " << ts1 << "; static constexpr long long GBMIN = " << p.g_cbmin << ", GBMAX = " << p.g_cbmax << ";\n";
+        o << "  template <bool CHECK> __device__ static __forceinline__ void ggather(const double* __restrict__ rp, const int ql, const int qlo, const int qhi, double (&acc)[1]) {\n";
+        for (int j : ord) {
+          const long long off = (long long)j - (long long)p.shift1[(size_t)j] * ts1;
+          o << "    if (!CHECK || (ql - (" << p.shift1[(size_t)j] << ") >= qlo && ql - (" << p.shift1[(size_t)j] << ") < qhi)) acc[0] += rp[" << off << "];\n";
+        }
+        o << "  }\n";
+      } else {
+        o << "  static constexpr bool TGRAD = false; static constexpr int TS1 = 1; static constexpr long long GBMIN = 0, GBMAX = 0;\n";
+        o << "  template <bool CHECK> __device__ static __forceinline__ void ggather(const double* __restrict__, const int, const int, const int, double (&)[1]) {}\n";
+      }
     }
     if (p.gather1) {
       // summation order of the reference for one variable: ascending global slot number = ascending point, then slot
@@ -833,7 +876,7 @@ inline std::string gen_pattern(PatternPlan& p, int index, bool windowed, const s
     }
     emit_eval3_fn(o, A + ", const XA x, const double* __restrict__ th, const double a0", "pa, kg, x, th, a0", a1, a2, B, tail);
     p.ppte = ppt_for(body_weight(B), a1 + a2);
-    o << "  static constexpr int PPTE = " << p.ppte << "; static constexpr bool G1 = " << (p.gather1 ? "true" : "false") << ";\n";
+    o << "  static constexpr int PPTE = " << p.ppte << "; static constexpr bool G1 = " << ((p.gather1 || p.tgrad) ? "true" : "false") << ";\n";
   }
   if (hd != nullptr && ns2 > 0 && p.tile_ok) {
     // Column-tile form (exb_tile_body): the block stages the second-order slots of the points around its tile of columns in
@@ -891,8 +934,9 @@ inline std::string plist(const std::vector<int>& v) {
   return s;
 }
 
-inline bool build_plan(Plan& pl, const void* ir, size_t bytes) {
+inline bool build_plan(Plan& pl, const void* ir, size_t bytes, const void* const* host_data = nullptr, int n_data = 0) {
   if (!parse_ir(ir, bytes, pl.m, pl.error)) return false;
+  if (getenv("EXB_NO_IOTA") == nullptr) detect_iota(pl.m, host_data, n_data);
   pl.pats.resize(pl.m.pats.size());
   for (size_t k = 0; k < pl.pats.size(); k++) {
     PatternPlan& p = pl.pats[k];
@@ -1005,7 +1049,8 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes) {
   for (size_t k = 0; k < pl.pats.size(); k++) {
     const PatternPlan& p = pl.pats[k];
     if (p.o2step > 0) pl.k_hess.push_back((int)k);
-    if (p.ir.kind == KIND_OBJ) { pl.k_obj.push_back((int)k); if (p.o1step > 0) (p.gather1 ? pl.k_ggrad : pl.k_sgrad).push_back((int)k); }
+    if (p.ir.kind == KIND_OBJ) { pl.k_obj.push_back((int)k); if (p.o1step > 0) (p.tgrad ? pl.k_tgrad : p.gather1 ? pl.k_ggrad : pl.k_sgrad).push_back((int)k); }
+    if (p.tgrad) pl.tgrad_halo = std::max(pl.tgrad_halo, (int)(p.g_cbmax - p.g_cbmin));
     else { pl.k_cons.push_back((int)k); if (p.o1step > 0) pl.k_jac.push_back((int)k); }
     if (p.ir.kind == KIND_AUG) pl.k_aug.push_back((int)k);
     pl.k_eval.push_back((int)k);   // every pattern has a value
@@ -1018,13 +1063,18 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes) {
   kern("exb_hess_g0", "exb_hess_body", pl.k_hess, "");
   if (pl.tile_ok) {
     o << "extern \"C\" __global__ void __launch_bounds__(EXB_BLOCK, EXB_MINB) exb_hessc_g0(const ExbGroup g, const ExbCall c, const ExbTile t) { "
-      << "exb_tile_body<" << pl.hd.size() << ", " << pl.tile_ppt << ", " << plist(pl.k_hess) << ">(g, c, t); }\n";
+      << "exb_tile_body<2, " << pl.hd.size() << ", " << pl.tile_ppt << ", " << plist(pl.k_hess) << ">(g, c, t); }\n";
   }
   if (pl.hess_windowed) kern("exb_hessp_g0", "exb_hessp_body", pl.k_hess, "");
   kern("exb_eval_g0", "exb_eval_body", pl.k_eval, "");
   kern("exb_jac_g0", "exb_d1_body", pl.k_jac, "");
   kern("exb_sgrad_g0", "exb_d1_body", pl.k_sgrad, "");
   kern("exb_ggrad_g0", "exb_ggrad_body", pl.k_ggrad, "");
+  if (!pl.k_tgrad.empty()) {
+    if (const char* e = getenv("EXB_TUNE_TGRAD_PPT")) { int v = atoi(e); if (v >= 1 && v <= 8) pl.tgrad_ppt = v; }
+    o << "extern \"C\" __global__ void __launch_bounds__(EXB_BLOCK, EXB_MINB) exb_gradt_g0(const ExbGroup g, const ExbCall c, const ExbTile t) { "
+      << "exb_tile_body<1, 1, " << pl.tgrad_ppt << ", " << plist(pl.k_tgrad) << ">(g, c, t); }\n";
+  }
   kern("exb_cons_g0", "exb_cons_body", pl.k_cons, "");
   kern("exb_obj_g0", "exb_obj_body", pl.k_obj, "");
   kern("exb_jstruct64_g0", "exb_jstruct_body", pl.k_jac, "long long, ");

@@ -163,10 +163,10 @@ bool load_nccl() {
   return g_nccl.ok;
 }
 
-enum { KN_HESS, KN_JAC, KN_SGRAD, KN_GGRAD, KN_CONS, KN_OBJ, KN_JSTRUCT64, KN_JSTRUCT32, KN_GSTRUCT64, KN_HSTRUCT64, KN_HSTRUCT32, KN_AUGROW, KN_JPROD, KN_JTPROD, KN_HPROD, KN_HESSC, KN_EVAL, KN_COUNT };
+enum { KN_HESS, KN_JAC, KN_SGRAD, KN_GGRAD, KN_CONS, KN_OBJ, KN_JSTRUCT64, KN_JSTRUCT32, KN_GSTRUCT64, KN_HSTRUCT64, KN_HSTRUCT32, KN_AUGROW, KN_JPROD, KN_JTPROD, KN_HPROD, KN_HESSC, KN_EVAL, KN_GRADT, KN_COUNT };
 const char* KNAME[KN_COUNT] = {"exb_hess_g0", "exb_jac_g0", "exb_sgrad_g0", "exb_ggrad_g0", "exb_cons_g0", "exb_obj_g0", "exb_jstruct64_g0",
                                "exb_jstruct32_g0", "exb_gstruct64_g0", "exb_hstruct64_g0", "exb_hstruct32_g0", "exb_augrow_g0",
-                               "exb_jprod_g0", "exb_jtprod_g0", "exb_hprod_g0", "exb_hessc_g0", "exb_eval_g0"};
+                               "exb_jprod_g0", "exb_jtprod_g0", "exb_hprod_g0", "exb_hessc_g0", "exb_eval_g0", "exb_gradt_g0"};
 
 }  // namespace
 
@@ -192,6 +192,7 @@ struct exb_plan {
       case KN_CONS: return pl.k_cons;
       case KN_OBJ: return pl.k_obj;
       case KN_EVAL: return pl.k_eval;
+      case KN_GRADT: return pl.k_tgrad;
       default: return pl.k_aug;
     }
   }
@@ -216,10 +217,10 @@ struct Launch {          // one generated kernel, ready to launch
   bool is_tile = false; ExbTile tile{};   // column-tile kernel (exb_tile_body): third kernel parameter
 };
 
-int make_plan(const void* ir, size_t bytes, exb_plan** out) {
+int make_plan(const void* ir, size_t bytes, exb_plan** out, const void* const* host_data = nullptr, int n_data = 0) {
   if (!ir || !out) return fail(EXB_ERR_ARG, "null argument");
   exb_plan* p = new exb_plan();
-  if (!exb::build_plan(p->pl, ir, bytes)) {
+  if (!exb::build_plan(p->pl, ir, bytes, host_data, n_data)) {
     std::string e = p->pl.error;
     delete p;
     return fail(EXB_ERR_IR, e);
@@ -610,6 +611,7 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       if (!base && n > 0) return fail(EXB_ERR_ARG, "null data buffer");
       for (size_t f = 0; f < p.ir.fields.size(); f++) {
         bool is32 = false;
+        if (f < p.ir.iota.size() && p.ir.iota[f]) continue;   // iota column: a function of the point number, never loaded
         int rc = upload_column(m, base, n, p.ir.stride, p.ir.fields[f], &a.col[f], &is32);
         if (rc) return rc;
         if (is32) a.i32mask |= (1LL << f);
@@ -644,7 +646,7 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
     m->v_lo = pl.m.nvar * m->rank / m->world; m->v_hi = pl.m.nvar * (m->rank + 1) / m->world;
     for (size_t k = 0; k < np && !all; k++) {
       const exb::PatternPlan& p = pl.pats[k];
-      if (!p.gather1 || m->world == 1 || m->v_hi <= m->v_lo) continue;
+      if (!(p.gather1 || p.tgrad || (pl.tile_ok && p.o2step > 0)) || m->world == 1 || m->v_hi <= m->v_lo) continue;
       if (!p.xr_ok) { all = true; break; }
       const long long w = p.xr_shift ? p.rhi - p.rlo : 0;   // a variable's points read x within this distance of it
       xl = std::min<long long>(xl, m->v_lo - w); xh = std::max<long long>(xh, m->v_hi + w);
@@ -675,7 +677,7 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       if (r != CUDA_SUCCESS) return fail(EXB_ERR_COMPILE, std::string("kernel ") + KNAME[kn] + " missing from module: " + cu_err(r));
       L.cand.push_back(fn);
     }
-    const bool tunable = kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD || kn == KN_GGRAD || kn == KN_CONS || kn == KN_OBJ || kn == KN_HESSC || kn == KN_EVAL;
+    const bool tunable = kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD || kn == KN_GGRAD || kn == KN_CONS || kn == KN_OBJ || kn == KN_HESSC || kn == KN_EVAL || kn == KN_GRADT;
     L.best = (!tunable || L.cand.size() == 1) ? 0 : tuned[kn];
     L.fn = L.cand[L.best >= 0 ? (size_t)L.best : 0];
     const long long BLK = P->pl.block;
@@ -692,7 +694,7 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       int ns = kn == KN_EVAL ? p.o1step + p.o2step : k2 ? p.o2step : k1 ? p.o1step : 1;
       if (ns <= EXB_TILE_MAX_NS && ns * ppt > maxns) maxns = ns * ppt;   // tile words per thread
     }
-    if (kn == KN_HESSC) {   // one block per tile of T consecutive COLUMNS of the owned range (exb_tile_body), no block -> pattern map
+    if (kn == KN_HESSC || kn == KN_GRADT) {   // one block per tile of T consecutive COLUMNS of the owned range (exb_tile_body), no block -> pattern map
       void* d_args = nullptr;
       int rc = dmalloc(m, &d_args, args.size() * sizeof(ExbPatArgs)); if (rc) return rc;
       CU_TRY(m, cudaMemcpy(d_args, args.data(), args.size() * sizeof(ExbPatArgs), cudaMemcpyHostToDevice));
@@ -700,13 +702,16 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       ExbTile& t = L.tile; memset(&t, 0, sizeof t);
       L.is_tile = true;
       t.c_lo = m->v_lo + 1; t.c_hi = m->v_hi + 1;
-      t.T = (int)BLK * pl.tile_ppt - pl.tile_halo; t.D = (int)pl.hd.size();
-      if (t.T < 32) continue;   // halo too wide for this block shape: the sorted gather stays in charge
+      const bool hc = kn == KN_HESSC;
+      t.T = (int)BLK * (hc ? pl.tile_ppt : pl.tgrad_ppt) - (hc ? pl.tile_halo : pl.tgrad_halo);
+      t.D = hc ? (int)pl.hd.size() : 1;
+      if (t.T < 32) { if (hc) continue; return fail(EXB_ERR_INTERNAL, "tile gradient: halo too wide for the block shape"); }
       size_t words = (size_t)t.T * (size_t)t.D;
-      for (int r = 0; r < t.D; r++) { t.lo[r] = pl.h_lo[(size_t)r]; t.len[r] = pl.h_len[(size_t)r]; t.dist[r] = pl.hd[(size_t)r]; }
+      if (hc) for (int r = 0; r < t.D; r++) { t.lo[r] = pl.h_lo[(size_t)r]; t.len[r] = pl.h_len[(size_t)r]; t.dist[r] = pl.hd[(size_t)r]; }
       for (int pi : lst) {
         const exb::PatternPlan& p = pl.pats[(size_t)pi];
-        words = std::max(words, (size_t)(t.T + (p.t_cbmax - p.t_cbmin)) * (size_t)(p.o2step | 1));
+        if (hc) words = std::max(words, (size_t)(t.T + (p.t_cbmax - p.t_cbmin)) * (size_t)(p.o2step | 1));
+        else words = std::max(words, (size_t)(t.T + (p.g_cbmax - p.g_cbmin)) * (size_t)(p.o1step | 1));
       }
       L.nblocks = (unsigned)((t.c_hi - t.c_lo + t.T - 1) / t.T);
       L.smem = (unsigned)(8 * ((words + 1) & ~(size_t)1));
@@ -715,7 +720,7 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
           r = g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)L.smem);
           if (r != CUDA_SUCCESS) return fail(EXB_ERR_CUDA, std::string("cuFuncSetAttribute(max dynamic smem): ") + cu_err(r));
         }
-      m->hess_tile = true;
+      if (hc) m->hess_tile = true;
       continue;
     }
     if (kn == KN_GGRAD) {   // one thread per VARIABLE (exb_ggrad_body), no block -> pattern map; runs even when this shard has no points (g = 0)
@@ -976,6 +981,13 @@ int exb_plan_create(const void* ir, size_t ir_bytes, const exb_options* opt, exb
   return make_plan(ir, ir_bytes, out);
   EXB_END
 }
+// same, with the iterator data at hand: lets the plan recognise iota columns (exb_ir.hpp detect_iota), as exb_create does
+int exb_plan_create_data(const void* ir, size_t ir_bytes, const void* const* host_data, int n_data, const exb_options* opt, exb_plan** out) {
+  EXB_BEGIN
+  (void)opt;
+  return make_plan(ir, ir_bytes, out, host_data, n_data);
+  EXB_END
+}
 int exb_plan_destroy(exb_plan* p) { delete p; return EXB_OK; }
 int exb_plan_dims(const exb_plan* p, int64_t* o) {
   if (!p || !o) return fail(EXB_ERR_HANDLE, "invalid handle");
@@ -1039,7 +1051,7 @@ int exb_create(const void* ir, size_t ir_bytes, const void* const* host_data, in
   if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) return fail(EXB_ERR_CUDA, "cudaGetDevice failed"); }
   if (dev >= ndev) return fail(EXB_ERR_ARG, "device ordinal out of range");
   exb_plan* P = nullptr;
-  int rc = make_plan(ir, ir_bytes, &P);
+  int rc = make_plan(ir, ir_bytes, &P, host_data, n_data);
   if (rc) return rc;
   rc = compile_plan(P, !(o.flags & EXB_FLAG_NO_COMPILE));
   if (rc) { delete P; return rc; }
@@ -1099,15 +1111,20 @@ int exb_obj(exb_model* m, const double* x, double* out_host, void* stream) {
 static int grad_impl(exb_model* m, const double* x, double* g, cudaStream_t st, bool slots_ready) {
   const exb::Plan& pl = m->plan->pl;
   ExbCall c{}; c.x = x; c.th = m->d_theta; c.out = m->d_gradbuf;
-  const bool gathered = !pl.k_ggrad.empty();
+  const bool tiled = !pl.k_tgrad.empty();
+  const bool gathered = !pl.k_ggrad.empty() || tiled;
   // fill!(g, 0) (ext:317): needed when some variable has no objective term -- and on a sharded handle, whose g must be zero
   // outside what it computes so that the shards add up
   // (not when the shards never need adding: a communicator is attached and every objective pattern is owner-computed)
   const bool owner_only = comm_on(m) && pl.k_sgrad.empty() && gathered;
   if ((m->world > 1 && !owner_only) || (m->world == 1 && !gathered && !(m->g_dense && m->g_runs == pl.m.nvar)))
     CU_TRY(m, cudaMemsetAsync(g, 0, (size_t)pl.m.nvar * 8, st));
-  if (gathered) {   // shift-indexed objective patterns: one thread per OWNED variable writes g[v] (0 where untouched)
-    ExbCall cg{}; cg.x = x; cg.th = m->d_theta; cg.out = g; cg.v0 = m->v_lo; cg.nout = m->v_hi - m->v_lo;
+  if (tiled) {      // shift-indexed objective patterns: a block per tile of OWNED variables evaluates the points around it once and
+    ExbCall ct{}; ct.x = x; ct.th = m->d_theta; ct.out = g;   // gathers their slots (exb_gradt_g0); g[v] assigned, 0 where untouched
+    int rc = launch(m, KN_GRADT, ct, st); if (rc) return rc;
+  }
+  if (!pl.k_ggrad.empty()) {   // per-variable form (patterns the tile kernel did not take): one thread per OWNED variable
+    ExbCall cg{}; cg.x = x; cg.th = m->d_theta; cg.out = g; cg.v0 = m->v_lo; cg.nout = m->v_hi - m->v_lo; cg.sigma = tiled ? 1.0 : 0.0;
     int rc = launch(m, KN_GGRAD, cg, st); if (rc) return rc;
   }
   if (!slots_ready) { int rc = launch(m, KN_SGRAD, c, st); if (rc) return rc; }  // kerg, ext:669-679
@@ -1839,12 +1856,13 @@ int exb_kernel_choice(const exb_model* m, int callback, int64_t* o) {
   static const int map[5] = {KN_OBJ, KN_GGRAD, KN_CONS, KN_JAC, KN_HESS};
   if (callback < 0 || callback > 4) return fail(EXB_ERR_ARG, "callback must be 0 (obj) .. 4 (hess)");
   int kn = map[callback];
+  if (kn == KN_GGRAD && m->k[KN_GRADT].nblocks > 0) kn = KN_GRADT;
   if (kn == KN_GGRAD && m->k[kn].nblocks == 0) kn = KN_SGRAD;
   const Launch& L = m->k[kn];
   o[0] = L.best >= 0 && (size_t)L.best < m->plan->var.size() ? m->plan->var[(size_t)L.best].minb : -1;
   o[1] = L.use_p >= 0 ? 1 : 0;
   o[2] = L.use_p >= 0 ? (int64_t)L.pgrid[(size_t)L.use_p] : (int64_t)L.nblocks;
-  o[3] = kn == KN_GGRAD ? 1 : 0;
+  o[3] = kn == KN_GGRAD ? 1 : kn == KN_GRADT ? 2 : 0;
   return EXB_OK;
 }
 int exb_comm_stats(const exb_model* m, int64_t* o) {

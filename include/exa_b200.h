@@ -103,6 +103,9 @@ typedef struct exb_options {
 
 /* ---- analysis (replaces src/simdfunction.jl:66-100 + the counters of nlp.jl) ---- */
 int exb_plan_create(const void* ir, size_t ir_bytes, const exb_options* opt, exb_plan** out);
+/* same with the iterator data at hand (as exb_create has it): integer fields that hold v0, v0 + 1, v0 + 2, ... (the `i` of an array
+ * of NamedTuples built from 1:n) are recognised, which turns a data-indexed pattern into a shift-indexed one */
+int exb_plan_create_data(const void* ir, size_t ir_bytes, const void* const* host_data, int n_data, const exb_options* opt, exb_plan** out);
 int exb_plan_destroy(exb_plan* p);
 int exb_plan_dims(const exb_plan* p, int64_t* out8);
 int exb_plan_npatterns(const exb_plan* p);

@@ -17,7 +17,7 @@ def _models():
     from edge_models import EDGE
     return {
         "lv_1003": lambda: M.luksan_vlcek(1003),                    # 4 tiles, ragged tail
-        "lv_254": lambda: M.luksan_vlcek(254),                      # exactly one tile
+        "lv_382": lambda: M.luksan_vlcek(382),                      # exactly one tile (128 x 3 columns - halo 2)
         "lv_5": lambda: M.luksan_vlcek(5),                          # tiny: every column is a boundary column
         "lv_guide_700": lambda: M.luksan_vlcek(700, order="guide"), # objective first
         "lv_param_300": lambda: M.luksan_vlcek_param(300),          # parameters in the objective

@@ -46,21 +46,60 @@ def test_generated_source_is_model_size_independent():
     a, b = E.Plan(M.luksan_vlcek(100)), E.Plan(M.luksan_vlcek(10_000))
     assert a.source() == b.source() and a.module_path() == b.module_path()
     src = a.source()
-    for kern in ("exb_hess_g0", "exb_jac_g0", "exb_ggrad_g0", "exb_cons_g0", "exb_obj_g0", "exb_hstruct64_g0"):
+    for kern in ("exb_hess_g0", "exb_jac_g0", "exb_gradt_g0", "exb_cons_g0", "exb_obj_g0", "exb_hstruct64_g0", "exb_eval_g0", "exb_hessc_g0"):
         assert f'extern "C" __global__ void __launch_bounds__(EXB_BLOCK, EXB_MINB) {kern}' in src
     assert "sincos" in src and "struct P0" in src and "struct P1" in src
 
 
-def test_gradient_kernel_choice():
-    """Shift-indexed objectives over a range (x[i-1], x[i]) get the owner-computes gradient kernel; objectives whose
-    variable indices come from iterator data keep the slot + segmented-sum path of the reference (ext:310-336,691-697)."""
+def _has(src, kernel):
+    return f"EXB_MINB) {kernel}(const ExbGroup" in src
+
+
+def test_gradient_kernel_choice(monkeypatch):
+    """Objectives whose slots address x[t + const] (t a range value, or the point number when an AoS iterator carries an iota
+    column) get the tile kernel: a block per tile of variables evaluates the points around it ONCE and gathers their slots in
+    the reference's order.  EXB_NO_TGRAD falls back to the per-variable owner-computes kernel for light bodies; objectives
+    indexed through iterator data keep the slot + segmented-sum path of the reference (ext:310-336,691-697)."""
     lv = E.Plan(M.luksan_vlcek(50)).source()
-    assert "exb_ggrad_g0" in lv and "exb_sgrad_g0" not in lv
-    # slot order for variable v: point v (slot of x[i]) before point v + 1 (slot of x[i-1]) = ascending slot number
-    g1 = lv[lv.index("double g1("):]
+    assert _has(lv, "exb_gradt_g0") is True and _has(lv, "exb_sgrad_g0") is False and _has(lv, "exb_ggrad_g0") is False
+    # summation order for variable v: point v (slot of x[i]) before point v + 1 (slot of x[i-1]) = ascending slot number
+    gg = lv[lv.rindex("void ggather("):]
+    gg = gg[:gg.index("}")]
+    assert gg.index("ql - (0)") < gg.index("ql - (-1)")
+    fam = E.Plan(M.pattern_family(100, 8)).source()       # `i` column = 1..n: recognised from the data, never loaded
+    assert _has(fam, "exb_gradt_g0") is True and _has(fam, "exb_sgrad_g0") is False
+    opf = E.Plan(M.ac_power(M.synthetic_power_data(30, 41, 6, seed=5))).source()
+    assert _has(opf, "exb_gradt_g0") is True                            # generator cost over pg[g.i], g.i = 1..ngen
+    monkeypatch.setenv("EXB_NO_TGRAD", "1")
+    lv2 = E.Plan(M.luksan_vlcek(50)).source()
+    assert _has(lv2, "exb_ggrad_g0") is True and _has(lv2, "exb_gradt_g0") is False
+    g1 = lv2[lv2.index("double g1("):]
     assert g1.index("s[1] : 0.0") < g1.index("s[0] : 0.0")
-    fam = E.Plan(M.pattern_family(100, 8)).source()
-    assert "exb_sgrad_g0" in fam and "exb_ggrad_g0" not in fam
+    monkeypatch.setenv("EXB_NO_IOTA", "1")
+    fam2 = E.Plan(M.pattern_family(100, 8)).source()
+    assert _has(fam2, "exb_sgrad_g0") is True and _has(fam2, "exb_gradt_g0") is False and _has(fam2, "exb_ggrad_g0") is False
+
+
+def test_iota_columns_are_recognised_from_the_data(monkeypatch):
+    """An integer field holding v0, v0 + 1, ... turns a data-indexed pattern into a shift-indexed one: index relations are decided
+    at build time, the duplicate-free Hessian is fused, the column is never loaded.  A permuted column is left alone."""
+    core = M.pattern_family(200, 8)
+    p = E.Plan(core)
+    src = p.source()
+    assert p.tile_info()["fused"] and p.tile_info()["nnzh_unique"] == 3 * 202 - 3
+    p0 = src[src.index("struct P0 {"):src.index("struct P1 {")]
+    assert "exb_ld_i(" not in p0 and "exb_twice_if_eq(" not in p0 and "kg + 1LL" in p0
+    # same structure and counts as without the hint
+    monkeypatch.setenv("EXB_NO_IOTA", "1")
+    q = E.Plan(core)
+    assert not q.tile_info()["fused"] and "exb_ld_i(" in q.source()
+    for k in range(p.npatterns()):
+        assert p.pattern_info(k) == q.pattern_info(k)
+    monkeypatch.delenv("EXB_NO_IOTA")
+    import numpy as np
+    core2 = M.pattern_family(200, 2)
+    core2.patterns[0].itr.array["i"][:] = np.random.default_rng(0).permutation(200) + 1
+    assert "exb_ld_i(" in E.Plan(core2).source()[:E.Plan(core2).source().index("struct P1 {")]
 
 
 def test_header_symbols_exported():
@@ -152,6 +191,8 @@ def test_persistent_kernel_is_opt_in_and_needs_windows(monkeypatch):
     src = _generated(lv)
     assert "exb_hessp_g0" in src and "XLO = 0, XHI = 2" in src and "XLO = -1, XHI = 0" in src      # LV constraint / objective windows
     assert "exb_hessp_g0" not in _generated(M.luksan_vlcek_aug(10, 2))                             # data-indexed (product iterator): no window
+    assert "exb_hessp_g0" in _generated(M.pattern_family(50, 8))                                   # iota column: as good as a range
+    monkeypatch.setenv("EXB_NO_IOTA", "1")
     assert "exb_hessp_g0" not in _generated(M.pattern_family(50, 8))
 
 
@@ -175,7 +216,7 @@ def test_kernel_modules_are_cached_compressed(tmp_path, monkeypatch):
     assert raw[:4] == b"\x7fELF" and len(raw) > 5 * os.path.getsize(path + ".gz") / 2
     (tmp_path / "m.cubin").write_bytes(raw)
     out = subprocess.run(["cuobjdump", "-res-usage", str(tmp_path / "m.cubin")], capture_output=True, text=True).stdout
-    for k in ("exb_hess_g0", "exb_jac_g0", "exb_ggrad_g0", "exb_cons_g0", "exb_obj_g0", "exb_hprod_g0"):
+    for k in ("exb_hess_g0", "exb_jac_g0", "exb_gradt_g0", "exb_cons_g0", "exb_obj_g0", "exb_hprod_g0", "exb_eval_g0", "exb_hessc_g0"):
         assert f"Function {k}:" in out
     again = E.Plan(M.luksan_vlcek(31))          # same source: cache hit on the compressed module, nothing recompiled
     t0 = os.path.getmtime(path + ".gz")
