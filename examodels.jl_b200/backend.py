@@ -30,6 +30,7 @@ _LIB = None
 
 EXB_FLAG_NO_COMPILE = 1
 EXB_FLAG_SORTED_PRODUCTS = 2
+EXB_FLAG_TUNE_AT_CREATE = 4
 _ERRS = {1: "invalid handle", 2: "internal error", 3: "malformed IR", 4: "kernel module compile/load failed",
          5: "CUDA error / no device", 6: "bad argument"}
 
@@ -42,7 +43,7 @@ exb_jprod exb_jtprod exb_hprod exb_compressed_dims exb_jac_structure_compressed6
 exb_jac_compressed exb_hess_compressed exb_set_timing exb_timings exb_kernel_choice exb_host_bytes
 exb_comm_unique_id exb_comm_init exb_comm_attach exb_comm_destroy exb_comm_set_mode exb_comm_gather_coo exb_owned
 exb_comm_stats exb_compressed_shard exb_jac_structure_compressed32 exb_hess_structure_compressed32
-exb_host_jac_compressed exb_host_hess_compressed exb_plan_tile exb_eval exb_plan_create_data""".split()
+exb_host_jac_compressed exb_host_hess_compressed exb_plan_tile exb_eval exb_plan_create_data exb_tune exb_build_info""".split()
 
 
 class ExbError(RuntimeError):
@@ -93,7 +94,7 @@ def _check(rc):
 
 class _Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("flags", C.c_int32),
-                ("fuse_below", C.c_int64)]
+                ("fuse_below", C.c_int64), ("tune_x0", C.c_void_p)]
 
 
 def _np_ptr(a):
@@ -164,7 +165,7 @@ def _is_torch(a):
 class ExaModel:
     """`ExaModel(core)` on one B200 (or on shard `rank` of `world` when sharded)."""
 
-    def __init__(self, core, device=None, rank=0, world=1, allow_compile=True, sorted_products=False):
+    def __init__(self, core, device=None, rank=0, world=1, allow_compile=True, sorted_products=False, tune_at_create=False):
         import torch  # device memory + streams only
 
         self._torch = torch
@@ -182,8 +183,10 @@ class ExaModel:
         ir, bufs = core.to_ir()
         self._ir, self._bufs = ir, bufs
         arr = (C.c_void_p * max(1, len(bufs)))(*[b.ctypes.data for b in bufs])
-        flags = (0 if allow_compile else EXB_FLAG_NO_COMPILE) | (EXB_FLAG_SORTED_PRODUCTS if sorted_products else 0)
-        opt = _Options(self.device.index, self.rank, self.world, flags, 0)
+        flags = ((0 if allow_compile else EXB_FLAG_NO_COMPILE) | (EXB_FLAG_SORTED_PRODUCTS if sorted_products else 0)
+                 | (EXB_FLAG_TUNE_AT_CREATE if tune_at_create else 0))
+        x0 = np.ascontiguousarray(meta["x0"], dtype=np.float64)
+        opt = _Options(self.device.index, self.rank, self.world, flags, 0, x0.ctypes.data if tune_at_create else None)
         self.h = C.c_void_p()
         _check(lib().exb_create(ir, C.c_size_t(len(ir)), arr, len(bufs), C.byref(opt), C.byref(self.h)))
         d = np.zeros(8, dtype=np.int64)
@@ -442,6 +445,15 @@ class ExaModel:
         o = np.zeros(2, dtype=np.int64)
         _check(lib().exb_host_bytes(self.h, _np_ptr(o)))
         return int(o[0]), int(o[1])
+
+    def tune(self, x, y=None):
+        """Rank the launch-shape variants of every kernel now (exb_tune), at the CUDA tensors x / y."""
+        _check(lib().exb_tune(self.h, self._dev(x, self.nvar), None if y is None else self._dev(y, self.ncon), self._stream()))
+
+    def build_info(self):
+        o = np.zeros(5)
+        _check(lib().exb_build_info(self.h, _np_ptr(o)))
+        return dict(zip(("plan_s", "nvcc_s", "load_s", "tune_s", "create_s"), (float(v) for v in o)))
 
     def stats(self):
         o = np.zeros(4, dtype=np.int64)

@@ -21,6 +21,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -374,6 +375,8 @@ struct exb_model {
   double *hx = nullptr, *hy = nullptr, *hout = nullptr; size_t hx_n = 0, hy_n = 0, hout_n = 0;
   double *dx = nullptr, *dy = nullptr, *dout = nullptr; size_t dx_n = 0, dy_n = 0, dout_n = 0;
   long long launches = 0, last_launches = 0;
+  std::string dev_name;            // device name without blanks (part of the tuning key)
+  double tune_s = 0, create_s = 0, nvcc_s = 0, load_s = 0, plan_s = 0;   // where model-build time went (exb_build_info)
   // multi-GPU: a communicator over the `world` handles of one sharded model (exb_comm_*); with it the reducing callbacks
   // complete themselves on the caller's stream
   ncclComm_t comm = nullptr; bool comm_owned = false; int comm_mode = EXB_COMM_REPLICATE;
@@ -429,41 +432,60 @@ int launch_persistent(exb_model* m, int kn, size_t pi, const ExbCall& c, cudaStr
   return EXB_OK;
 }
 
-// First call of a tunable kernel: run every variant on the caller's own buffers (each one fully
-// defines the output, so the result is valid whichever ran last), time them with events and keep
-// the fastest.  This one call synchronises the stream; later calls do not.
+// Tuning of a kernel's launch-shape variant: run every variant on the given buffers (each one fully defines the output, so
+// the result is valid whichever ran last), time them with events -- MEDIAN of 5 runs after a warm-up (9 for launches under
+// 50 us, whose timing is noisier) -- and keep the fastest.  Happens at the kernel's first call (that one call synchronises the
+// stream; later calls do not), or for every kernel at exb_create / exb_tune (EXB_FLAG_TUNE_AT_CREATE), so that no solver
+// callback ever synchronises.  The verdict is remembered per (kernel, device, grid-size class) in exb_<hash>.tune.
+std::string tune_key(exb_model* m, int kn) {
+  const Launch& L = m->k[kn];
+  int lg = 0; for (unsigned v = L.nblocks; v > 1; v >>= 1) lg++;
+  return std::string(KNAME[kn]) + "@" + m->dev_name + "@" + std::to_string(lg / 2);   // size class: a factor of 4 in blocks
+}
+void tune_remember(exb_model* m, const std::string& line) {   // one O_APPEND write per verdict: atomic for concurrent writers
+  int fd = open(m->plan->tune_path.c_str(), O_WRONLY | O_APPEND | O_CREAT, 0666);
+  if (fd < 0) return;
+  ssize_t w = write(fd, line.data(), line.size());
+  (void)w;
+  close(fd);
+}
 int tune(exb_model* m, int kn, const ExbCall& c, cudaStream_t st) {
   Launch& L = m->k[kn];
   cudaEvent_t e0, e1;
   CU_TRY(m, cudaEventCreate(&e0)); CU_TRY(m, cudaEventCreate(&e1));
   int rc = EXB_OK; float best_ms = 0, best_classic_ms = 0; int best = 0, best_classic = 0;
   const size_t nc = L.cand.size(), np = L.pcand.size();
+  const auto t_begin = std::chrono::steady_clock::now();
   for (size_t v = 0; v < nc + np && !rc; v++) {
     auto run = [&]() { return v < nc ? launch_fn(m, kn, L.cand[v], c, st) : launch_persistent(m, kn, v - nc, c, st); };
     rc = run();                                                    // warm-up (module load, caches)
-    float ms = 1e30f;
-    for (int rep = 0; rep < 2 && !rc; rep++) {
+    std::vector<float> ts;
+    int reps = 5;
+    for (int rep = 0; rep < reps && !rc; rep++) {
       cudaEventRecord(e0, st);
       rc = run();
       cudaEventRecord(e1, st);
       if (cudaEventSynchronize(e1) != cudaSuccess) rc = fail(EXB_ERR_CUDA, "kernel failed while tuning");
       float t = 0; cudaEventElapsedTime(&t, e0, e1);
-      if (t < ms) ms = t;
+      ts.push_back(t);
+      if (rep == 4 && reps == 5 && t < 0.05f) reps = 9;
     }
+    if (rc) break;
+    std::sort(ts.begin(), ts.end());
+    const float ms = ts[ts.size() / 2];
     if (v == 0 || ms < best_ms) { best_ms = ms; best = (int)v; }
     if (v < nc && (v == 0 || ms < best_classic_ms)) { best_classic_ms = ms; best_classic = (int)v; }
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  m->tune_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
   if (rc) return rc;
   // the classic form stays available (windowed launches of the host shims, graph capture); the persistent one is used
   // for whole-grid launches when it measured faster
   L.best = best_classic; L.fn = L.cand[(size_t)best_classic];
   L.use_p = best >= (int)nc ? best - (int)nc : -1;
-  if (m->rank == 0 && best_ms >= 0.03f) {   // remember, unless the launch was too short to rank variants (append; last entry wins)
-    std::ofstream tf(m->plan->tune_path, std::ios::app);
-    tf << KNAME[kn] << " " << m->plan->var[(size_t)best_classic].minb << "\n";
-    if (np > 0) tf << KNAME[kn] << "+persistent " << (L.use_p >= 0 ? m->plan->var[(size_t)L.use_p].minb : -1) << "\n";
-  }
+  std::string line = tune_key(m, kn) + " " + std::to_string(m->plan->var[(size_t)best_classic].minb) + "\n";
+  if (np > 0) line += tune_key(m, kn) + "+persistent " + std::to_string(L.use_p >= 0 ? m->plan->var[(size_t)L.use_p].minb : -1) + "\n";
+  tune_remember(m, line);
   return EXB_OK;
 }
 
@@ -564,6 +586,8 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
   {  // sm_100 only
     cudaDeviceProp prop;
     CU_TRY(m, cudaGetDeviceProperties(&prop, m->device));
+    m->dev_name = prop.name;
+    for (char& ch : m->dev_name) if (ch == ' ' || ch == '@') ch = '_';
     if (prop.major != 10) return fail(EXB_ERR_CUDA, "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + "; this evaluator targets sm_100a (B200) only");
   }
   // module
@@ -576,20 +600,13 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
     if (r != CUDA_SUCCESS) return fail(EXB_ERR_COMPILE, "cuModuleLoadData(" + v.cubin_path + "): " + cu_err(r));
     m->mods.push_back(mod);
   }
-  // a previous run's tuning result for this model's kernels: "<kernel> <minb>" lines
-  std::vector<int> tuned(KN_COUNT, -1), tuned_p(KN_COUNT, -2);   // tuned_p: -2 unknown, -1 classic wins, >= 0 persistent variant
+  // a previous run's tuning results for this model's kernels: "<kernel>@<device>@<size class> <minb>" lines (last entry wins);
+  // they are matched once the grids are known (after the kernel loop below)
+  std::vector<std::pair<std::string, int>> tune_lines;
   {
     std::ifstream tf(P->tune_path);
     std::string name; int mb;
-    while (tf >> name >> mb)
-      for (int kn = 0; kn < KN_COUNT; kn++) {
-        if (name == KNAME[kn])
-          for (size_t vi = 0; vi < P->var.size(); vi++) if (P->var[vi].minb == mb) tuned[kn] = (int)vi;
-        if (name == std::string(KNAME[kn]) + "+persistent") {
-          tuned_p[kn] = -1;
-          for (size_t vi = 0; vi < P->var.size(); vi++) if (P->var[vi].minb == mb) tuned_p[kn] = (int)vi;
-        }
-      }
+    while (tf >> name >> mb) tune_lines.push_back({name, mb});
   }
 
   // per-pattern arguments
@@ -678,8 +695,8 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       L.cand.push_back(fn);
     }
     const bool tunable = kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD || kn == KN_GGRAD || kn == KN_CONS || kn == KN_OBJ || kn == KN_HESSC || kn == KN_EVAL || kn == KN_GRADT;
-    L.best = (!tunable || L.cand.size() == 1) ? 0 : tuned[kn];
-    L.fn = L.cand[L.best >= 0 ? (size_t)L.best : 0];
+    L.best = (!tunable || L.cand.size() == 1) ? 0 : -1;
+    L.fn = L.cand[0];
     const long long BLK = P->pl.block;
     std::vector<ExbPatArgs> args(lst.size());
     std::vector<long long> nb(lst.size());
@@ -714,7 +731,9 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
         else words = std::max(words, (size_t)(t.T + (p.g_cbmax - p.g_cbmin)) * (size_t)(p.o1step | 1));
       }
       L.nblocks = (unsigned)((t.c_hi - t.c_lo + t.T - 1) / t.T);
-      L.smem = (unsigned)(8 * ((words + 1) & ~(size_t)1));
+      words = (words + 1) & ~(size_t)1;
+      t.half = lst.size() > 1 ? (int)words : 0;   // two staging buffers when there is more than one pattern
+      L.smem = (unsigned)(8 * (words + (size_t)t.half));
       if (L.smem > 48u * 1024u)
         for (CUfunction fn : L.cand) {
           r = g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)L.smem);
@@ -796,8 +815,25 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
         L.pcand.push_back(fn);
         L.pgrid.push_back((unsigned)std::min<long long>((long long)L.pw[3], (long long)per_sm * nsm));
       }
-      if (tuned_p[kn] >= -1 && L.best >= 0) L.use_p = tuned_p[kn];
-      else L.best = -1;   // no verdict on the persistent form yet: tune at the first call
+      L.best = -1;        // verdicts (classic and persistent) are matched below
+    }
+  }
+  // remembered tuning verdicts, now that every kernel's grid (hence its size class) is known
+  for (int kn = 0; kn < KN_COUNT; kn++) {
+    Launch& L = m->k[kn];
+    if (L.cand.size() < 2 || L.best >= 0) continue;
+    const std::string key = tune_key(m, kn);
+    int cls = -1, per = -2;
+    for (auto& ln : tune_lines) {
+      if (ln.first == key) { cls = -1; for (size_t vi = 0; vi < P->var.size(); vi++) if (P->var[vi].minb == ln.second) cls = (int)vi; }
+      if (ln.first == key + "+persistent") { per = -1; for (size_t vi = 0; vi < P->var.size(); vi++) if (P->var[vi].minb == ln.second) per = (int)vi; }
+    }
+    const bool need_p = !L.pcand.empty();
+    if (cls >= 0 && (!need_p || per >= -1)) {
+      L.best = cls; L.fn = L.cand[(size_t)cls];
+      if (need_p) L.use_p = per;
+    }
+    if (kn == KN_HESS && need_p) {
       if (const char* e = getenv("EXB_TUNE_FORCE_PERSISTENT")) {   // test / development knob: 1 = always, 0 = never
         if (L.best < 0) { L.best = 0; L.fn = L.cand[0]; }
         L.use_p = atoi(e) ? 0 : -1;
@@ -1037,11 +1073,13 @@ int exb_plan_compile(exb_plan* p) {
   EXB_END
 }
 
+static int tune_all(exb_model* m, const double* x, const double* y, bool x_on_host, void* stream);
+
 int exb_create(const void* ir, size_t ir_bytes, const void* const* host_data, int n_data, const exb_options* opt, exb_model** out) {
   EXB_BEGIN
   if (!out) return fail(EXB_ERR_ARG, "null argument");
   *out = nullptr;
-  exb_options o{-1, 0, 1, 0, 0};
+  exb_options o{-1, 0, 1, 0, 0, nullptr};
   if (opt) o = *opt;
   if (o.world < 1 || o.rank < 0 || o.rank >= o.world) return fail(EXB_ERR_ARG, "bad rank / world");
   int ndev = 0;
@@ -1051,16 +1089,26 @@ int exb_create(const void* ir, size_t ir_bytes, const void* const* host_data, in
   if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) return fail(EXB_ERR_CUDA, "cudaGetDevice failed"); }
   if (dev >= ndev) return fail(EXB_ERR_ARG, "device ordinal out of range");
   exb_plan* P = nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
   int rc = make_plan(ir, ir_bytes, &P, host_data, n_data);
   if (rc) return rc;
+  const auto t1 = std::chrono::steady_clock::now();
   rc = compile_plan(P, !(o.flags & EXB_FLAG_NO_COMPILE));
   if (rc) { delete P; return rc; }
+  const auto t2 = std::chrono::steady_clock::now();
   exb_model* m = new exb_model();
   m->plan = P; m->device = dev; m->rank = o.rank; m->world = o.world;
   m->sorted_products = (o.flags & EXB_FLAG_SORTED_PRODUCTS) != 0;
   DeviceGuard dg(dev);
   rc = build_model(m, host_data, n_data);
   if (rc) { std::string keep = g_err; free_model(m); g_err = keep; return rc; }
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+  m->plan_s = secs(t0, t1); m->nvcc_s = P->from_cache ? 0.0 : secs(t1, t2); m->load_s = secs(t2, std::chrono::steady_clock::now());
+  if (o.flags & EXB_FLAG_TUNE_AT_CREATE) {   // so that no solver callback ever synchronises (see tune())
+    rc = tune_all(m, o.tune_x0, nullptr, true, nullptr);
+    if (rc) { std::string keep = g_err; free_model(m); g_err = keep; return rc; }
+  }
+  m->create_s = secs(t0, std::chrono::steady_clock::now());
   *out = m;
   return EXB_OK;
   EXB_END
@@ -1695,6 +1743,86 @@ int exb_host_hess(exb_model* m, const double* x, const double* y, double obj_wei
   { EXB_BEGIN EXB_GUARD(m); bool done = false; int prc = host_coo_pipelined(m, KN_HESS, x, y, obj_weight, out, &done); if (prc || done) return prc; EXB_END }
   EXB_HOST_VEC(pl.nnzh, slices(m, 2), exb_hess(m, m->dx, y ? m->dy : nullptr, obj_weight, m->dout, m->hstream))
 }
+// Pipelined form of exb_host_hess_compressed for page-locked caller buffers.  In a shift-indexed model a window of COLUMNS
+// needs only the matching windows of x and y (plus a halo of a few entries), so everything streams: while window w's values
+// travel to the host (second stream), window w + 1's x / y pieces go up and its tiles are evaluated -- H2D and D2H overlap
+// (PCIe is full duplex) instead of following each other.
+static int host_hessc_pipelined(exb_model* m, const double* x, const double* y, double sigma, double* out, bool* done) {
+  *done = false;
+  Launch& L = m->k[KN_HESSC];
+  const exb::Plan& pl = m->plan->pl;
+  static const int wenv = getenv("EXB_HOST_WINDOWS") ? atoi(getenv("EXB_HOST_WINDOWS")) : 8;
+  if (!m->hess_tile || wenv < 2 || L.best < 0 || !L.fn || L.nblocks < 16) return EXB_OK;
+  const ExbTile& T0 = L.tile;
+  const long long o_lo = tile_before(T0, T0.c_lo), o_hi = tile_before(T0, T0.c_hi), total = tile_unique(m);
+  if (o_hi - o_lo < (1LL << 18)) return EXB_OK;
+  if (!is_pinned(x) || (y && !is_pinned(y)) || !is_pinned(out + o_lo)) return EXB_OK;
+  const std::vector<int>& lst = m->plan->list(KN_HESSC);
+  long long H = 0;   // how far from a window of columns the variables read by its tiles can lie
+  for (int pi : lst) {
+    const exb::PatternPlan& p = pl.pats[(size_t)pi];
+    if (!p.xr_ok || p.xr_fixed) return EXB_OK;
+    H = std::max<long long>(H, (p.t_cbmax - p.t_cbmin) + (p.rhi - p.rlo) + 1);
+  }
+  int rc = host_stream(m); if (rc) return rc;
+  if (!m->hstream2) CU_TRY(m, cudaStreamCreateWithFlags(&m->hstream2, cudaStreamNonBlocking));
+  const int W = (int)std::min<long long>(wenv, L.nblocks);
+  while ((int)m->hev.size() < W) { cudaEvent_t e; CU_TRY(m, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); m->hev.push_back(e); }
+  rc = ensure_host(m, &m->hx, &m->hx_n, &m->dx, &m->dx_n, 0, (size_t)pl.m.nvar); if (rc) return rc;
+  if (y) { rc = ensure_host(m, &m->hy, &m->hy_n, &m->dy, &m->dy_n, 0, (size_t)pl.ncon); if (rc) return rc; }
+  rc = ensure_host(m, &m->hout, &m->hout_n, &m->dout, &m->dout_n, 0, (size_t)total); if (rc) return rc;
+  m->last_h2d = 0; m->last_d2h = 0;
+  long long x_up = std::max<long long>(0, T0.c_lo - 1 - H);           // x[x_up_lo, x_up) is on the device so far (0-based)
+  const long long x_first = x_up;
+  std::vector<long long> y_up(lst.size(), -1);                        // per constraint pattern: rows [.., y_up) uploaded (0-based row numbers)
+  (void)x_first;
+  for (int w = 0; w < W; w++) {
+    const long long b0 = (long long)L.nblocks * w / W, b1 = (long long)L.nblocks * (w + 1) / W;
+    if (b1 <= b0) continue;
+    const long long cw_lo = T0.c_lo + b0 * T0.T, cw_hi = std::min<long long>(T0.c_hi, T0.c_lo + b1 * T0.T);   // 1-based columns [cw_lo, cw_hi)
+    const long long x_need = std::min<long long>(pl.m.nvar, cw_hi - 1 + H);
+    if (x_need > x_up) {
+      CU_TRY(m, cudaMemcpyAsync(m->dx + x_up, x + x_up, (size_t)(x_need - x_up) * 8, cudaMemcpyHostToDevice, m->hstream));
+      m->last_h2d += (x_need - x_up) * 8; x_up = x_need;
+    }
+    if (y)
+      for (size_t q = 0; q < lst.size(); q++) {
+        const exb::PatternPlan& p = pl.pats[(size_t)lst[q]];
+        if (p.ir.kind != exb::KIND_CON || p.ir.nitr == 0) continue;
+        // points staged by the window's tiles: range values [cw_lo - cbmax, cw_hi - 1 - cbmin], point k = value - start, row o0 + k
+        long long k0 = cw_lo - p.t_cbmax - p.ir.range_start, k1 = cw_hi - p.t_cbmin - p.ir.range_start;   // [k0, k1)
+        k0 = std::max<long long>(0, k0); k1 = std::min<long long>(p.ir.nitr, k1);
+        if (k1 <= k0) continue;
+        long long r0 = p.o0 + k0, r1 = p.o0 + k1;
+        if (y_up[q] > r0) r0 = y_up[q];
+        if (r1 > r0) {
+          CU_TRY(m, cudaMemcpyAsync(m->dy + r0, y + r0, (size_t)(r1 - r0) * 8, cudaMemcpyHostToDevice, m->hstream));
+          m->last_h2d += (r1 - r0) * 8; y_up[q] = r1;
+        }
+      }
+    {
+      ExbGroup g = L.g;
+      ExbCall cc{}; cc.x = m->dx; cc.y = y ? m->dy : nullptr; cc.th = m->d_theta; cc.sigma = sigma; cc.out = m->dout;
+      ExbTile tt = T0; tt.c_lo = cw_lo; tt.c_hi = cw_hi;
+      void* params[3] = {&g, &cc, &tt};
+      CUresult r = g_drv.LaunchKernel(L.fn, (unsigned)(b1 - b0), 1, 1, (unsigned)pl.block, 1, 1, L.smem, (CUstream)m->hstream, params, nullptr);
+      if (r != CUDA_SUCCESS) return fail(EXB_ERR_CUDA, std::string("windowed launch of ") + KNAME[KN_HESSC] + ": " + cu_err(r));
+      m->launches++; m->last_launches++;
+    }
+    CU_TRY(m, cudaEventRecord(m->hev[(size_t)w], m->hstream));
+    CU_TRY(m, cudaStreamWaitEvent(m->hstream2, m->hev[(size_t)w], 0));
+    const long long q0 = tile_before(T0, cw_lo), q1 = tile_before(T0, cw_hi);
+    if (q1 > q0) {
+      CU_TRY(m, cudaMemcpyAsync(out + q0, m->dout + q0, (size_t)(q1 - q0) * 8, cudaMemcpyDeviceToHost, m->hstream2));
+      m->last_d2h += (q1 - q0) * 8;
+    }
+  }
+  CU_TRY(m, cudaStreamSynchronize(m->hstream2));
+  CU_TRY(m, cudaStreamSynchronize(m->hstream));
+  *done = true;
+  return EXB_OK;
+}
+
 // duplicate-free forms with host buffers: the D2H copy carries the unique entries only (LV: 2N - 1 instead of 9N - 15 doubles)
 int exb_host_jac_compressed(exb_model* m, const double* x, double* out) {
   const double* yy = nullptr;
@@ -1704,6 +1832,7 @@ int exb_host_jac_compressed(exb_model* m, const double* x, double* out) {
 }
 int exb_host_hess_compressed(exb_model* m, const double* x, const double* y, double obj_weight, double* out) {
   const double* yy = y;
+  { EXB_BEGIN EXB_GUARD(m); bool done = false; int prc = host_hessc_pipelined(m, x, y, obj_weight, out, &done); if (prc || done) return prc; EXB_END }
   int64_t sh[3] = {0, 0, 0};
   { int rc0 = exb_compressed_shard(m, sh); if (rc0) return rc0; }
   long long nh = 0;
@@ -1732,6 +1861,53 @@ int exb_host_jac_structure64(exb_model* m, int64_t* rows, int64_t* cols) {
 }
 int exb_host_hess_structure64(exb_model* m, int64_t* rows, int64_t* cols) {
   EXB_BEGIN EXB_GUARD(m); return host_structure(m, KN_HSTRUCT64, m->plan->pl.nnzh, rows, cols); EXB_END
+}
+
+// Tune every kernel now, on scratch outputs: each value callback is called once (its first call is what ranks the variants).
+// x: nvar doubles (device, or host when x_on_host; NULL: all ones); y: ncon device doubles (NULL: all ones).
+static int tune_all(exb_model* m, const double* x, const double* y, bool x_on_host, void* stream) {
+  const exb::Plan& pl = m->plan->pl;
+  cudaStream_t st = (cudaStream_t)stream;
+  double *dx = nullptr, *dy = nullptr, *g = nullptr, *c = nullptr, *jac = nullptr, *hess = nullptr, *obj = nullptr;
+  auto n1 = [](long long n) { return (size_t)(n > 0 ? n : 1) * 8; };
+  static const long long ONE = 0x3ff0000000000000LL;
+  int rc = EXB_OK;
+  cudaError_t e = cudaSuccess;
+  auto al = [&](double** p, long long n) { if (e == cudaSuccess) e = cudaMalloc((void**)p, n1(n)); };
+  al(&dx, pl.m.nvar); al(&dy, pl.ncon); al(&g, pl.m.nvar); al(&c, pl.ncon); al(&jac, pl.nnzj); al(&hess, pl.nnzh); al(&obj, 1);
+  if (e == cudaSuccess) {
+    if (x) e = cudaMemcpyAsync(dx, x, (size_t)pl.m.nvar * 8, x_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st);
+    else e = exb_fx_fill((long long*)dx, pl.m.nvar, ONE, st);
+  }
+  if (e == cudaSuccess) {
+    if (y) e = cudaMemcpyAsync(dy, y, (size_t)pl.ncon * 8, cudaMemcpyDeviceToDevice, st);
+    else e = exb_fx_fill((long long*)dy, pl.ncon, ONE, st);
+  }
+  if (e != cudaSuccess) rc = fail(EXB_ERR_CUDA, std::string("exb_tune: ") + cudaGetErrorString(e));
+  if (!rc) rc = exb_eval(m, EXB_EVAL_ALL, dx, dy, 1.0, obj, g, c, jac, hess, stream);
+  if (!rc) rc = exb_obj_async(m, dx, obj, stream);
+  if (!rc) rc = exb_grad(m, dx, g, stream);
+  if (!rc) rc = exb_cons(m, dx, c, stream);
+  if (!rc) rc = exb_jac(m, dx, jac, stream);
+  if (!rc) rc = exb_hess(m, dx, dy, 1.0, hess, stream);
+  if (!rc && m->hess_tile) rc = exb_hess_compressed(m, dx, dy, 1.0, hess, stream);
+  if (cudaStreamSynchronize(st) != cudaSuccess && !rc) rc = fail(EXB_ERR_CUDA, "exb_tune: kernel failed");
+  for (double* p : {dx, dy, g, c, jac, hess, obj}) if (p) cudaFree(p);
+  m->launches = 0; m->last_launches = 0;
+  return rc;
+}
+int exb_tune(exb_model* m, const double* x, const double* y, void* stream) {
+  EXB_BEGIN
+  EXB_GUARD(m);
+  return tune_all(m, x, y, false, stream);
+  EXB_END
+}
+// out[0..4] = seconds spent in: planning + code generation, nvcc (0 when the module came from the cache), module load + data
+// upload + build-time sorts, tuning so far, exb_create in total
+int exb_build_info(const exb_model* m, double* out5) {
+  if (!m || !out5) return fail(EXB_ERR_HANDLE, "invalid handle");
+  out5[0] = m->plan_s; out5[1] = m->nvcc_s; out5[2] = m->load_s; out5[3] = m->tune_s; out5[4] = m->create_s;
+  return EXB_OK;
 }
 
 // ---- multi-GPU: the communicator of a sharded model (include/exa_b200.h) ----------------------------------------------------

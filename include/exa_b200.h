@@ -69,7 +69,7 @@
 extern "C" {
 #endif
 
-#define EXB_ABI_VERSION 1
+#define EXB_ABI_VERSION 2 /* 2: exb_options.tune_x0 */
 
 enum {
   EXB_OK = 0,
@@ -90,12 +90,18 @@ typedef struct exb_options {
   int32_t world;       /* ... out of `world` contiguous shards (1 = whole model) */
   int32_t flags;       /* EXB_FLAG_* */
   int64_t fuse_below;  /* reserved (every pattern of a callback shares one launch); pass 0 */
+  const double* tune_x0; /* EXB_FLAG_TUNE_AT_CREATE: HOST pointer to nvar doubles to tune at (the model's x0); NULL = all ones */
 } exb_options;
 
 #define EXB_FLAG_NO_COMPILE 1 /* fail instead of invoking nvcc when the module is not cached */
 #define EXB_FLAG_SORTED_PRODUCTS 2 /* exb_jprod / exb_jtprod / exb_hprod: the reference's scheme (COO values into scratch, then
                                      SpMV over a pre-sorted structure, ext:353-511; bitwise reproducible) instead of the default
                                      kernels fused into the derivative sweep (jtprod / hprod use FP64 atomic adds) */
+
+#define EXB_FLAG_TUNE_AT_CREATE 4 /* rank the launch-shape variants of every kernel inside exb_create (on scratch outputs, at
+                                     exb_options.tune_x0), so that no callback ever synchronises; default: each kernel is ranked at
+                                     its first call, which synchronises the stream once.  Verdicts are remembered per (kernel,
+                                     device, grid-size class) next to the cached modules either way. */
 
 /* out[0..7] = nvar ncon nnzj nnzh nobj nnzg nconaug npar
  * (NLPModelMeta fields of src/nlp.jl:765-798 plus the scratch sizes of ext:21-31) */
@@ -131,6 +137,12 @@ int exb_create(const void* ir, size_t ir_bytes, const void* const* host_data, in
                const exb_options* opt, exb_model** out);
 int exb_destroy(exb_model* m);
 int exb_dims(const exb_model* m, int64_t* out8);
+/* rank the launch-shape variants of every kernel now, at the DEVICE vectors x[nvar] / y[ncon] (NULL: all ones), on scratch
+ * outputs; synchronises.  Collective on sharded handles with a communicator.  See EXB_FLAG_TUNE_AT_CREATE. */
+int exb_tune(exb_model* m, const double* x, const double* y, void* stream);
+/* out[0..4] = seconds spent in: planning + code generation, nvcc (0: module came from the cache), module load + data upload +
+ * build-time sorts, tuning so far, exb_create in total */
+int exb_build_info(const exb_model* m, double* out5);
 /* theta: pointer to npar doubles, DEVICE or HOST (cudaMemcpyDefault; copied; set_value!, src/nlp.jl:1217-1287) */
 int exb_set_params(exb_model* m, const double* theta, void* stream);
 

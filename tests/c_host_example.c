@@ -21,7 +21,7 @@ int main(int argc, char** argv) {
   void* ir = slurp(argv[1], &nir);
   double* x = (double*)slurp(argv[2], &nx);
   double* y = (double*)slurp(argv[3], &ny);
-  exb_options opt = {-1, 0, 1, 0, 0};
+  exb_options opt = {-1, 0, 1, 0, 0, NULL};
   exb_model* m = NULL;
   if (exb_create(ir, nir, NULL, 0, &opt, &m)) { fprintf(stderr, "exb_create: %s\n", exb_last_error()); return 1; }
   int64_t d[EXB_NDIMS];

@@ -46,7 +46,7 @@ def test_generated_source_is_model_size_independent():
     a, b = E.Plan(M.luksan_vlcek(100)), E.Plan(M.luksan_vlcek(10_000))
     assert a.source() == b.source() and a.module_path() == b.module_path()
     src = a.source()
-    for kern in ("exb_hess_g0", "exb_jac_g0", "exb_gradt_g0", "exb_cons_g0", "exb_obj_g0", "exb_hstruct64_g0", "exb_eval_g0", "exb_hessc_g0"):
+    for kern in ("exb_hess_g0", "exb_jac_g0", "exb_ggrad_g0", "exb_cons_g0", "exb_obj_g0", "exb_hstruct64_g0", "exb_eval_g0", "exb_hessc_g0"):
         assert f'extern "C" __global__ void __launch_bounds__(EXB_BLOCK, EXB_MINB) {kern}' in src
     assert "sincos" in src and "struct P0" in src and "struct P1" in src
 
@@ -56,28 +56,30 @@ def _has(src, kernel):
 
 
 def test_gradient_kernel_choice(monkeypatch):
-    """Objectives whose slots address x[t + const] (t a range value, or the point number when an AoS iterator carries an iota
-    column) get the tile kernel: a block per tile of variables evaluates the points around it ONCE and gathers their slots in
-    the reference's order.  EXB_NO_TGRAD falls back to the per-variable owner-computes kernel for light bodies; objectives
+    """Three gradient forms, chosen per objective pattern at build time.  Slots that address x[t + const] (t a range value, or the
+    point number when an AoS iterator carries an iota column): (a) a light body that reads no iterator data is re-evaluated
+    once per slot by the per-variable owner-computes kernel (LV); (b) anything else goes to the tile kernel -- a block per tile
+    of variables evaluates the points around it ONCE and gathers their slots in the reference's order.  (c) Objectives
     indexed through iterator data keep the slot + segmented-sum path of the reference (ext:310-336,691-697)."""
     lv = E.Plan(M.luksan_vlcek(50)).source()
-    assert _has(lv, "exb_gradt_g0") is True and _has(lv, "exb_sgrad_g0") is False and _has(lv, "exb_ggrad_g0") is False
+    assert _has(lv, "exb_ggrad_g0") and not _has(lv, "exb_sgrad_g0") and not _has(lv, "exb_gradt_g0")
     # summation order for variable v: point v (slot of x[i]) before point v + 1 (slot of x[i-1]) = ascending slot number
-    gg = lv[lv.rindex("void ggather("):]
-    gg = gg[:gg.index("}")]
-    assert gg.index("ql - (0)") < gg.index("ql - (-1)")
-    fam = E.Plan(M.pattern_family(100, 8)).source()       # `i` column = 1..n: recognised from the data, never loaded
-    assert _has(fam, "exb_gradt_g0") is True and _has(fam, "exb_sgrad_g0") is False
-    opf = E.Plan(M.ac_power(M.synthetic_power_data(30, 41, 6, seed=5))).source()
-    assert _has(opf, "exb_gradt_g0") is True                            # generator cost over pg[g.i], g.i = 1..ngen
-    monkeypatch.setenv("EXB_NO_TGRAD", "1")
-    lv2 = E.Plan(M.luksan_vlcek(50)).source()
-    assert _has(lv2, "exb_ggrad_g0") is True and _has(lv2, "exb_gradt_g0") is False
-    g1 = lv2[lv2.index("double g1("):]
+    g1 = lv[lv.index("double g1("):]
     assert g1.index("s[1] : 0.0") < g1.index("s[0] : 0.0")
+    fam = E.Plan(M.pattern_family(100, 8)).source()       # `i` column = 1..n: recognised from the data, never loaded
+    assert _has(fam, "exb_gradt_g0") and not _has(fam, "exb_sgrad_g0") and not _has(fam, "exb_ggrad_g0")
+    gg = fam[fam.rindex("void ggather("):]
+    gg = gg[:gg.index("}")]
+    assert gg.count("acc[0] +=") >= 1
+    opf = E.Plan(M.ac_power(M.synthetic_power_data(30, 41, 6, seed=5))).source()
+    assert _has(opf, "exb_gradt_g0")                        # generator cost over pg[g.i], g.i = 1..ngen: reads cost data -> tile form
+    monkeypatch.setenv("EXB_NO_TGRAD", "1")
+    fam1 = E.Plan(M.pattern_family(100, 8)).source()
+    assert _has(fam1, "exb_sgrad_g0") and not _has(fam1, "exb_gradt_g0")
+    monkeypatch.delenv("EXB_NO_TGRAD")
     monkeypatch.setenv("EXB_NO_IOTA", "1")
     fam2 = E.Plan(M.pattern_family(100, 8)).source()
-    assert _has(fam2, "exb_sgrad_g0") is True and _has(fam2, "exb_gradt_g0") is False and _has(fam2, "exb_ggrad_g0") is False
+    assert _has(fam2, "exb_sgrad_g0") and not _has(fam2, "exb_gradt_g0") and not _has(fam2, "exb_ggrad_g0")
 
 
 def test_iota_columns_are_recognised_from_the_data(monkeypatch):
@@ -109,7 +111,7 @@ def test_header_symbols_exported():
     lib = B.lib()
     for s in decl:
         assert hasattr(lib, s), f"{s} declared in include/exa_b200.h but not exported"
-    assert lib.exb_abi_version() == 1
+    assert lib.exb_abi_version() == 2
 
 
 def test_malformed_ir_is_rejected():
@@ -216,7 +218,7 @@ def test_kernel_modules_are_cached_compressed(tmp_path, monkeypatch):
     assert raw[:4] == b"\x7fELF" and len(raw) > 5 * os.path.getsize(path + ".gz") / 2
     (tmp_path / "m.cubin").write_bytes(raw)
     out = subprocess.run(["cuobjdump", "-res-usage", str(tmp_path / "m.cubin")], capture_output=True, text=True).stdout
-    for k in ("exb_hess_g0", "exb_jac_g0", "exb_gradt_g0", "exb_cons_g0", "exb_obj_g0", "exb_hprod_g0", "exb_eval_g0", "exb_hessc_g0"):
+    for k in ("exb_hess_g0", "exb_jac_g0", "exb_ggrad_g0", "exb_cons_g0", "exb_obj_g0", "exb_hprod_g0", "exb_eval_g0", "exb_hessc_g0"):
         assert f"Function {k}:" in out
     again = E.Plan(M.luksan_vlcek(31))          # same source: cache hit on the compressed module, nothing recompiled
     t0 = os.path.getmtime(path + ".gz")
@@ -224,3 +226,19 @@ def test_kernel_modules_are_cached_compressed(tmp_path, monkeypatch):
     monkeypatch.setenv("EXB_KEEP_CUBIN", "1")   # development: keep the raw module next to it
     q = E.Plan(M.luksan_vlcek(30, order="guide")).compile()
     assert os.path.exists(q) and os.path.exists(q + ".gz")
+
+
+def test_kernel_pattern_lists_keep_objectives_out_of_the_constraint_kernels():
+    """An objective pattern with a fixed-index variable (no tile / per-variable gradient form) goes to the slot kernel, never
+    to exb_jac_g0 / exb_cons_g0 (regression: a dangling else once put it there and its gradient slot landed in jac[0])."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from edge_models import EDGE
+    src = E.Plan(EDGE["single_points_and_constants"]()).source()
+
+    def lst(kernel):
+        line = next(ln for ln in src.splitlines() if f"EXB_MINB) {kernel}(const ExbGroup" in ln)
+        return re.findall(r"P(\d+)", line[line.index("<"):line.index(">")])
+    assert lst("exb_sgrad_g0") == ["0"] and lst("exb_obj_g0") == ["0"]
+    assert "0" not in lst("exb_jac_g0") and "0" not in lst("exb_cons_g0")
+    assert lst("exb_eval_g0") == [str(k) for k in range(6)]
