@@ -1173,6 +1173,22 @@ static int grad_impl(exb_model* m, const double* x, double* g, cudaStream_t st, 
   }
   if (!pl.k_ggrad.empty()) {   // per-variable form (patterns the tile kernel did not take): one thread per OWNED variable
     ExbCall cg{}; cg.x = x; cg.th = m->d_theta; cg.out = g; cg.v0 = m->v_lo; cg.nout = m->v_hi - m->v_lo; cg.sigma = tiled ? 1.0 : 0.0;
+    if (tiled && m->k[KN_GGRAD].best < 0 && m->k[KN_GGRAD].nblocks > 0) {
+      // on top of the tile kernel's result the launch ACCUMULATES, so it is not idempotent and must not be repeated by the
+      // tuner: rank its variants once in assign mode on a scratch vector (skipped while a graph is being captured)
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+      if (cs == cudaStreamCaptureStatusNone) {
+        double* tmp = nullptr;
+        CU_TRY(m, cudaMalloc((void**)&tmp, (size_t)(pl.m.nvar > 0 ? pl.m.nvar : 1) * 8));
+        ExbCall ct = cg; ct.out = tmp; ct.sigma = 0.0;
+        int trc = tune(m, KN_GGRAD, ct, st);
+        cudaFree(tmp);
+        if (trc) return trc;
+      } else {
+        m->k[KN_GGRAD].best = 0;
+      }
+    }
     int rc = launch(m, KN_GGRAD, cg, st); if (rc) return rc;
   }
   if (!slots_ready) { int rc = launch(m, KN_SGRAD, c, st); if (rc) return rc; }  // kerg, ext:669-679

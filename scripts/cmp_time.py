@@ -4,8 +4,8 @@ sys.path.insert(0, ".")
 import numpy as np, torch
 import examodels_jl_b200 as E
 from examodels_jl_b200 import models as M
-N = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10_000_000
-core = M.luksan_vlcek(N)
+N = int(float(sys.argv[1])) if len(sys.argv) > 1 and sys.argv[1] != "family" else 10_000_000
+core = M.pattern_family(1_000_000, 32) if len(sys.argv) > 1 and sys.argv[1] == "family" else M.luksan_vlcek(N)
 meta = core.meta()
 def timeit(f, n=30):
     for _ in range(5): f()
