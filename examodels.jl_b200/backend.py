@@ -43,7 +43,8 @@ exb_jprod exb_jtprod exb_hprod exb_compressed_dims exb_jac_structure_compressed6
 exb_jac_compressed exb_hess_compressed exb_set_timing exb_timings exb_kernel_choice exb_host_bytes
 exb_comm_unique_id exb_comm_init exb_comm_attach exb_comm_destroy exb_comm_set_mode exb_comm_gather_coo exb_owned
 exb_comm_stats exb_compressed_shard exb_jac_structure_compressed32 exb_hess_structure_compressed32
-exb_host_jac_compressed exb_host_hess_compressed exb_plan_tile exb_eval exb_plan_create_data exb_tune exb_build_info""".split()
+exb_host_jac_compressed exb_host_hess_compressed exb_plan_tile exb_eval exb_plan_create_data exb_tune exb_build_info exb_host_jprod exb_host_jtprod exb_host_hprod
+exb_host_jac_structure32 exb_host_hess_structure32""".split()
 
 
 class ExbError(RuntimeError):
@@ -298,8 +299,9 @@ class ExaModel:
             f = getattr(lib(), f"exb_{which}_structure{64 if rows.dtype == torch.int64 else 32}")
             _check(f(self.h, self._dev(rows, n, rows.dtype), self._dev(cols, n, cols.dtype), self._stream()))
         else:
-            f = getattr(lib(), f"exb_host_{which}_structure64")
-            _check(f(self.h, self._host(rows, n, np.int64), self._host(cols, n, np.int64)))
+            assert rows.dtype == cols.dtype and rows.dtype in (np.int64, np.int32)
+            f = getattr(lib(), f"exb_host_{which}_structure{64 if rows.dtype == np.int64 else 32}")
+            _check(f(self.h, self._host(rows, n, rows.dtype), self._host(cols, n, cols.dtype)))
         return rows, cols
 
     def jac_structure(self, rows, cols):
@@ -310,14 +312,25 @@ class ExaModel:
 
     # -- matrix-free products (src/nlp.jl:1882-1978 | ext:353-511) ---------------------------
     def jprod_nln(self, x, v, Jv):
+        if not _is_torch(x):
+            _check(lib().exb_host_jprod(self.h, self._host(x, self.nvar), self._host(v, self.nvar), self._host(Jv, self.ncon)))
+            return Jv
         _check(lib().exb_jprod(self.h, self._dev(x, self.nvar), self._dev(v, self.nvar), self._dev(Jv, self.ncon), self._stream()))
         return Jv
 
     def jtprod_nln(self, x, v, Jtv):
+        if not _is_torch(x):
+            _check(lib().exb_host_jtprod(self.h, self._host(x, self.nvar), self._host(v, self.ncon), self._host(Jtv, self.nvar)))
+            return Jtv
         _check(lib().exb_jtprod(self.h, self._dev(x, self.nvar), self._dev(v, self.ncon), self._dev(Jtv, self.nvar), self._stream()))
         return Jtv
 
     def hprod(self, x, y, v, Hv, obj_weight=1.0):
+        if not _is_torch(x):
+            yp = None if y is None else self._host(y, self.ncon)
+            _check(lib().exb_host_hprod(self.h, self._host(x, self.nvar), yp, self._host(v, self.nvar), C.c_double(float(obj_weight)),
+                                        self._host(Hv, self.nvar)))
+            return Hv
         yp = None if y is None else self._dev(y, self.ncon)
         _check(lib().exb_hprod(self.h, self._dev(x, self.nvar), yp, self._dev(v, self.nvar), C.c_double(float(obj_weight)),
                                self._dev(Hv, self.nvar), self._stream()))

@@ -89,7 +89,7 @@ struct Plan {
   bool tile_ok = false;
   std::vector<i64> hd;         // distinct row - column distances of the model's Hessian entries, ascending
   std::vector<i64> h_lo, h_len;   // per distance: the ONE interval of (1-based) columns in which the entry exists
-  int tile_halo = 0, tile_ppt = 3;   // tile_ppt: columns per thread (EXB_TUNE_TILE_PPT; measured on LV: 2 -> 0.147, 3 -> 0.142, 4 -> 0.150 ms)
+  int tile_halo = 0, tile_ppt = 3;   // tile_ppt: columns per thread (chosen in build_plan; EXB_TUNE_TILE_PPT overrides)
   int tgrad_halo = 0, tgrad_ppt = 4;   // gradient mode of the tile kernel (exb_gradt_g0)
   bool idx32 = false;          // every index (variables, points, slots) fits 31 bits: address arithmetic in 32 bits
   int block = 128, minb = 16;  // launch shape of the generated kernels (tuning knobs: EXB_TUNE_BLOCK / EXB_TUNE_MINB)
@@ -1015,6 +1015,10 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes, const void* const
     bool any = false; pl.tile_ok = true;
     for (auto& p : pl.pats) { compute_tile(p); if (p.o2step > 0) { any = true; pl.tile_ok = pl.tile_ok && p.tile_ok; } }
     pl.tile_ok = pl.tile_ok && any && getenv("EXB_NO_TILE") == nullptr;
+    // columns per thread: few patterns (LV) -- larger tiles amortise the per-tile prologue (measured 2 -> 0.147, 3 -> 0.142, 4 ->
+    // 0.150 ms); many patterns reading iterator data (32-pattern family) -- small tiles keep more blocks resident to hide the
+    // load latency of each pattern's phase (measured 1 -> 0.291, 2 -> 0.552, 3 -> 0.710 ms)
+    { int nh = 0; for (auto& p : pl.pats) if (p.o2step > 0) nh++; pl.tile_ppt = nh > 4 ? 1 : 3; }
     if (const char* e = getenv("EXB_TUNE_TILE_PPT")) { int v = atoi(e); if (v >= 1 && v <= 8) pl.tile_ppt = v; }
     if (pl.tile_ok) {
       for (auto& p : pl.pats) for (i64 d : p.t2_d) pl.hd.push_back(d);
@@ -1077,6 +1081,7 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes, const void* const
   kern("exb_sgrad_g0", "exb_d1_body", pl.k_sgrad, "");
   kern("exb_ggrad_g0", "exb_ggrad_body", pl.k_ggrad, "");
   if (!pl.k_tgrad.empty()) {
+    pl.tgrad_ppt = pl.k_tgrad.size() > 4 ? 1 : 2;   // same reasoning as tile_ppt
     if (const char* e = getenv("EXB_TUNE_TGRAD_PPT")) { int v = atoi(e); if (v >= 1 && v <= 8) pl.tgrad_ppt = v; }
     o << "extern \"C\" __global__ void __launch_bounds__(EXB_BLOCK, EXB_MINB) exb_gradt_g0(const ExbGroup g, const ExbCall c, const ExbTile t) { "
       << "exb_tile_body<1, 1, " << pl.tgrad_ppt << ", " << plist(pl.k_tgrad) << ">(g, c, t); }\n";

@@ -44,7 +44,7 @@ namespace {
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
-const char* NVCC_FLAGS_CLEAN = "-cubin -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17";
+const char* NVCC_FLAGS_CLEAN = "-cubin -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xptxas -v";   // -v: registers / spills per kernel into <hash>.cubin.log
 
 uint64_t fnv1a(const std::string& s, uint64_t h = 1469598103934665603ULL) {
   for (unsigned char c : s) { h ^= c; h *= 1099511628211ULL; }
@@ -1855,6 +1855,58 @@ int exb_host_hess_compressed(exb_model* m, const double* x, const double* y, dou
   { int64_t t = 0; int rc0 = exb_compressed_dims(m, nullptr, &t); if (rc0) return rc0; nh = t; }
   std::vector<std::pair<long long, long long>> mine = {{(long long)sh[0], (long long)sh[1]}};
   EXB_HOST_VEC(nh, mine, exb_hess_compressed(m, m->dx, y ? m->dy : nullptr, obj_weight, m->dout, m->hstream))
+}
+// matrix-free products with host buffers: x (and y) go up through host_in, the multiplied vector through its own staging
+static int host_vec_in(exb_model* m, const double* v, long long n, double** dv) {
+  *dv = nullptr;
+  CU_TRY(m, cudaMalloc((void**)dv, (size_t)(n > 0 ? n : 1) * 8));
+  cudaError_t e = cudaMemcpyAsync(*dv, v, (size_t)n * 8, cudaMemcpyHostToDevice, m->hstream);
+  if (e != cudaSuccess) { cudaFree(*dv); *dv = nullptr; return fail(EXB_ERR_CUDA, cudaGetErrorString(e)); }
+  m->last_h2d += n * 8;
+  return EXB_OK;
+}
+int exb_host_jprod(exb_model* m, const double* x, const double* v, double* out) {
+  const double* yy = nullptr; double* dv = nullptr;
+  { EXB_BEGIN EXB_GUARD(m); int r0 = host_stream(m); if (r0) return r0; r0 = host_vec_in(m, v, m->plan->pl.m.nvar, &dv); if (r0) return r0; EXB_END }
+  struct Free { double* p; ~Free() { if (p) cudaFree(p); } } fr{dv};
+  EXB_HOST_VEC(pl.ncon, whole(pl.ncon), (m->last_h2d += 0, exb_jprod(m, m->dx, dv, m->dout, m->hstream)))
+}
+int exb_host_jtprod(exb_model* m, const double* x, const double* v, double* out) {
+  const double* yy = nullptr; double* dv = nullptr;
+  { EXB_BEGIN EXB_GUARD(m); int r0 = host_stream(m); if (r0) return r0; r0 = host_vec_in(m, v, m->plan->pl.ncon, &dv); if (r0) return r0; EXB_END }
+  struct Free { double* p; ~Free() { if (p) cudaFree(p); } } fr{dv};
+  EXB_HOST_VEC(pl.m.nvar, whole(pl.m.nvar), exb_jtprod(m, m->dx, dv, m->dout, m->hstream))
+}
+int exb_host_hprod(exb_model* m, const double* x, const double* y, const double* v, double obj_weight, double* out) {
+  const double* yy = y; double* dv = nullptr;
+  { EXB_BEGIN EXB_GUARD(m); int r0 = host_stream(m); if (r0) return r0; r0 = host_vec_in(m, v, m->plan->pl.m.nvar, &dv); if (r0) return r0; EXB_END }
+  struct Free { double* p; ~Free() { if (p) cudaFree(p); } } fr{dv};
+  EXB_HOST_VEC(pl.m.nvar, whole(pl.m.nvar), exb_hprod(m, m->dx, y ? m->dy : nullptr, dv, obj_weight, m->dout, m->hstream))
+}
+}  // extern "C"
+template <typename I>
+static int host_structure_t(exb_model* m, int kn, long long n, I* rows, I* cols) {
+  int rc = host_stream(m); if (rc) return rc;
+  I *dr = nullptr, *dc = nullptr;
+  CU_TRY(m, cudaMalloc((void**)&dr, (size_t)(n ? n : 1) * sizeof(I)));
+  cudaError_t e = cudaMalloc((void**)&dc, (size_t)(n ? n : 1) * sizeof(I));
+  if (e != cudaSuccess) { cudaFree(dr); return fail(EXB_ERR_CUDA, cudaGetErrorString(e)); }
+  rc = structure(m, kn, dr, dc, m->hstream);
+  if (!rc) {
+    cudaMemcpyAsync(rows, dr, (size_t)n * sizeof(I), cudaMemcpyDeviceToHost, m->hstream);
+    cudaMemcpyAsync(cols, dc, (size_t)n * sizeof(I), cudaMemcpyDeviceToHost, m->hstream);
+    e = cudaStreamSynchronize(m->hstream);
+    if (e != cudaSuccess) rc = fail(EXB_ERR_CUDA, cudaGetErrorString(e));
+  }
+  cudaFree(dr); cudaFree(dc);
+  return rc;
+}
+extern "C" {
+int exb_host_jac_structure32(exb_model* m, int32_t* rows, int32_t* cols) {
+  EXB_BEGIN EXB_GUARD(m); return host_structure_t<int32_t>(m, KN_JSTRUCT32, m->plan->pl.nnzj, rows, cols); EXB_END
+}
+int exb_host_hess_structure32(exb_model* m, int32_t* rows, int32_t* cols) {
+  EXB_BEGIN EXB_GUARD(m); return host_structure_t<int32_t>(m, KN_HSTRUCT32, m->plan->pl.nnzh, rows, cols); EXB_END
 }
 static int host_structure(exb_model* m, int kn, long long n, int64_t* rows, int64_t* cols) {
   int rc = host_stream(m); if (rc) return rc;

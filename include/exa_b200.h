@@ -230,6 +230,11 @@ int exb_host_hess(exb_model* m, const double* x, const double* y, double obj_wei
 /* duplicate-free forms: the D2H copy carries the unique entries only */
 int exb_host_jac_compressed(exb_model* m, const double* x, double* vals);
 int exb_host_hess_compressed(exb_model* m, const double* x, const double* y, double obj_weight, double* vals);
+int exb_host_jprod(exb_model* m, const double* x, const double* v, double* Jv);
+int exb_host_jtprod(exb_model* m, const double* x, const double* v, double* Jtv);
+int exb_host_hprod(exb_model* m, const double* x, const double* y, const double* v, double obj_weight, double* Hv);
+int exb_host_jac_structure32(exb_model* m, int32_t* rows, int32_t* cols);   /* the AOT path passes Cint (ExaModelsCompiler.jl:1650-1668) */
+int exb_host_hess_structure32(exb_model* m, int32_t* rows, int32_t* cols);
 int exb_host_jac_structure64(exb_model* m, int64_t* rows, int64_t* cols);
 int exb_host_hess_structure64(exb_model* m, int64_t* rows, int64_t* cols);
 

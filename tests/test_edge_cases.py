@@ -80,3 +80,14 @@ def test_gpu_edge_models_match_oracle(exa, name):
     # host-buffer shims on ragged sizes
     hh = np.full(m.nnzh, np.nan); assert_close(m.hess_coord(x, y, hh, obj_weight=0.7), ora.hess_coord(x, y, 0.7), "host hess")
     cc = np.full(m.ncon, np.nan); assert_close(m.cons_nln(x, cc), ora.cons(x), "host cons")
+    if m.ncon and m.nnzj:   # products and 32-bit structures through the host shims
+        vh = np.random.default_rng(3).standard_normal(m.nvar); wh = np.random.default_rng(4).standard_normal(m.ncon)
+        assert_close(m.jprod_nln(x, vh, np.full(m.ncon, np.nan)), ora.jprod(x, vh), "host jprod")
+        assert_close(m.jtprod_nln(x, wh, np.full(m.nvar, np.nan)), ora.jtprod(x, wh), "host jtprod")
+        assert_close(m.hprod(x, y, vh, np.full(m.nvar, np.nan), obj_weight=0.7), ora.hprod(x, y, vh, 0.7), "host hprod")
+        r32, c32 = np.zeros(m.nnzj, dtype=np.int32), np.zeros(m.nnzj, dtype=np.int32)
+        m.jac_structure(r32, c32)
+        assert np.array_equal(r32.astype(np.int64), jr) and np.array_equal(c32.astype(np.int64), jc)
+    r32, c32 = np.zeros(m.nnzh, dtype=np.int32), np.zeros(m.nnzh, dtype=np.int32)
+    m.hess_structure(r32, c32)
+    assert np.array_equal(r32.astype(np.int64), hr) and np.array_equal(c32.astype(np.int64), hc)
