@@ -1,0 +1,62 @@
+"""Launch-shape tuning (csrc/exb_runtime.cpp tune / tune_all): explicit (exb_tune, EXB_FLAG_TUNE_AT_CREATE) so that no solver
+callback synchronises, verdicts remembered per (kernel, device, grid-size class), stable across re-creations."""
+import os
+
+import numpy as np
+import pytest
+
+from util import assert_close, inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def test_tune_at_create_leaves_nothing_to_tune(exa, tmp_path, monkeypatch):
+    import shutil
+    import torch
+    from examodels_jl_b200 import models as M
+    from oracle.oracle_api import Oracle
+    # a private cache: modules copied from the tree's cache (no nvcc), no tuning verdicts yet
+    src = os.path.join(os.path.dirname(exa.backend.__file__), "_kcache")
+    core = M.luksan_vlcek(30_000)
+    mod = os.path.basename(exa.Plan(core).module_path())
+    os.makedirs(tmp_path / "kc")
+    for f in os.listdir(src):
+        if f.endswith(".cubin.gz"):
+            shutil.copy(os.path.join(src, f), tmp_path / "kc" / f)
+    monkeypatch.setenv("EXB_CACHE_DIR", str(tmp_path / "kc"))
+    m = exa.ExaModel(core, tune_at_create=True)
+    info = m.build_info()
+    assert info["tune_s"] > 0 and info["nvcc_s"] == 0 and info["create_s"] >= info["tune_s"]
+    for cb in ("obj", "grad", "cons", "jac", "hess"):
+        assert m.kernel_choice(cb)["min_blocks"] in (16, 12, 1)          # every callback kernel has its verdict
+    tune_files = [f for f in os.listdir(tmp_path / "kc") if f.endswith(".tune")]
+    assert len(tune_files) == 1
+    lines = open(tmp_path / "kc" / tune_files[0]).read().split("\n")
+    assert any(ln.startswith("exb_hess_g0@NVIDIA_B200@") for ln in lines) and any(ln.startswith("exb_eval_g0@") for ln in lines)
+    # first callbacks: one launch each, results right
+    ora = Oracle.from_core(core)
+    x, y = inputs(core)
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    h = m.hess_coord(dx, dy, m.new(m.nnzh))
+    assert m.stats()["last_launches"] == 1
+    assert_close(h.cpu().numpy(), ora.hess_coord(x, y, 1.0), "hess after tune-at-create")
+    # a second handle of the same model on the same device reads the verdicts: same choice, no tuning time
+    choice = {cb: m.kernel_choice(cb)["min_blocks"] for cb in ("obj", "grad", "cons", "jac", "hess")}
+    m2 = exa.ExaModel(core)
+    assert m2.build_info()["tune_s"] == 0
+    assert {cb: m2.kernel_choice(cb)["min_blocks"] for cb in choice} == choice
+    assert mod
+
+
+def test_explicit_tune_call(exa):
+    import torch
+    from examodels_jl_b200 import models as M
+    core = M.ac_power(M.synthetic_power_data(300, 420, 70, seed=2))
+    m = exa.ExaModel(core)
+    x, y = inputs(core)
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    m.tune(dx, dy)
+    assert all(m.kernel_choice(cb)["min_blocks"] in (16, 12, 1) for cb in ("obj", "cons", "jac", "hess"))
+    t0 = m.build_info()["tune_s"]
+    g = m.grad(dx, m.new(m.nvar))
+    assert m.build_info()["tune_s"] == t0 and np.isfinite(g.cpu().numpy()).all()
