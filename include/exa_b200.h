@@ -25,7 +25,13 @@
  *   - work is enqueued on the caller's stream and NOT synchronised, except where a
  *     scalar is returned to the host (`exb_obj`), mirroring the KA callbacks, which
  *     never call `synchronize`;
- *   - a handle is thread-compatible (one caller at a time); handles are independent.
+ *   - a handle is thread-compatible (one caller at a time, on ONE stream at a time: its scratch -- conbuffer, gradient buffer,
+ *     objective partials, host staging -- is per handle, so `exb_cons` on one stream and `exb_jprod` on another would race);
+ *     handles are independent;
+ *   - the first call of a value callback ranks the launch-shape variants of its kernel and synchronises the stream ONCE
+ *     (exb_tune / EXB_FLAG_TUNE_AT_CREATE move that to model build);
+ *   - parity with the reference is defined on finite points: multiplications by the structural zeros of the linear operators are
+ *     folded at build time, so a non-finite adjoint yields 0 where the reference's literal `adj * zero(x)` yields NaN.
  *
  * There is no CPU fallback: every evaluation entry point fails with EXB_ERR_CUDA if
  * no sm_100 device / kernel module is available.
