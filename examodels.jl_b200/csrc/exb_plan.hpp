@@ -84,6 +84,11 @@ struct Plan {
   std::string error;
   // pattern lists per kernel (indices into pats), fixed at generation time
   std::vector<int> k_hess, k_jac, k_sgrad, k_ggrad, k_cons, k_obj, k_aug, k_eval, k_tgrad;
+  // launch entries of exb_hess_g0: a pattern with many second-order slots per point (the 47-slot dynamics row of the COPS rocket:
+  // 108 registers and a 48 KB tile per block -> 4 blocks per SM) CAN be split into two entries that evaluate the same points but
+  // keep / stage / store one half of the slots each [w0, w1): the other half is dead code in that entry, registers and tile
+  // shrink; the forward sweep is done twice.  Opt-in: measured slower (see the kernel-list loop in build_plan)
+  std::vector<int> k_hess_l; std::vector<std::pair<int, int>> k_hess_w;
   bool hess_windowed = false;  // every Hessian pattern has an x window: the persistent kernel exb_hessp_g0 is generated too
   // duplicate-free Hessian emitted directly (exb_hessc_g0): possible when every pattern with second-order slots is tile_ok
   bool tile_ok = false;
@@ -930,6 +935,7 @@ inline std::string gen_pattern(PatternPlan& p, int index, bool windowed, const s
     emit_fn(o, "void s2(" + A + ", long long (&r)[" + std::to_string(a2) + "], long long (&c)[" + std::to_string(a2) + "])", B, tail);
   }
   o << "  static constexpr int PPT0 = " << p.ppt0 << ", PPT1 = " << p.ppt1 << ", PPT2 = " << p.ppt2 << ";\n";
+  o << "  static constexpr int W0 = 0, W1 = " << ns2 << ";   // window of second-order slots an exb_hess_g0 entry keeps (ExbSplit narrows it)\n";
   o << "};\n";
   return o.str();
 }
@@ -1058,7 +1064,18 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes, const void* const
   // kernel pattern lists
   for (size_t k = 0; k < pl.pats.size(); k++) {
     const PatternPlan& p = pl.pats[k];
-    if (p.o2step > 0) pl.k_hess.push_back((int)k);
+    if (p.o2step > 0) {
+      pl.k_hess.push_back((int)k);
+      // opt-in (EXB_TUNE_SPLIT_NS = slots per point above which a pattern is split): MEASURED SLOWER on the rocket nh = 1e6 --
+      // hess_coord! 0.117 ms split (90 registers, 5 blocks / SM) against 0.101 ms whole (108 registers, 4 blocks / SM); 0.110 /
+      // 0.115 ms with 85- / 64-register builds: the second forward sweep and the row-wise stores cost more than the occupancy buys
+      const int split_ns = getenv("EXB_TUNE_SPLIT_NS") ? atoi(getenv("EXB_TUNE_SPLIT_NS")) : 0;
+      if (split_ns > 0 && p.o2step > split_ns) {
+        const int h = (p.o2step + 1) / 2;
+        pl.k_hess_l.push_back((int)k); pl.k_hess_w.push_back({0, h});
+        pl.k_hess_l.push_back((int)k); pl.k_hess_w.push_back({h, p.o2step});
+      } else { pl.k_hess_l.push_back((int)k); pl.k_hess_w.push_back({0, p.o2step}); }
+    }
     if (p.ir.kind == KIND_OBJ) { pl.k_obj.push_back((int)k); if (p.o1step > 0) (p.tgrad ? pl.k_tgrad : p.gather1 ? pl.k_ggrad : pl.k_sgrad).push_back((int)k); }
     else { pl.k_cons.push_back((int)k); if (p.o1step > 0) pl.k_jac.push_back((int)k); }
     if (p.tgrad) pl.tgrad_halo = std::max(pl.tgrad_halo, (int)(p.g_cbmax - p.g_cbmin));
@@ -1070,7 +1087,18 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes, const void* const
     o << "extern \"C\" __global__ void __launch_bounds__(EXB_BLOCK, EXB_MINB) " << name << "(const ExbGroup g, const ExbCall c) { "
       << body << "<" << targ << plist(v) << ">(g, c); }\n";
   };
-  kern("exb_hess_g0", "exb_hess_body", pl.k_hess, "");
+  if (pl.k_hess_l.size() != pl.k_hess.size()) pl.hess_windowed = false;   // the (opt-in) persistent form knows no split entries
+  if (!pl.k_hess_l.empty()) {
+    std::string lst;
+    for (size_t q = 0; q < pl.k_hess_l.size(); q++) {
+      const int k = pl.k_hess_l[q];
+      const bool whole = pl.k_hess_w[q].first == 0 && pl.k_hess_w[q].second == pl.pats[(size_t)k].o2step;
+      if (q) lst += ", ";
+      lst += whole ? "P" + std::to_string(k)
+                   : "ExbSplit<P" + std::to_string(k) + ", " + std::to_string(pl.k_hess_w[q].first) + ", " + std::to_string(pl.k_hess_w[q].second) + ">";
+    }
+    o << "extern \"C\" __global__ void __launch_bounds__(EXB_BLOCK, EXB_MINB) exb_hess_g0(const ExbGroup g, const ExbCall c) { exb_hess_body<" << lst << ">(g, c); }\n";
+  }
   if (pl.tile_ok) {
     o << "extern \"C\" __global__ void __launch_bounds__(EXB_BLOCK, EXB_MINB) exb_hessc_g0(const ExbGroup g, const ExbCall c, const ExbTile t) { "
       << "exb_tile_body<2, " << pl.hd.size() << ", " << pl.tile_ppt << ", " << plist(pl.k_hess) << ">(g, c, t); }\n";

@@ -186,7 +186,8 @@ struct exb_plan {
   bool from_cache = false;
   const std::vector<int>& list(int kn) const {
     switch (kn) {
-      case KN_HESS: case KN_HSTRUCT64: case KN_HSTRUCT32: case KN_HPROD: case KN_HESSC: return pl.k_hess;
+      case KN_HESS: return pl.k_hess_l;
+      case KN_HSTRUCT64: case KN_HSTRUCT32: case KN_HPROD: case KN_HESSC: return pl.k_hess;
       case KN_JAC: case KN_JSTRUCT64: case KN_JSTRUCT32: case KN_JPROD: case KN_JTPROD: return pl.k_jac;
       case KN_SGRAD: case KN_GSTRUCT64: return pl.k_sgrad;
       case KN_GGRAD: return pl.k_ggrad;
@@ -709,6 +710,10 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       nb[q] = (args[q].n + BLK * ppt - 1) / (BLK * ppt);
       tot += nb[q]; if (nb[q] > maxnb) maxnb = nb[q];
       int ns = kn == KN_EVAL ? p.o1step + p.o2step : k2 ? p.o2step : k1 ? p.o1step : 1;
+      if (kn == KN_HESS) {   // a split entry stages only its window of slots (rows padded to an odd word count)
+        const int nw = pl.k_hess_w[q].second - pl.k_hess_w[q].first;
+        if (nw != p.o2step) ns = nw | 1;
+      }
       if (ns <= EXB_TILE_MAX_NS && ns * ppt > maxns) maxns = ns * ppt;   // tile words per thread
     }
     if (kn == KN_HESSC || kn == KN_GRADT) {   // one block per tile of T consecutive COLUMNS of the owned range (exb_tile_body), no block -> pattern map

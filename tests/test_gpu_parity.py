@@ -337,3 +337,23 @@ def test_cuda_path_replays_the_reference_ipopt_logs(exa, torch_):
         m.set_params(run["theta"])
         rows, final, _, _ = newton_kkt_replay(cb, core.meta()["x0"], len(run["iterations"]) - 1)
         check_ipopt_run(run, rows, final)
+
+
+def test_split_hessian_pattern(exa, torch_, monkeypatch):
+    """Opt-in (EXB_TUNE_SPLIT_NS): a pattern with many second-order slots per point is evaluated by two launch entries that keep
+    one half of its slots each (csrc/exb_device.cuh ExbSplit / exb_store_rows; measured slower on the rocket, hence opt-in):
+    same vector as the whole-pattern kernel, bit for bit, incl. ragged tiles and a sharded handle."""
+    from examodels_jl_b200 import models as M
+    torch = torch_
+    core = M.goddard_rocket(50)
+    x, y = inputs(core)
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    whole = exa.ExaModel(core)
+    ref = whole.hess_coord(dx, dy, whole.new(whole.nnzh).fill_(float("nan")), obj_weight=0.7)
+    monkeypatch.setenv("EXB_TUNE_SPLIT_NS", "32")
+    assert "ExbSplit<P2, 0, 24>, ExbSplit<P2, 24, 47>" in exa.Plan(core).source()
+    for kw in ({}, dict(rank=1, world=2)):
+        split = exa.ExaModel(core, **kw)
+        got = split.hess_coord(dx, dy, split.new(split.nnzh).fill_(float("nan")), obj_weight=0.7)
+        mine = ~torch.isnan(got)
+        assert mine.any() and (kw or mine.all()) and torch.equal(got[mine], ref[mine])

@@ -60,3 +60,21 @@ def test_explicit_tune_call(exa):
     t0 = m.build_info()["tune_s"]
     g = m.grad(dx, m.new(m.nvar))
     assert m.build_info()["tune_s"] == t0 and np.isfinite(g.cpu().numpy()).all()
+
+
+def test_choice_is_stable_over_repeated_creates(exa):
+    """A latency-bound model (AC-OPF: every kernel is a few microseconds, where a single timing would rank the variants at
+    random): the first handle ranks them (median of 5-9 runs) and remembers the verdict whatever the kernel's duration; the next
+    20 handles of the same model on the same device launch the same variants and never tune."""
+    import torch
+    from examodels_jl_b200 import models as M
+    core = M.ac_power(M.synthetic_power_data(300, 420, 70, seed=2))
+    x, y = inputs(core)
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    first = exa.ExaModel(core)
+    first.tune(dx, dy)
+    ref = {cb: first.kernel_choice(cb)["min_blocks"] for cb in ("obj", "grad", "cons", "jac", "hess")}
+    assert all(v in (16, 12, 1) for v in ref.values())
+    for _ in range(20):
+        m = exa.ExaModel(core)
+        assert {cb: m.kernel_choice(cb)["min_blocks"] for cb in ref} == ref and m.build_info()["tune_s"] == 0
