@@ -242,3 +242,45 @@ def test_kernel_pattern_lists_keep_objectives_out_of_the_constraint_kernels():
     assert lst("exb_sgrad_g0") == ["0"] and lst("exb_obj_g0") == ["0"]
     assert "0" not in lst("exb_jac_g0") and "0" not in lst("exb_cons_g0")
     assert lst("exb_eval_g0") == [str(k) for k in range(6)]
+
+
+def test_ir_validation_rejects_what_the_round_1_review_listed():
+    """Unknown iterator kind / field type, DATA_SELF on an AoS iterator, DATA_FIELD on a range, a field that sticks out of its
+    element, negative nvar: EXB_ERR_IR (3) with a message, never a crash or a silent misread."""
+    import struct
+    lib = B.lib()
+
+    def create(words):
+        ir = struct.pack(f"<{len(words)}q", *words)
+        h = C.c_void_p()
+        rc = lib.exb_plan_create(ir, C.c_size_t(len(ir)), None, C.byref(h))
+        if rc == 0:
+            lib.exb_plan_destroy(h)
+        return rc, lib.exb_last_error().decode()
+
+    def words_of(core):
+        ir, _ = core.to_ir()
+        return list(struct.unpack(f"<{len(ir) // 8}q", ir))
+    lv = words_of(M.luksan_vlcek(10))
+    assert create(lv)[0] == 0
+    bad = list(lv); bad[2] = -5                      # nvar
+    assert create(bad) == (3, "negative nvar / npar")
+    bad = list(lv); bad[8] = 7                       # itr_kind of pattern 0 (header 6 words; kind, nitr, itr_kind)
+    assert create(bad)[0] == 3 and "iterator kind" in create(bad)[1]
+    d = np.zeros(4, dtype=np.dtype([("i", "i8"), ("a", "f8")])); d["i"] = [1, 2, 3, 4]
+    c = E.ExaCore(); x = c.add_var(6); c.add_obj(lambda q: q.a * x[q.i] ** 2, d)
+    aos = words_of(c)
+    assert create(aos)[0] == 0
+    k = 6 + 6                                        # header + (kind nitr itr_kind start databuf stride) -> nfields
+    assert aos[k] == 2
+    bad = list(aos); bad[k + 2] = 9                  # type of field 0
+    assert create(bad)[0] == 3 and "field type" in create(bad)[1]
+    bad = list(aos); bad[k + 1] = 12                 # byte offset of field 0: 12 + 8 > stride 16
+    assert create(bad)[0] == 3 and "outside the iterator element" in create(bad)[1]
+    # a DATA_SELF node inside an AoS pattern (tag 2): patch the first DATA_FIELD node (tag 3) of the tree
+    nn = k + 1 + 2 * 2 + 4 + 1                       # fields, o0 o1 o2 base, nidx(=0)
+    nnodes = aos[nn]
+    nodes = nn + 1
+    j = next(q for q in range(nnodes) if aos[nodes + 4 * q] == 3)
+    bad = list(aos); bad[nodes + 4 * j] = 2
+    assert create(bad)[0] == 3 and "DATA_SELF" in create(bad)[1]
