@@ -1368,8 +1368,11 @@ int ensure_buffers(exb_model* m, int passes = 3) {
 
 // which: 1 = products (row- and column-sorted), 2 = compressed (sorted by (col, row)); passes: bit 0 Jacobian, bit 1 Hessian
 int ensure_sorted(exb_model* m, int which, int passes = 3) {
-  if (m->world != 1) return fail(EXB_ERR_ARG, "the sorted-structure forms (EXB_FLAG_SORTED_PRODUCTS products, duplicate-free COO of models that are not "
-                                              "shift-indexed) are not available on sharded handles");
+  // products: a sharded handle sorts the slots of ITS points only (everything else carries the sentinel key and is dropped), so its
+  // deterministic SpMV yields the shard's partial product.  The duplicate-free COO through the sorted list would need the
+  // duplicates of different shards summed: single handle only (shift-indexed models use the tile kernel, which shards).
+  if (m->world != 1 && which == 2) return fail(EXB_ERR_ARG, "the duplicate-free COO of a model that is not shift-indexed is built from a sorted "
+                                                           "list of ALL slots: not available on sharded handles");
   if (which == 1) { if (m->prod_ready) return EXB_OK; passes = 3; }
   if (which == 2) { if (m->cmpj_ready) passes &= ~1; if (m->cmp_ready) passes &= ~2; if (!passes) return EXB_OK; }
   const exb::Plan& pl = m->plan->pl;
@@ -1383,6 +1386,11 @@ int ensure_sorted(exb_model* m, int which, int passes = 3) {
     CU_TRY(m, cudaMalloc((void**)&rows, (size_t)n * 8));
     cudaError_t e1 = cudaMalloc((void**)&cols, (size_t)n * 8), e2 = cudaMalloc((void**)&keys, (size_t)n * 8);
     rc = (e1 != cudaSuccess || e2 != cudaSuccess) ? fail(EXB_ERR_CUDA, "out of device memory building the sorted structure") : EXB_OK;
+    if (!rc && m->world > 1) {   // slots of other shards: sentinel keys (the structure kernels write this handle's points only)
+      cudaError_t ef = exb_fx_fill(rows, n, EXB_FX_SENTINEL, 0);
+      if (ef == cudaSuccess) ef = exb_fx_fill(cols, n, EXB_FX_SENTINEL, 0);
+      if (ef != cudaSuccess) rc = fail(EXB_ERR_CUDA, cudaGetErrorString(ef));
+    }
     if (!rc) rc = structure_raw(m, pass == 0 ? KN_JSTRUCT64 : KN_HSTRUCT64, rows, cols, 0);
     if (!rc && cudaStreamSynchronize(0) != cudaSuccess) rc = fail(EXB_ERR_CUDA, "structure kernel failed");
     if (!rc && which == 1) {
@@ -1437,7 +1445,8 @@ int exb_jprod(exb_model* m, const double* x, const double* v, double* Jv, void* 
   int rc = ensure_sorted(m, 1); if (rc) return rc;
   rc = exb_jac(m, x, m->d_jacbuf, stream); if (rc) return rc;
   CU_TRY(m, cudaMemsetAsync(Jv, 0, (size_t)pl.ncon * 8, st));
-  return spmv(m, m->jrow, m->d_jacbuf, v, Jv, 0, 0, st);                 // kerspmv, ext:482-488
+  rc = spmv(m, m->jrow, m->d_jacbuf, v, Jv, 0, 0, st); if (rc) return rc;   // kerspmv, ext:482-488
+  return comm_on(m) ? comm_allreduce(m, Jv, pl.ncon, st) : EXB_OK;
   EXB_END
 }
 int exb_jtprod(exb_model* m, const double* x, const double* v, double* Jtv, void* stream) {
@@ -1455,7 +1464,8 @@ int exb_jtprod(exb_model* m, const double* x, const double* v, double* Jtv, void
   int rc = ensure_sorted(m, 1); if (rc) return rc;
   rc = exb_jac(m, x, m->d_jacbuf, stream); if (rc) return rc;
   CU_TRY(m, cudaMemsetAsync(Jtv, 0, (size_t)pl.m.nvar * 8, st));
-  return spmv(m, m->jcol, m->d_jacbuf, v, Jtv, 0, 0, st);                // kerspmv2, ext:489-495
+  rc = spmv(m, m->jcol, m->d_jacbuf, v, Jtv, 0, 0, st); if (rc) return rc;   // kerspmv2, ext:489-495
+  return comm_on(m) ? comm_allreduce(m, Jtv, pl.m.nvar, st) : EXB_OK;
   EXB_END
 }
 int exb_hprod(exb_model* m, const double* x, const double* y, const double* v, double obj_weight, double* Hv, void* stream) {
@@ -1474,7 +1484,8 @@ int exb_hprod(exb_model* m, const double* x, const double* y, const double* v, d
   rc = exb_hess(m, x, y, obj_weight, m->d_hessbuf, stream); if (rc) return rc;
   CU_TRY(m, cudaMemsetAsync(Hv, 0, (size_t)pl.m.nvar * 8, st));
   rc = spmv(m, m->hrow, m->d_hessbuf, v, Hv, 0, 0, st); if (rc) return rc;   // lower triangle incl. diagonal (kersyspmv, ext:496-503)
-  return spmv(m, m->hcol, m->d_hessbuf, v, Hv, 1, 1, st);                    // transpose of the strict lower part (kersyspmv2, ext:504-511)
+  rc = spmv(m, m->hcol, m->d_hessbuf, v, Hv, 1, 1, st); if (rc) return rc;   // transpose of the strict lower part (kersyspmv2, ext:504-511)
+  return comm_on(m) ? comm_allreduce(m, Hv, pl.m.nvar, st) : EXB_OK;
   EXB_END
 }
 

@@ -195,7 +195,8 @@ int exb_eval(exb_model* m, unsigned mask, const double* x, const double* y, doub
  * (deterministic), jtprod and hprod add into the pre-zeroed output with FP64 atomics; nothing of size nnzj / nnzh is
  * written or read and sharded handles return their partial sums.  With EXB_FLAG_SORTED_PRODUCTS: the reference's scheme,
  * COO values into a buffer owned by the handle, multiplied through row- / column-sorted copies of the structure (built on
- * first use, ext:56-175); bitwise reproducible; not available on sharded handles. */
+ * first use, ext:56-175); bitwise reproducible; a sharded handle sorts the slots of its own points and returns the shard's partial
+ * product (completed by the all-reduce when a communicator is attached). */
 int exb_jprod(exb_model* m, const double* x, const double* v, double* Jv, void* stream);    /* Jv[ncon]  */
 int exb_jtprod(exb_model* m, const double* x, const double* v, double* Jtv, void* stream);  /* Jtv[nvar] */
 int exb_hprod(exb_model* m, const double* x, const double* y, const double* v, double obj_weight, double* Hv,

@@ -68,6 +68,32 @@ def test_fused_products_on_a_sharded_handle(exa):
     assert_close(Hv.cpu().numpy(), ora.hprod(x, y, v, 0.7), "sharded hprod")
 
 
+def test_sorted_products_on_a_sharded_handle_are_deterministic(exa):
+    """EXB_FLAG_SORTED_PRODUCTS on sharded handles: every rank sorts the slots of its own points, its SpMV has a fixed summation
+    order (no atomics), the partial products add up to the full product and repeat bit for bit."""
+    import torch
+    from examodels_jl_b200 import models as M
+    from oracle.oracle_api import Oracle
+    for core in (M.luksan_vlcek_aug(21, 3), M.ac_power(M.synthetic_power_data(300, 420, 70, seed=2))):
+        ora = Oracle.from_core(core)
+        x, y = inputs(core)
+        rng = np.random.default_rng(12)
+        v, w = rng.standard_normal(ora.nvar), rng.standard_normal(ora.ncon)
+        dx, dy, dv, dw = (torch.from_numpy(a).cuda() for a in (x, y, v, w))
+        Jv, Jtw, Hv = (torch.zeros(n, dtype=torch.float64, device="cuda") for n in (ora.ncon, ora.nvar, ora.nvar))
+        for r in range(3):
+            m = exa.ExaModel(core, rank=r, world=3, sorted_products=True)
+            a = m.hprod(dx, dy, dv, m.new(m.nvar), obj_weight=0.7)
+            b = m.hprod(dx, dy, dv, m.new(m.nvar), obj_weight=0.7)
+            assert torch.equal(a, b)
+            t1 = m.jtprod_nln(dx, dw, m.new(m.nvar)); t2 = m.jtprod_nln(dx, dw, m.new(m.nvar))
+            assert torch.equal(t1, t2)
+            Jv += m.jprod_nln(dx, dv, m.new(m.ncon)); Jtw += t1; Hv += a
+        assert_close(Jv.cpu().numpy(), ora.jprod(x, v), "sharded sorted jprod")
+        assert_close(Jtw.cpu().numpy(), ora.jtprod(x, w), "sharded sorted jtprod")
+        assert_close(Hv.cpu().numpy(), ora.hprod(x, y, v, 0.7), "sharded sorted hprod")
+
+
 def _compress_ref(rows, cols, vals):
     """src/utils.jl:478-487,564-579: stable sort of ((col,row), k) by (col,row); unique runs; sum in slot order."""
     order = np.lexsort((rows, cols))          # primary key col, secondary row; lexsort is stable
