@@ -1685,8 +1685,17 @@ static int host_coo_pipelined(exb_model* m, int kn, const double* x, const doubl
   rc = ensure_host(m, &m->hx, &m->hx_n, &m->dx, &m->dx_n, 0, (size_t)pl.m.nvar); if (rc) return rc;
   if (y) { rc = ensure_host(m, &m->hy, &m->hy_n, &m->dy, &m->dy_n, 0, (size_t)pl.ncon); if (rc) return rc; }
   rc = ensure_host(m, &m->hout, &m->hout_n, &m->dout, &m->dout_n, 0, (size_t)total); if (rc) return rc;
-  if (m->x_hi > m->x_lo) CU_TRY(m, cudaMemcpyAsync(m->dx + m->x_lo, x + m->x_lo, (size_t)(m->x_hi - m->x_lo) * 8, cudaMemcpyHostToDevice, m->hstream));
-  m->last_h2d = (m->x_hi - m->x_lo) * 8; m->last_d2h = 0;
+  // x: when every listed pattern is shift-indexed (variables = range value + const, no fixed-index variable) a window of points
+  // reads a window of x, so x goes up window by window too (only the first window's piece is not overlapped with a download);
+  // otherwise indices are data and x goes first and whole
+  bool xwin = true;
+  for (int pi : lst) { const exb::PatternPlan& p = pl.pats[(size_t)pi]; if (!p.xr_ok || p.xr_fixed || !p.xr_shift) xwin = false; }
+  long long x_up = m->x_lo;   // x[x_lo, x_up) is on the device
+  m->last_h2d = 0; m->last_d2h = 0;
+  if (!xwin && m->x_hi > m->x_lo) {
+    CU_TRY(m, cudaMemcpyAsync(m->dx + m->x_lo, x + m->x_lo, (size_t)(m->x_hi - m->x_lo) * 8, cudaMemcpyHostToDevice, m->hstream));
+    m->last_h2d = (m->x_hi - m->x_lo) * 8; x_up = m->x_hi;
+  }
   bool ywin = y != nullptr;   // multipliers can follow the windows only when every row is `o0 + k` (no augmentation in the list)
   for (int pi : lst) if (pl.pats[(size_t)pi].ir.kind == exb::KIND_AUG) ywin = false;
   if (y && !ywin) { CU_TRY(m, cudaMemcpyAsync(m->dy, y, (size_t)pl.ncon * 8, cudaMemcpyHostToDevice, m->hstream)); m->last_h2d += pl.ncon * 8; }
@@ -1704,6 +1713,23 @@ static int host_coo_pipelined(exb_model* m, int kn, const double* x, const doubl
       if (b0 + csz > bmax[(size_t)q]) bmax[(size_t)q] = b0 + csz;
     }
     std::vector<std::pair<long long, long long>> outs;
+    if (xwin) {   // the part of x this window's points read (windows advance monotonically through every pattern)
+      long long need = x_up;
+      for (size_t q = 0; q < lst.size(); q++) {
+        if (bmin[q] < 0) continue;
+        const size_t pi = (size_t)lst[q];
+        const exb::PatternPlan& p = pl.pats[pi];
+        const long long n = m->hi[pi] - m->lo[pi], per = BLK * L.ppt[q];
+        const long long p1 = std::min(n, bmax[q] * per);
+        need = std::max(need, p.ir.range_start + m->lo[pi] + p1 - 1 + p.rhi);   // exclusive 0-based bound of the last variable read
+      }
+      if (w == W - 1) need = m->x_hi;
+      need = std::min(need, m->x_hi);
+      if (need > x_up) {
+        CU_TRY(m, cudaMemcpyAsync(m->dx + x_up, x + x_up, (size_t)(need - x_up) * 8, cudaMemcpyHostToDevice, m->hstream));
+        m->last_h2d += (need - x_up) * 8; x_up = need;
+      }
+    }
     for (size_t q = 0; q < lst.size(); q++) {
       if (bmin[q] < 0) continue;
       const size_t pi = (size_t)lst[q];
