@@ -364,6 +364,11 @@ def eval_legs(ctx, core, name, steps=20, check="window", graph=False, peak=None)
         ms_g, _ = timed(ctx, gr.replay, steps)
         out["full_callback"]["cuda_graph_ms_per_eval"] = ms_g
         out["full_callback"]["cuda_graph_evals_per_s"] = 1e3 / ms_g
+        out["full_callback"]["cuda_graph_what"] = "the five separate callbacks on parallel graph branches"
+        gf = m.capture_fused_eval(x, y, od, g, c, jac, hess)
+        ms_gf, _ = timed(ctx, gf.replay, steps)
+        out["full_callback"]["cuda_graph_fused_ms_per_eval"] = ms_gf
+        out["full_callback"]["cuda_graph_fused_evals_per_s"] = 1e3 / ms_gf
     # parity of what the timed calls left in the buffers
     allcb()
     torch.cuda.synchronize()

@@ -336,6 +336,18 @@ class ExaModel:
                                self._dev(Hv, self.nvar), self._stream()))
         return Hv
 
+    def capture_fused_eval(self, x, y, obj_out, g, c, jac, hess, obj_weight=1.0):
+        """`eval_all` (one sweep + its finishing steps) at fixed buffers as ONE CUDA graph: for latency-bound models the 3-4
+        launches of the fused evaluation replay without per-launch submission cost.  Returns the `torch.cuda.CUDAGraph`."""
+        torch = self._torch
+        for _ in range(2):         # first call ranks the launch-shape variants (synchronises): not capturable
+            self.eval_all(x, y, obj_out, g, c, jac, hess, obj_weight=obj_weight)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.eval_all(x, y, obj_out, g, c, jac, hess, obj_weight=obj_weight)
+        return graph
+
     def capture_full_eval(self, x, y, obj_out, g, c, jac, hess, obj_weight=1.0):
         """Capture obj + grad! + cons! + jac_coord! + hess_coord! at fixed buffers into ONE CUDA graph.
         For the many-small-patterns regime (AC-OPF: ~0.6 M nonzeros) a full evaluation is launch-latency

@@ -118,6 +118,30 @@ def test_cuda_graph_full_eval_matches_eager(exa, torch_):
         assert torch.equal(h, m.hess_coord(dx, dy, m.new(m.nnzh), obj_weight=0.5))
 
 
+def test_cuda_graph_of_the_fused_evaluation(exa, torch_):
+    """`exb_eval` (one sweep + finishing steps) captured as one CUDA graph replays to the oracle's values after x / y change."""
+    from examodels_jl_b200 import models as M
+    from oracle.oracle_api import Oracle
+    torch = torch_
+    for core in (M.ac_power(M.synthetic_power_data(300, 420, 70, seed=2)), M.luksan_vlcek(5000)):
+        m, ora = exa.ExaModel(core), Oracle.from_core(core)
+        x, y = inputs(core)
+        dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+        od, g, c, j, h = m.new(1), m.new(m.nvar), m.new(m.ncon), m.new(m.nnzj), m.new(m.nnzh)
+        gr = m.capture_fused_eval(dx, dy, od, g, c, j, h, obj_weight=0.5)
+        x2, y2 = inputs(core, 5)
+        dx.copy_(torch.from_numpy(x2)); dy.copy_(torch.from_numpy(y2))
+        for t in (od, g, c, j, h):
+            t.fill_(float("nan"))
+        gr.replay()
+        torch.cuda.synchronize()
+        assert abs(od.item() - ora.obj(x2)) <= 1e-10 * max(1.0, abs(ora.obj(x2)))
+        assert_close(g.cpu().numpy(), ora.grad(x2), "graph grad")
+        assert_close(c.cpu().numpy(), ora.cons(x2), "graph cons")
+        assert_close(j.cpu().numpy(), ora.jac_coord(x2), "graph jac")
+        assert_close(h.cpu().numpy(), ora.hess_coord(x2, y2, 0.5), "graph hess")
+
+
 def test_plain_c_host_through_the_abi(exa, tmp_path):
     """The boundary is usable without Python: a C program (tests/c_host_example.c) linked against libexa_b200.so
     builds LV N=5000 from an IR file and evaluates hess_coord! / obj with host buffers."""
