@@ -40,7 +40,7 @@ def test_own_arm_lines_carry_the_contract():
 def test_round_2_lines_carry_everything_the_metric_names():
     """Round 2: the ONE line also carries the sustained figure with its clock samples, full-callback evals/s at every N (collectives
     in the timed region), the strong-scaling legs, configs 3-5 and a parity block against the oracle -- at N = 1, 2 and 8."""
-    for name, n in (("r02_bench_line.json", 1), ("r02_bench_line_2gpu.json", 2), ("r02_bench_line_8gpu.json", 8)):
+    for name, n in (("r02_bench_line.json", 1), ("r02_bench_line_2gpu.json", 2), ("r02_bench_line_4gpu.json", 4), ("r02_bench_line_8gpu.json", 8)):
         d = _load(name)
         for k in BASE + ("roofline", "clocks", "sustained", "full_callback", "strong", "configs", "parity"):
             assert k in d, (name, k)
