@@ -607,7 +607,7 @@ def main():
     # ---------------- strong scaling and the other BASELINE configs ----------------
     strong, configs = None, None
     if not args.quick:
-        strong = eval_legs(ctx, M.luksan_vlcek(N_PER_GPU), f"LV N={N_PER_GPU} total over {world} rank(s)", peak=peak)
+        strong = eval_legs(ctx, M.luksan_vlcek(N_PER_GPU), f"LV N={N_PER_GPU} total over {world} rank(s)", graph=True, peak=peak)
         configs = {}
         configs["config4_acopf_10k"] = eval_legs(ctx, M.ac_power(M.synthetic_power_data()), "synthetic 10k-bus AC-OPF pattern set (15 patterns)",
                                                  check="full", graph=True, peak=peak)
