@@ -125,3 +125,39 @@ def special_sweep(n=257):
 
 EDGE = {"mixed_gradient": mixed_gradient, "only_objective": only_objective, "only_constraints": only_constraints, "empty_patterns": empty_patterns,
         "single_points_and_constants": single_points_and_constants, "self_loops": self_loops, "field_types": field_types}
+
+
+def tile_fuzz(seed):
+    """Random shift-indexed models for the column-tile kernels (duplicate-free Hessian, tile gradient): 2-4 patterns over
+    different sub-ranges (so the per-distance column intervals start / end at different places, sometimes with gaps -> the
+    sorted-gather fallback), shifts in [-3, 3], bodies mixing products, powers, sin / exp, parameters-free."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(150, 900))
+    c = E.ExaCore(); x = c.add_var(n, start=rng.uniform(0.4, 0.9, n))
+    from examodels_jl_b200.graph import sin, exp, cos
+    if seed == 99:   # two patterns over disjoint ranges: the columns of distance 1 have a GAP -> no closed form, sorted gather
+        c.add_con(lambda i: x[i] * x[i + 1] + sin(x[i]), range(1, 50))
+        c.add_obj(lambda i: x[i] * x[i + 1] ** 2, range(100, 140))
+        return c
+    npat = int(rng.integers(2, 5))
+    for k in range(npat):
+        sh = sorted(set(int(v) for v in rng.integers(-3, 4, size=int(rng.integers(2, 4)))))
+        lo = 1 - min(sh) + int(rng.integers(0, 40)); hi = n - max(sh) - int(rng.integers(0, 40))
+        if rng.random() < 0.3:                       # a short pattern somewhere in the middle
+            lo = int(rng.integers(lo, (lo + hi) // 2)); hi = int(rng.integers(lo + 5, hi))
+        kind = int(rng.integers(0, 3))
+        a, b = sh[0], sh[-1]
+        m = sh[len(sh) // 2]
+
+        def body(i, a=a, b=b, m=m, kind=kind):
+            t = x[i + a] * x[i + b] ** 2 + sin(x[i + m] - x[i + a])
+            if kind == 1:
+                t = t * exp(x[i + b] * 0.3) + x[i + m] ** 3
+            if kind == 2:
+                t = t + cos(x[i + a] * x[i + m]) * x[i + b]
+            return t
+        if k % 2 == 0:
+            c.add_con(body, range(lo, hi + 1))
+        else:
+            c.add_obj(body, range(lo, hi + 1))
+    return c

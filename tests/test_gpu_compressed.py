@@ -113,3 +113,40 @@ def test_fused_duplicate_free_hessian_on_sharded_handles(exa, world):
         assert np.all((ch[lo:hi] > vlo) & (ch[lo:hi] <= vhi))            # exactly the entries of the owned columns
     assert (cover == 1).all()
     assert_close(full, vh, "sharded fused hess")
+
+
+@pytest.mark.parametrize("seed", list(range(6)) + [99])
+def test_tile_kernels_on_random_shift_indexed_models(exa, seed):
+    """Random patterns over different sub-ranges with shifts in [-3, 3]: the closed-form structure, the fused duplicate-free
+    values (or the sorted-gather fallback when a distance's columns have a gap), the gradient and the fused evaluation against
+    the oracle."""
+    import torch
+    from edge_models import tile_fuzz
+    core = tile_fuzz(seed)
+    ora, x, y, (rh, ch, vh) = _ref(core, 0.5)
+    m = exa.ExaModel(core)
+    cm = m.compressed()
+    assert cm.nnzh == len(rh) and cm.fused_hess == exa.Plan(core).tile_info()["fused"] and cm.fused_hess == (seed != 99)
+    r, c = cm.new(cm.nnzh, torch.int64), cm.new(cm.nnzh, torch.int64)
+    cm.hess_structure(r, c)
+    assert np.array_equal(r.cpu().numpy(), rh) and np.array_equal(c.cpu().numpy(), ch)
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    assert_close(cm.hess_coord(dx, dy, cm.new(cm.nnzh).fill_(float("nan")), obj_weight=0.5).cpu().numpy(), vh, "duplicate-free hess")
+    assert_close(m.grad(dx, m.new(m.nvar).fill_(float("nan"))).cpu().numpy(), ora.grad(x), "grad")
+    outs = [m.new(k).fill_(float("nan")) for k in (1, m.nvar, m.ncon, m.nnzj, m.nnzh)]
+    m.eval_all(dx, dy, *outs, obj_weight=0.5)
+    assert_close(outs[1].cpu().numpy(), ora.grad(x), "eval grad")
+    assert_close(outs[4].cpu().numpy(), ora.hess_coord(x, y, 0.5), "eval hess")
+    if m.ncon:
+        assert_close(outs[2].cpu().numpy(), ora.cons(x), "eval cons")
+        assert_close(outs[3].cpu().numpy(), ora.jac_coord(x), "eval jac")
+    # sharded: owned columns tile the unique list
+    if cm.fused_hess:
+        full = np.full(len(rh), np.nan)
+        for rk in range(3):
+            ms = exa.ExaModel(core, rank=rk, world=3)
+            cs = ms.compressed()
+            v = cs.hess_coord(dx, dy, cs.new(cs.nnzh).fill_(float("nan")), obj_weight=0.5).cpu().numpy()
+            assert np.isnan(full[cs.hess_lo:cs.hess_hi]).all()
+            full[cs.hess_lo:cs.hess_hi] = v[cs.hess_lo:cs.hess_hi]
+        assert_close(full, vh, "sharded duplicate-free hess")

@@ -284,3 +284,19 @@ def test_ir_validation_rejects_what_the_round_1_review_listed():
     j = next(q for q in range(nnodes) if aos[nodes + 4 * q] == 3)
     bad = list(aos); bad[nodes + 4 * j] = 2
     assert create(bad)[0] == 3 and "DATA_SELF" in create(bad)[1]
+
+
+def test_duplicate_free_hessian_closed_form_counts():
+    """The fused form's unique count is a closed form of the pattern shifts: it must equal the number of distinct coordinates of
+    the oracle's structure on random shift-indexed models; a distance whose columns have a gap switches the fused form off."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from edge_models import tile_fuzz
+    for seed in range(6):
+        core = tile_fuzz(seed)
+        r, c = Oracle.from_core(core).hess_structure()
+        info = E.Plan(core).tile_info()
+        assert info["fused"] and info["nnzh_unique"] == len(set(zip(r.tolist(), c.tolist())))
+    assert not E.Plan(tile_fuzz(99)).tile_info()["fused"]
+    for core in (M.goddard_rocket(20), M.ac_power(M.synthetic_power_data(30, 41, 6, seed=5)), M.luksan_vlcek_aug(9, 3)):
+        assert not E.Plan(core).tile_info()["fused"]        # fixed-index variable / data-indexed / product iterators
