@@ -49,7 +49,7 @@ struct PatternPlan {
   i64 oa = 0;                  // aug: first conbuffer slot (ConstraintAugmentation.oa)
   i64 ob = 0;                  // obj: first objbuffer slot
   int ppt0 = 1, ppt1 = 1, ppt2 = 1;   // points per thread in the value / first-order / second-order kernels
-  int ppte = 1;                       // ... and in the fused evaluation kernel (exb_eval_g0)
+  int ppte = 1, ppte1 = 1;            // ... and in the fused evaluation kernels (exb_eval_g0; first-order form exb_eval1_g0)
   std::vector<int> leaf1;      // representative Var IR node per first-order slot
   std::vector<std::pair<int, int>> leaf2;
   // owner-computes gradient (see gen_pattern, g1): every first-order slot's variable index is `t + shift1[j]` with
@@ -651,21 +651,21 @@ inline void emit_eval_fn(std::ostringstream& o, const std::string& name, const s
 // Fused evaluation of one point: value, first-order slots (adjoint 1) and second-order slots (adjoint a0) from ONE forward
 // sweep (exb_eval_block).  Same fast / slow split as emit_eval_fn.
 inline void emit_eval3_fn(std::ostringstream& o, const std::string& params, const std::string& args, int n1, int n2, const Body& B,
-                          const std::vector<std::string>& tail) {
+                          const std::vector<std::string>& tail, const std::string& fn = "d012") {
   const std::string outs = ", double& v, double (&s1)[" + std::to_string(n1) + "], double (&s2)[" + std::to_string(n2) + "]";
-  o << "  template <bool SLOW, class XA> __device__ static __forceinline__ void d012_t(" << params << outs << ", bool& bad) {\n";
+  o << "  template <bool SLOW, class XA> __device__ static __forceinline__ void " << fn << "_t(" << params << outs << ", bool& bad) {\n";
   for (auto& l : B.lines) o << "    " << l << "\n";
   for (auto& l : tail) o << "    " << l << "\n";
   o << "  }\n";
   const bool fast = body_uses_fast(B);
   if (fast)
-    o << "  template <class XA> __device__ static __noinline__ void d012_slow(" << params << ", double* __restrict__ so) { bool bad = false; double v; double s1[" << n1
-      << "], s2[" << n2 << "]; d012_t<true>(" << args << ", v, s1, s2, bad); so[0] = v; for (int j = 0; j < " << n1 << "; j++) so[1 + j] = s1[j]; for (int j = 0; j < "
+    o << "  template <class XA> __device__ static __noinline__ void " << fn << "_slow(" << params << ", double* __restrict__ so) { bool bad = false; double v; double s1[" << n1
+      << "], s2[" << n2 << "]; " << fn << "_t<true>(" << args << ", v, s1, s2, bad); so[0] = v; for (int j = 0; j < " << n1 << "; j++) so[1 + j] = s1[j]; for (int j = 0; j < "
       << n2 << "; j++) so[" << 1 + n1 << " + j] = s2[j]; }\n";
-  o << "  template <class XA> __device__ static __forceinline__ void d012(" << params << outs << ") {\n    bool bad = false;\n";
-  o << "    d012_t<false>(" << args << ", v, s1, s2, bad);\n";
+  o << "  template <class XA> __device__ static __forceinline__ void " << fn << "(" << params << outs << ") {\n    bool bad = false;\n";
+  o << "    " << fn << "_t<false>(" << args << ", v, s1, s2, bad);\n";
   if (fast)
-    o << "    if (bad) { double q[" << 1 + n1 + n2 << "]; d012_slow(" << args << ", q); v = q[0]; for (int j = 0; j < " << n1 << "; j++) s1[j] = q[1 + j]; for (int j = 0; j < "
+    o << "    if (bad) { double q[" << 1 + n1 + n2 << "]; " << fn << "_slow(" << args << ", q); v = q[0]; for (int j = 0; j < " << n1 << "; j++) s1[j] = q[1 + j]; for (int j = 0; j < "
       << n2 << "; j++) s2[j] = q[" << 1 + n1 << " + j]; }\n";
   o << "  }\n";
 }
@@ -889,6 +889,21 @@ inline std::string gen_pattern(PatternPlan& p, int index, bool windowed, const s
     p.ppte = ppt_for(body_weight(B), a1 + a2);
     o << "  static constexpr int PPTE = " << p.ppte << "; static constexpr bool G1 = " << ((p.gather1 || p.tgrad) ? "true" : "false") << ";\n";
   }
+  {  // d01: value + first-order slots from one order-1 sweep (exb_eval with mask obj | grad | cons | jac: the first-order evaluation
+     // a solver does at a new iterate); same signature as d012, s2 / a0 unused
+    Body B; Gen g(p, B, 1);
+    NV& r = g.fwd(p.ir.root);
+    std::vector<std::string> tail;
+    tail.push_back("v = " + r.x.s + ";");
+    if (ns1 > 0) {
+      g.comp = &p.comp1; g.slot.assign((size_t)ns1, K(0)); g.cnt = 0;
+      g.rpass1(p.ir.root, K(1));
+      for (int j = 0; j < ns1; j++) tail.push_back("s1[" + std::to_string(j) + "] = " + g.slot[(size_t)j].s + ";");
+    }
+    emit_eval3_fn(o, A + ", const XA x, const double* __restrict__ th, const double a0", "pa, kg, x, th, a0", a1, a2, B, tail, "d01");
+    p.ppte1 = ppt_for(body_weight(B), a1 + 1);
+    o << "  static constexpr int PPTE1 = " << p.ppte1 << ";\n";
+  }
   if (hd != nullptr && ns2 > 0 && p.tile_ok) {
     // Column-tile form (exb_tile_body): the block stages the second-order slots of the points around its tile of columns in
     // shared memory (`raw`, point-major, TSTRIDE words per point); the thread that owns column c then sums every slot that
@@ -1104,7 +1119,9 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes, const void* const
       << "exb_tile_body<2, " << pl.hd.size() << ", " << pl.tile_ppt << ", " << plist(pl.k_hess) << ">(g, c, t); }\n";
   }
   if (pl.hess_windowed) kern("exb_hessp_g0", "exb_hessp_body", pl.k_hess, "");
-  kern("exb_eval_g0", "exb_eval_body", pl.k_eval, "");
+  kern("exb_eval_g0", "exb_eval_body", pl.k_eval, "2, ");
+  kern("exb_eval1_g0", "exb_eval_body", pl.k_eval, "1, ");
+  kern("exb_eval0_g0", "exb_eval_body", pl.k_eval, "0, ");
   kern("exb_jac_g0", "exb_d1_body", pl.k_jac, "");
   kern("exb_sgrad_g0", "exb_d1_body", pl.k_sgrad, "");
   kern("exb_ggrad_g0", "exb_ggrad_body", pl.k_ggrad, "");

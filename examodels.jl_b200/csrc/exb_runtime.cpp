@@ -164,10 +164,10 @@ bool load_nccl() {
   return g_nccl.ok;
 }
 
-enum { KN_HESS, KN_JAC, KN_SGRAD, KN_GGRAD, KN_CONS, KN_OBJ, KN_JSTRUCT64, KN_JSTRUCT32, KN_GSTRUCT64, KN_HSTRUCT64, KN_HSTRUCT32, KN_AUGROW, KN_JPROD, KN_JTPROD, KN_HPROD, KN_HESSC, KN_EVAL, KN_GRADT, KN_COUNT };
+enum { KN_HESS, KN_JAC, KN_SGRAD, KN_GGRAD, KN_CONS, KN_OBJ, KN_JSTRUCT64, KN_JSTRUCT32, KN_GSTRUCT64, KN_HSTRUCT64, KN_HSTRUCT32, KN_AUGROW, KN_JPROD, KN_JTPROD, KN_HPROD, KN_HESSC, KN_EVAL, KN_GRADT, KN_EVAL1, KN_EVAL0, KN_COUNT };
 const char* KNAME[KN_COUNT] = {"exb_hess_g0", "exb_jac_g0", "exb_sgrad_g0", "exb_ggrad_g0", "exb_cons_g0", "exb_obj_g0", "exb_jstruct64_g0",
                                "exb_jstruct32_g0", "exb_gstruct64_g0", "exb_hstruct64_g0", "exb_hstruct32_g0", "exb_augrow_g0",
-                               "exb_jprod_g0", "exb_jtprod_g0", "exb_hprod_g0", "exb_hessc_g0", "exb_eval_g0", "exb_gradt_g0"};
+                               "exb_jprod_g0", "exb_jtprod_g0", "exb_hprod_g0", "exb_hessc_g0", "exb_eval_g0", "exb_gradt_g0", "exb_eval1_g0", "exb_eval0_g0"};
 
 }  // namespace
 
@@ -193,7 +193,7 @@ struct exb_plan {
       case KN_GGRAD: return pl.k_ggrad;
       case KN_CONS: return pl.k_cons;
       case KN_OBJ: return pl.k_obj;
-      case KN_EVAL: return pl.k_eval;
+      case KN_EVAL: case KN_EVAL1: case KN_EVAL0: return pl.k_eval;
       case KN_GRADT: return pl.k_tgrad;
       default: return pl.k_aug;
     }
@@ -355,6 +355,7 @@ struct exb_model {
   double* d_theta = nullptr;
   double* d_objpart = nullptr; double* d_obj = nullptr;
   double* d_objpart_e = nullptr; long long n_objpart_e = 0;   // objective partials of the fused evaluation kernel
+  double* d_objpart_e1 = nullptr; double* d_objpart_e0 = nullptr;   // ... of its first-order / value-only forms (one partial per block)
   double* d_gradbuf = nullptr; double* d_conbuf = nullptr;
   // sorted (target, slot) lists: grad (ext:39-46) and constraint augmentation (ext:48-53)
   void *g_slot = nullptr, *g_target = nullptr, *g_ptr = nullptr; long long g_runs = 0; int g_i32 = 0, g_dense = 0;
@@ -695,7 +696,7 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       if (r != CUDA_SUCCESS) return fail(EXB_ERR_COMPILE, std::string("kernel ") + KNAME[kn] + " missing from module: " + cu_err(r));
       L.cand.push_back(fn);
     }
-    const bool tunable = kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD || kn == KN_GGRAD || kn == KN_CONS || kn == KN_OBJ || kn == KN_HESSC || kn == KN_EVAL || kn == KN_GRADT;
+    const bool tunable = kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD || kn == KN_GGRAD || kn == KN_CONS || kn == KN_OBJ || kn == KN_HESSC || kn == KN_EVAL || kn == KN_GRADT || kn == KN_EVAL1 || kn == KN_EVAL0;
     L.best = (!tunable || L.cand.size() == 1) ? 0 : -1;
     L.fn = L.cand[0];
     const long long BLK = P->pl.block;
@@ -706,10 +707,10 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       args[q] = pa[(size_t)lst[q]];
       const exb::PatternPlan& p = pl.pats[(size_t)lst[q]];
       const bool k2 = kn == KN_HESS || kn == KN_HPROD, k1 = kn == KN_JAC || kn == KN_SGRAD || kn == KN_JPROD || kn == KN_JTPROD, k0 = kn == KN_CONS || kn == KN_OBJ;
-      const int ppt = kn == KN_EVAL ? p.ppte : k2 ? p.ppt2 : k1 ? p.ppt1 : k0 ? p.ppt0 : 1;
+      const int ppt = kn == KN_EVAL ? p.ppte : kn == KN_EVAL1 ? p.ppte1 : kn == KN_EVAL0 ? p.ppt0 : k2 ? p.ppt2 : k1 ? p.ppt1 : k0 ? p.ppt0 : 1;
       nb[q] = (args[q].n + BLK * ppt - 1) / (BLK * ppt);
       tot += nb[q]; if (nb[q] > maxnb) maxnb = nb[q];
-      int ns = kn == KN_EVAL ? p.o1step + p.o2step : k2 ? p.o2step : k1 ? p.o1step : 1;
+      int ns = kn == KN_EVAL ? p.o1step + p.o2step : kn == KN_EVAL1 ? p.o1step : k2 ? p.o2step : k1 ? p.o1step : 1;
       if (kn == KN_HESS) {   // a split entry stages only its window of slots (rows padded to an odd word count)
         const int nw = pl.k_hess_w[q].second - pl.k_hess_w[q].first;
         if (nw != p.o2step) ns = nw | 1;
@@ -778,7 +779,7 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       L.ppt.push_back(kn == KN_HESS ? p.ppt2 : (kn == KN_JAC || kn == KN_SGRAD) ? p.ppt1 : (kn == KN_CONS || kn == KN_OBJ) ? p.ppt0 : 1);
       L.ns.push_back(kn == KN_HESS ? p.o2step : (kn == KN_JAC || kn == KN_SGRAD) ? p.o1step : 1);
     }
-    L.smem = (kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD || kn == KN_EVAL) ? (maxns > 1 ? (unsigned)(BLK * maxns * 8) : 16u) : 0u;
+    L.smem = (kn == KN_HESS || kn == KN_JAC || kn == KN_SGRAD || kn == KN_EVAL || kn == KN_EVAL1) ? (maxns > 1 ? (unsigned)(BLK * maxns * 8) : 16u) : kn == KN_EVAL0 ? 16u : 0u;
     if (L.smem > 48u * 1024u)   // tiles of patterns with many slots per point: opt in to large dynamic shared memory
       for (CUfunction fn : L.cand) {
         r = g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)L.smem);
@@ -856,6 +857,12 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
   rc = dmalloc(m, (void**)&m->d_obj, 8); if (rc) return rc;
   rc = dmalloc(m, (void**)&m->d_objpart_e, (size_t)(m->n_objpart_e + 1) * 8); if (rc) return rc;
   CU_TRY(m, cudaMemset(m->d_objpart_e, 0, (size_t)(m->n_objpart_e + 1) * 8));
+  for (int lv = 0; lv < 2; lv++) {   // padding blocks and constraint blocks never write their partial: zeroed once
+    double** dp = lv ? &m->d_objpart_e1 : &m->d_objpart_e0;
+    const size_t nb_ = (size_t)m->k[lv ? KN_EVAL1 : KN_EVAL0].nblocks + 1;
+    rc = dmalloc(m, (void**)dp, nb_ * 8); if (rc) return rc;
+    CU_TRY(m, cudaMemset(*dp, 0, nb_ * 8));
+  }
   rc = dmalloc(m, (void**)&m->d_gradbuf, (size_t)pl.nnzg * 8); if (rc) return rc;
   rc = dmalloc(m, (void**)&m->d_conbuf, (size_t)pl.nconaug * 8); if (rc) return rc;
   // gradient sparsity: (var, slot) sorted by var (ext:39-46)
@@ -1280,6 +1287,20 @@ int exb_eval(exb_model* m, unsigned mask, const double* x, const double* y, doub
     return fail(EXB_ERR_ARG, "exb_eval: a requested output is NULL");
   static const bool no_fused = getenv("EXB_NO_FUSED_EVAL") != nullptr;
   const bool fused = mask == EXB_EVAL_ALL && !no_fused && m->k[KN_EVAL].fn && m->k[KN_EVAL].nblocks > 0;
+  const int level = mask == EXB_EVAL_FIRST ? 1 : mask == EXB_EVAL_VALUES ? 0 : -1;
+  const int knl = level == 1 ? KN_EVAL1 : KN_EVAL0;
+  if (!fused && level >= 0 && !no_fused && m->k[knl].fn && m->k[knl].nblocks > 0) {
+    // first-order evaluation (obj + grad! + cons! + jac_coord!) or values only (obj + cons!) from one sweep
+    int rc = cons_prepare(m, cvals, st); if (rc) return rc;
+    ExbCall c{}; c.x = x; c.th = m->d_theta;
+    c.e_jac = jac; c.e_c = cvals; c.e_gb = m->d_gradbuf; c.e_cb = m->d_conbuf; c.e_obj = level == 1 ? m->d_objpart_e1 : m->d_objpart_e0;
+    rc = launch(m, knl, c, st); if (rc) return rc;
+    CU_TRY(m, exb_fx_sum(c.e_obj, m->k[knl].nblocks, obj_dev, st));
+    m->launches++; m->last_launches++;
+    if (comm_on(m)) { rc = comm_allreduce(m, obj_dev, 1, st); if (rc) return rc; }
+    if (level == 1) { rc = grad_impl(m, x, g, st, true); if (rc) return rc; }
+    return cons_finish(m, cvals, st);
+  }
   if (!fused) {
     int rc = EXB_OK;
     long long nl = 0, nc = 0;   // the callbacks reset the per-call counters: keep the totals of this call

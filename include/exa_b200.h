@@ -178,7 +178,8 @@ int exb_hess(exb_model* m, const double* x, const double* y, double obj_weight, 
  * and hess_coord! at the same x, and the reference walks every pattern's tree once per callback).  mask = EXB_EVAL_ALL: every
  * data point is evaluated once by one generated launch (exb_eval_g0) that writes c, jac, hess, the gradient slots and the
  * objective's partial sums; the small finishing steps of the separate callbacks follow (fixed-order sum, owner-computed
- * gradient, segmented sums, collectives of a sharded model).  Any other mask: the requested callbacks one by one.  Outputs not
+ * gradient, segmented sums, collectives of a sharded model).  mask = EXB_EVAL_FIRST / EXB_EVAL_VALUES: the same with a first-order /
+ * value-only sweep.  Any other mask: the requested callbacks one by one.  Outputs not
  * requested may be NULL; *obj_dev is a DEVICE double (no synchronisation); y == NULL is the objective-only Hessian form. */
 #define EXB_EVAL_OBJ 1u
 #define EXB_EVAL_GRAD 2u
@@ -186,6 +187,8 @@ int exb_hess(exb_model* m, const double* x, const double* y, double obj_weight, 
 #define EXB_EVAL_JAC 8u
 #define EXB_EVAL_HESS 16u
 #define EXB_EVAL_ALL 31u
+#define EXB_EVAL_FIRST 15u  /* obj | grad | cons | jac: ONE first-order sweep (exb_eval1_g0) */
+#define EXB_EVAL_VALUES 5u  /* obj | cons: ONE value sweep (exb_eval0_g0), e.g. a line-search probe */
 int exb_eval(exb_model* m, unsigned mask, const double* x, const double* y, double obj_weight, double* obj_dev, double* g, double* c,
              double* jac, double* hess, void* stream);
 

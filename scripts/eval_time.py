@@ -27,6 +27,11 @@ ref = [t.clone() for t in (od, g, c, j, h)]
 t_fused = timeit(lambda: m.eval_all(x, y, od, g, c, j, h))
 eq = [bool(torch.equal(a, b)) for a, b in zip(ref, (od, g, c, j, h))]
 md = [float((a - b).abs().max() / max(1e-300, float(b.abs().max()))) for a, b in zip((od, g, c, j, h), ref)]
+t_first_sep = timeit(lambda: (m.obj_async(x, od), m.grad(x, g), m.cons_nln(x, c), m.jac_coord(x, j)))
+t_first = timeit(lambda: m.eval_all(x, None, od, g, c, j, None, mask=15))
+t_val_sep = timeit(lambda: (m.obj_async(x, od), m.cons_nln(x, c)))
+t_val = timeit(lambda: m.eval_all(x, None, od, None, c, None, None, mask=5))
+print(f"{key}: first-order (obj+grad+cons+jac) separate {t_first_sep:.4f} ms  fused {t_first:.4f} ms;  values (obj+cons) separate {t_val_sep:.4f} ms  fused {t_val:.4f} ms")
 alg = 8 * (m.nnzh + m.nnzj + m.ncon + m.nvar + 2 * m.nvar + m.ncon)
 print(f"{key}: separate {t_sep:.4f} ms ({1e3 / t_sep:.0f} evals/s)  fused {t_fused:.4f} ms ({1e3 / t_fused:.0f} evals/s), launches {m.stats()['last_launches']}; "
       f"bitwise equal obj/grad/cons/jac/hess {eq}, max rel diff {['%.1e' % v for v in md]}")

@@ -70,6 +70,19 @@ def test_fused_evaluation_matches_oracle_and_separate_callbacks(exa, name):
     c2, j2 = m.new(m.ncon).fill_(nan), m.new(m.nnzj).fill_(nan)
     m.eval_all(dx, None, None, None, c2, j2, None, mask=4 | 8)
     assert torch.equal(c2, sep[2]) and torch.equal(j2, sep[3])
+    # first-order sweep (obj | grad | cons | jac: exb_eval1_g0) and value sweep (obj | cons: exb_eval0_g0)
+    o1, g1, c1, j1 = m.new(1).fill_(nan), m.new(m.nvar).fill_(nan), m.new(m.ncon).fill_(nan), m.new(m.nnzj).fill_(nan)
+    m.eval_all(dx, None, o1, g1, c1, j1, None, mask=15)
+    m.eval_all(dx, None, o1, g1, c1, j1, None, mask=15)
+    assert abs(float(o1.item()) - ref) <= 1e-10 * max(1.0, abs(ref))
+    assert_close(g1.cpu().numpy(), ora.grad(x), "first-order sweep grad")
+    assert_close(c1.cpu().numpy(), ora.cons(x), "first-order sweep cons")
+    assert_close(j1.cpu().numpy(), ora.jac_coord(x), "first-order sweep jac")
+    o0, c0 = m.new(1).fill_(nan), m.new(m.ncon).fill_(nan)
+    m.eval_all(dx, None, o0, None, c0, None, None, mask=5)
+    assert abs(float(o0.item()) - ref) <= 1e-10 * max(1.0, abs(ref))
+    assert_close(c0.cpu().numpy(), ora.cons(x), "value sweep cons")
+    assert torch.equal(c0, sep[2])          # the value function is the very code of exb_cons_g0
 
 
 def test_fused_evaluation_is_one_sweep(exa):
