@@ -333,6 +333,11 @@ def eval_legs(ctx, core, name, steps=20, check="window", graph=False, peak=None)
            "full_callback": {"ms_per_eval": ms_f, "evals_per_s": 1e3 / ms_f, "launches_per_eval": int(nl),
                              "api": "exb_eval(EXB_EVAL_ALL): one sweep", "callbacks": "obj+grad!+cons!+jac_coord!+hess_coord!",
                              "separate_callbacks_ms_per_eval": ms_s, "separate_callbacks_evals_per_s": 1e3 / ms_s}}
+    # the first-order evaluation a solver does at a new iterate (obj + grad! + cons! + jac_coord!) from one sweep
+    ms_1, _ = timed(ctx, lambda: m.eval_all(x, None, od, g, c, jac, None, mask=15), steps)
+    ms_1s, _ = timed(ctx, lambda: (m.obj_async(x, od), m.grad(x, g), m.cons_nln(x, c), m.jac_coord(x, jac)), steps)
+    out["first_order"] = {"ms_per_eval": ms_1, "evals_per_s": 1e3 / ms_1, "api": "exb_eval(EXB_EVAL_FIRST): one sweep",
+                          "callbacks": "obj+grad!+cons!+jac_coord!", "separate_callbacks_ms_per_eval": ms_1s}
     if hasattr(m, "compressed"):
         try:
             cm = m.compressed()
