@@ -382,6 +382,7 @@ struct exb_model {
   // multi-GPU: a communicator over the `world` handles of one sharded model (exb_comm_*); with it the reducing callbacks
   // complete themselves on the caller's stream
   ncclComm_t comm = nullptr; bool comm_owned = false; int comm_mode = EXB_COMM_REPLICATE;
+  cudaStream_t cstream = nullptr; cudaEvent_t cev1 = nullptr, cev2 = nullptr;   // side stream of the early objective all-reduce (exb_eval)
   long long collectives = 0, last_collectives = 0;
   // per-callback device timing (the TimedNLPModel role, src/utils.jl:271-408): CUDA events around each callback
   bool timing = false;
@@ -908,6 +909,9 @@ void free_model(exb_model* m) {
   if (!m) return;
   DeviceGuard dg(m->device);
   if (m->comm && m->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+  if (m->cstream) cudaStreamDestroy(m->cstream);
+  if (m->cev1) cudaEventDestroy(m->cev1);
+  if (m->cev2) cudaEventDestroy(m->cev2);
   for (void* p : m->dev) cudaFree(p);
   for (CUmodule mod : m->mods) if (mod && g_drv.ModuleUnload) g_drv.ModuleUnload(mod);
   if (m->hx) cudaFreeHost(m->hx);
@@ -1269,6 +1273,31 @@ int exb_hess(exb_model* m, const double* x, const double* y, double obj_weight, 
   EXB_END
 }
 
+// Sharded handles with a communicator: the objective's all-reduce is a latency (one double, ~20 us over 8 GPUs), not a
+// bandwidth cost.  The fused evaluation therefore computes the objective FIRST with the small value kernel (exb_obj_g0 + the
+// fixed-order sum), starts its all-reduce on a side stream, and runs the sweep meanwhile: the latency hides behind the sweep
+// instead of following it.  `join` makes the caller's stream wait for the reduced objective.
+static int obj_early_fork(exb_model* m, const double* x, double* obj_dev, cudaStream_t st) {
+  if (!m->cstream) {
+    CU_TRY(m, cudaStreamCreateWithFlags(&m->cstream, cudaStreamNonBlocking));
+    CU_TRY(m, cudaEventCreateWithFlags(&m->cev1, cudaEventDisableTiming));
+    CU_TRY(m, cudaEventCreateWithFlags(&m->cev2, cudaEventDisableTiming));
+  }
+  ExbCall c{}; c.x = x; c.th = m->d_theta; c.out2 = m->d_objpart;
+  int rc = launch(m, KN_OBJ, c, st); if (rc) return rc;
+  CU_TRY(m, exb_fx_sum(m->d_objpart, m->k[KN_OBJ].nblocks, obj_dev, st));
+  m->launches++; m->last_launches++;
+  CU_TRY(m, cudaEventRecord(m->cev1, st));
+  CU_TRY(m, cudaStreamWaitEvent(m->cstream, m->cev1, 0));
+  rc = comm_allreduce(m, obj_dev, 1, m->cstream); if (rc) return rc;
+  CU_TRY(m, cudaEventRecord(m->cev2, m->cstream));
+  return EXB_OK;
+}
+static int obj_early_join(exb_model* m, cudaStream_t st) {
+  CU_TRY(m, cudaStreamWaitEvent(st, m->cev2, 0));
+  return EXB_OK;
+}
+
 // One sweep for several callbacks at the same x (the composition of src/nlp.jl:1827-1940).  With every bit of `mask` set each
 // data point is evaluated ONCE by exb_eval_g0 (value + first-order + second-order slots; csrc/exb_device.cuh exb_eval_block):
 // c / conbuffer, the objective's block partials, jac, the gradient slots and hess are written by that one launch; what
@@ -1291,15 +1320,19 @@ int exb_eval(exb_model* m, unsigned mask, const double* x, const double* y, doub
   const int knl = level == 1 ? KN_EVAL1 : KN_EVAL0;
   if (!fused && level >= 0 && !no_fused && m->k[knl].fn && m->k[knl].nblocks > 0) {
     // first-order evaluation (obj + grad! + cons! + jac_coord!) or values only (obj + cons!) from one sweep
-    int rc = cons_prepare(m, cvals, st); if (rc) return rc;
+    const bool early = comm_on(m);
+    int rc = early ? obj_early_fork(m, x, obj_dev, st) : EXB_OK; if (rc) return rc;
+    rc = cons_prepare(m, cvals, st); if (rc) return rc;
     ExbCall c{}; c.x = x; c.th = m->d_theta;
     c.e_jac = jac; c.e_c = cvals; c.e_gb = m->d_gradbuf; c.e_cb = m->d_conbuf; c.e_obj = level == 1 ? m->d_objpart_e1 : m->d_objpart_e0;
     rc = launch(m, knl, c, st); if (rc) return rc;
-    CU_TRY(m, exb_fx_sum(c.e_obj, m->k[knl].nblocks, obj_dev, st));
-    m->launches++; m->last_launches++;
-    if (comm_on(m)) { rc = comm_allreduce(m, obj_dev, 1, st); if (rc) return rc; }
+    if (!early) {
+      CU_TRY(m, exb_fx_sum(c.e_obj, m->k[knl].nblocks, obj_dev, st));
+      m->launches++; m->last_launches++;
+    }
     if (level == 1) { rc = grad_impl(m, x, g, st, true); if (rc) return rc; }
-    return cons_finish(m, cvals, st);
+    rc = cons_finish(m, cvals, st); if (rc) return rc;
+    return early ? obj_early_join(m, st) : EXB_OK;
   }
   if (!fused) {
     int rc = EXB_OK;
@@ -1313,15 +1346,19 @@ int exb_eval(exb_model* m, unsigned mask, const double* x, const double* y, doub
     m->last_launches = nl; m->last_collectives = nc;
     return rc;
   }
-  int rc = cons_prepare(m, cvals, st); if (rc) return rc;
+  const bool early = comm_on(m);
+  int rc = early ? obj_early_fork(m, x, obj_dev, st) : EXB_OK; if (rc) return rc;
+  rc = cons_prepare(m, cvals, st); if (rc) return rc;
   ExbCall c{}; c.x = x; c.y = y; c.th = m->d_theta; c.sigma = obj_weight; c.out = hess;
   c.e_jac = jac; c.e_c = cvals; c.e_gb = m->d_gradbuf; c.e_cb = m->d_conbuf; c.e_obj = m->d_objpart_e;
   rc = launch(m, KN_EVAL, c, st); if (rc) return rc;
-  CU_TRY(m, exb_fx_sum(m->d_objpart_e, m->n_objpart_e, obj_dev, st));
-  m->launches++; m->last_launches++;
-  if (comm_on(m)) { rc = comm_allreduce(m, obj_dev, 1, st); if (rc) return rc; }
+  if (!early) {
+    CU_TRY(m, exb_fx_sum(m->d_objpart_e, m->n_objpart_e, obj_dev, st));
+    m->launches++; m->last_launches++;
+  }
   rc = grad_impl(m, x, g, st, true); if (rc) return rc;
-  return cons_finish(m, cvals, st);
+  rc = cons_finish(m, cvals, st); if (rc) return rc;
+  return early ? obj_early_join(m, st) : EXB_OK;
   EXB_END
 }
 

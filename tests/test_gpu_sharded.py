@@ -78,6 +78,22 @@ def _worker(rank, world, port, which, q):
             checks(sm)
             st = local.comm_stats()
             assert st["attached"] == 1 and st["collectives"] >= 7
+            # the fused sweep on a sharded handle: the objective's all-reduce runs on a side stream, hidden behind the sweep
+            od, g2, c2 = local.new(1).fill_(nan), local.new(local.nvar).fill_(nan), local.new(local.ncon).fill_(nan)
+            j2, h2 = local.new(local.nnzj).fill_(nan), local.new(local.nnzh).fill_(nan)
+            for _ in range(2):
+                local.eval_all(dx, dy, od, g2, c2, j2, h2, obj_weight=0.5)
+            torch.cuda.synchronize()
+            assert abs(float(od.item()) - full.obj(x)) <= 1e-10 * max(1.0, abs(full.obj(x)))
+            assert_close(g2.cpu().numpy(), full.grad(x), "eval grad (replicate)")
+            assert_close(c2.cpu().numpy(), full.cons(x), "eval cons (replicate)")
+            hh = h2.cpu().numpy(); own = ~np.isnan(hh)
+            assert own.any() and not own.all()
+            assert_close(hh[own], full.hess_coord(x, y, 0.5)[own], "eval hess (own slices)")
+            o1 = local.new(1).fill_(nan)
+            local.eval_all(dx, None, o1, g2, c2, j2, None, mask=15)
+            torch.cuda.synchronize()
+            assert abs(float(o1.item()) - full.obj(x)) <= 1e-10 * max(1.0, abs(full.obj(x)))
             # (3) owner mode, the sharded consumer: g on the owned variables, c on the rows of the own points
             local.comm_set_mode("owner")
             lo, hi = local.owned()
