@@ -1274,26 +1274,24 @@ int exb_hess(exb_model* m, const double* x, const double* y, double obj_weight, 
 }
 
 // Sharded handles with a communicator: the objective's all-reduce is a latency (one double, ~20 us over 8 GPUs), not a
-// bandwidth cost.  The fused evaluation therefore computes the objective FIRST with the small value kernel (exb_obj_g0 + the
-// fixed-order sum), starts its all-reduce on a side stream, and runs the sweep meanwhile: the latency hides behind the sweep
-// instead of following it.  `join` makes the caller's stream wait for the reduced objective.
-static int obj_early_fork(exb_model* m, const double* x, double* obj_dev, cudaStream_t st) {
+// bandwidth cost.  After the sweep and the fixed-order sum of the partials it is started on a SIDE stream, the gradient and
+// constraint finishing steps run meanwhile on the caller's stream, and `join` makes the caller's stream wait for the reduced
+// objective at the end.  (Tried and measured worse: computing the objective FIRST with the separate value kernel so that the
+// all-reduce hides behind the sweep itself -- the extra pass over the objective patterns costs more than the latency it hides:
+// 2 GPUs, config 5 full evaluation 0.325 -> 0.356 ms, LV weak 0.257 -> 0.267 ms.)
+static int obj_fork(exb_model* m, double* obj_dev, cudaStream_t st) {
   if (!m->cstream) {
     CU_TRY(m, cudaStreamCreateWithFlags(&m->cstream, cudaStreamNonBlocking));
     CU_TRY(m, cudaEventCreateWithFlags(&m->cev1, cudaEventDisableTiming));
     CU_TRY(m, cudaEventCreateWithFlags(&m->cev2, cudaEventDisableTiming));
   }
-  ExbCall c{}; c.x = x; c.th = m->d_theta; c.out2 = m->d_objpart;
-  int rc = launch(m, KN_OBJ, c, st); if (rc) return rc;
-  CU_TRY(m, exb_fx_sum(m->d_objpart, m->k[KN_OBJ].nblocks, obj_dev, st));
-  m->launches++; m->last_launches++;
   CU_TRY(m, cudaEventRecord(m->cev1, st));
   CU_TRY(m, cudaStreamWaitEvent(m->cstream, m->cev1, 0));
-  rc = comm_allreduce(m, obj_dev, 1, m->cstream); if (rc) return rc;
+  int rc = comm_allreduce(m, obj_dev, 1, m->cstream); if (rc) return rc;
   CU_TRY(m, cudaEventRecord(m->cev2, m->cstream));
   return EXB_OK;
 }
-static int obj_early_join(exb_model* m, cudaStream_t st) {
+static int obj_join(exb_model* m, cudaStream_t st) {
   CU_TRY(m, cudaStreamWaitEvent(st, m->cev2, 0));
   return EXB_OK;
 }
@@ -1320,19 +1318,17 @@ int exb_eval(exb_model* m, unsigned mask, const double* x, const double* y, doub
   const int knl = level == 1 ? KN_EVAL1 : KN_EVAL0;
   if (!fused && level >= 0 && !no_fused && m->k[knl].fn && m->k[knl].nblocks > 0) {
     // first-order evaluation (obj + grad! + cons! + jac_coord!) or values only (obj + cons!) from one sweep
-    const bool early = comm_on(m);
-    int rc = early ? obj_early_fork(m, x, obj_dev, st) : EXB_OK; if (rc) return rc;
-    rc = cons_prepare(m, cvals, st); if (rc) return rc;
+    int rc = cons_prepare(m, cvals, st); if (rc) return rc;
     ExbCall c{}; c.x = x; c.th = m->d_theta;
     c.e_jac = jac; c.e_c = cvals; c.e_gb = m->d_gradbuf; c.e_cb = m->d_conbuf; c.e_obj = level == 1 ? m->d_objpart_e1 : m->d_objpart_e0;
     rc = launch(m, knl, c, st); if (rc) return rc;
-    if (!early) {
-      CU_TRY(m, exb_fx_sum(c.e_obj, m->k[knl].nblocks, obj_dev, st));
-      m->launches++; m->last_launches++;
-    }
+    CU_TRY(m, exb_fx_sum(c.e_obj, m->k[knl].nblocks, obj_dev, st));
+    m->launches++; m->last_launches++;
+    const bool side = comm_on(m);
+    if (side) { rc = obj_fork(m, obj_dev, st); if (rc) return rc; }
     if (level == 1) { rc = grad_impl(m, x, g, st, true); if (rc) return rc; }
     rc = cons_finish(m, cvals, st); if (rc) return rc;
-    return early ? obj_early_join(m, st) : EXB_OK;
+    return side ? obj_join(m, st) : EXB_OK;
   }
   if (!fused) {
     int rc = EXB_OK;
@@ -1346,19 +1342,17 @@ int exb_eval(exb_model* m, unsigned mask, const double* x, const double* y, doub
     m->last_launches = nl; m->last_collectives = nc;
     return rc;
   }
-  const bool early = comm_on(m);
-  int rc = early ? obj_early_fork(m, x, obj_dev, st) : EXB_OK; if (rc) return rc;
-  rc = cons_prepare(m, cvals, st); if (rc) return rc;
+  int rc = cons_prepare(m, cvals, st); if (rc) return rc;
   ExbCall c{}; c.x = x; c.y = y; c.th = m->d_theta; c.sigma = obj_weight; c.out = hess;
   c.e_jac = jac; c.e_c = cvals; c.e_gb = m->d_gradbuf; c.e_cb = m->d_conbuf; c.e_obj = m->d_objpart_e;
   rc = launch(m, KN_EVAL, c, st); if (rc) return rc;
-  if (!early) {
-    CU_TRY(m, exb_fx_sum(m->d_objpart_e, m->n_objpart_e, obj_dev, st));
-    m->launches++; m->last_launches++;
-  }
+  CU_TRY(m, exb_fx_sum(m->d_objpart_e, m->n_objpart_e, obj_dev, st));
+  m->launches++; m->last_launches++;
+  const bool side = comm_on(m);
+  if (side) { rc = obj_fork(m, obj_dev, st); if (rc) return rc; }
   rc = grad_impl(m, x, g, st, true); if (rc) return rc;
   rc = cons_finish(m, cvals, st); if (rc) return rc;
-  return early ? obj_early_join(m, st) : EXB_OK;
+  return side ? obj_join(m, st) : EXB_OK;
   EXB_END
 }
 

@@ -78,7 +78,7 @@ def _worker(rank, world, port, which, q):
             checks(sm)
             st = local.comm_stats()
             assert st["attached"] == 1 and st["collectives"] >= 7
-            # the fused sweep on a sharded handle: the objective's all-reduce runs on a side stream, hidden behind the sweep
+            # the fused sweep on a sharded handle: the objective's all-reduce runs on a side stream next to the finishing steps
             od, g2, c2 = local.new(1).fill_(nan), local.new(local.nvar).fill_(nan), local.new(local.ncon).fill_(nan)
             j2, h2 = local.new(local.nnzj).fill_(nan), local.new(local.nnzh).fill_(nan)
             for _ in range(2):
