@@ -359,9 +359,11 @@ struct exb_model {
   double* d_gradbuf = nullptr; double* d_conbuf = nullptr;
   // sorted (target, slot) lists: grad (ext:39-46) and constraint augmentation (ext:48-53)
   void *g_slot = nullptr, *g_target = nullptr, *g_ptr = nullptr; long long g_runs = 0; int g_i32 = 0, g_dense = 0;
+  void *g_long = nullptr, *a_long = nullptr;   // runs of thousands of slots on one target (exb_fx_long_runs): summed by chunks
+  std::vector<void*> long_lists;              // every such list, for exb_destroy
   void *a_slot = nullptr, *a_target = nullptr, *a_ptr = nullptr; long long a_runs = 0; int a_i32 = 0, a_dense = 0;
   // sorted structure for the matrix-free products (ext:56-175) and the duplicate-free COO (utils.jl:425-579)
-  struct Sorted { void *slot = nullptr, *other = nullptr, *target = nullptr, *ptr = nullptr; long long runs = 0, nslots = 0; int i32 = 0, dense = 0;
+  struct Sorted { void *slot = nullptr, *other = nullptr, *target = nullptr, *ptr = nullptr, *lng = nullptr; long long runs = 0, nslots = 0; int i32 = 0, dense = 0;
                   long long *urows = nullptr, *ucols = nullptr; };
   Sorted jrow, jcol, hrow, hcol, jcmp, hcmp;
   bool prod_ready = false, cmp_ready = false, cmpj_ready = false;
@@ -877,6 +879,8 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       long long ns = 0;
       e = exb_fx_sort_runs(keys, pl.nnzg, (long long**)&m->g_slot, (long long**)&m->g_target, (long long**)&m->g_ptr, &m->g_runs, &ns, 0);
       if (e == cudaSuccess) e = exb_fx_pack_runs(&m->g_slot, &m->g_target, &m->g_ptr, ns, m->g_runs, std::max(pl.nnzg, pl.m.nvar), &m->g_i32, &m->g_dense, 0);
+      if (e == cudaSuccess) e = exb_fx_long_runs(m->g_ptr, m->g_target, m->g_i32, m->g_runs, ns, &m->g_long, 0);
+      if (m->g_long) m->long_lists.push_back(m->g_long);
       if (e != cudaSuccess) lrc = fail(EXB_ERR_CUDA, std::string("gradient sparsity sort: ") + cudaGetErrorString(e));
     }
     cudaFree(keys);
@@ -894,6 +898,8 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
       long long ns = 0;
       e = exb_fx_sort_runs(keys, pl.nconaug, (long long**)&m->a_slot, (long long**)&m->a_target, (long long**)&m->a_ptr, &m->a_runs, &ns, 0);
       if (e == cudaSuccess) e = exb_fx_pack_runs(&m->a_slot, &m->a_target, &m->a_ptr, ns, m->a_runs, std::max(pl.nconaug, pl.ncon), &m->a_i32, &m->a_dense, 0);
+      if (e == cudaSuccess) e = exb_fx_long_runs(m->a_ptr, m->a_target, m->a_i32, m->a_runs, ns, &m->a_long, 0);
+      if (m->a_long) m->long_lists.push_back(m->a_long);
       if (e != cudaSuccess) lrc = fail(EXB_ERR_CUDA, std::string("augmentation sparsity sort: ") + cudaGetErrorString(e));
     }
     cudaFree(keys);
@@ -913,6 +919,7 @@ void free_model(exb_model* m) {
   if (m->cev1) cudaEventDestroy(m->cev1);
   if (m->cev2) cudaEventDestroy(m->cev2);
   for (void* p : m->dev) cudaFree(p);
+  for (void* q : m->long_lists) exb_fx_long_free(q);
   for (CUmodule mod : m->mods) if (mod && g_drv.ModuleUnload) g_drv.ModuleUnload(mod);
   if (m->hx) cudaFreeHost(m->hx);
   if (m->hy) cudaFreeHost(m->hy);
@@ -1210,8 +1217,8 @@ static int grad_impl(exb_model* m, const double* x, double* g, cudaStream_t st, 
     int rc = launch(m, KN_GGRAD, cg, st); if (rc) return rc;
   }
   if (!slots_ready) { int rc = launch(m, KN_SGRAD, c, st); if (rc) return rc; }  // kerg, ext:669-679
-  CU_TRY(m, exb_fx_compress(m->d_gradbuf, m->g_ptr, m->g_slot, m->g_target, m->g_i32, m->g_runs, g, (gathered || m->world > 1) ? 1 : 0, st));   // ext:691-697
-  if (m->g_runs > 0) { m->launches++; m->last_launches++; }
+  CU_TRY(m, exb_fx_compress(m->d_gradbuf, m->g_ptr, m->g_slot, m->g_target, m->g_i32, m->g_runs, g, (gathered || m->world > 1) ? 1 : 0, m->g_long, st));   // ext:691-697
+  if (m->g_runs > 0) { const int nl = m->g_long ? 3 : 1; m->launches += nl; m->last_launches += nl; }
   if (comm_on(m)) {
     // slot-kernel patterns leave partial sums over this shard's points anywhere in g: sum the shards.  A model whose
     // objective patterns are all owner-computed has every g[v] exact on the rank that owns v: nothing to reduce, and
@@ -1239,8 +1246,8 @@ static int cons_prepare(exb_model* m, double* cvals, cudaStream_t st) {
   return EXB_OK;
 }
 static int cons_finish(exb_model* m, double* cvals, cudaStream_t st) {
-  CU_TRY(m, exb_fx_compress(m->d_conbuf, m->a_ptr, m->a_slot, m->a_target, m->a_i32, m->a_runs, cvals, 1, st));   // ext:691-697
-  if (m->a_runs > 0) { m->launches++; m->last_launches++; }
+  CU_TRY(m, exb_fx_compress(m->d_conbuf, m->a_ptr, m->a_slot, m->a_target, m->a_i32, m->a_runs, cvals, 1, m->a_long, st));   // ext:691-697
+  if (m->a_runs > 0) { const int nl = m->a_long ? 3 : 1; m->launches += nl; m->last_launches += nl; }
   return comm_finish_rows(m, cvals, st);
 }
 int exb_cons(exb_model* m, const double* x, double* cvals, void* stream) {
@@ -1400,6 +1407,9 @@ int build_sorted(exb_model* m, const long long* keys, long long n, long long max
   S.slot = slot; S.target = target; S.ptr = ptr;
   e = exb_fx_pack_runs(&S.slot, &S.target, &S.ptr, S.nslots, S.runs, std::max(max_index, n), &S.i32, &S.dense, 0);
   if (e != cudaSuccess) return fail(EXB_ERR_CUDA, std::string("structure pack: ") + cudaGetErrorString(e));
+  e = exb_fx_long_runs(S.ptr, S.target, S.i32, S.runs, S.nslots, &S.lng, 0);
+  if (e != cudaSuccess) return fail(EXB_ERR_CUDA, std::string("long-run list: ") + cudaGetErrorString(e));
+  if (S.lng) m->long_lists.push_back(S.lng);
   if (other_src && S.nslots > 0) {
     CU_TRY(m, cudaMalloc(&S.other, (size_t)S.nslots * (S.i32 ? 4 : 8)));
     CU_TRY(m, exb_fx_gather(other_src, S.slot, S.i32, S.other, S.nslots, 0));
@@ -1467,8 +1477,8 @@ int ensure_sorted(exb_model* m, int which, int passes = 3) {
 }
 
 int spmv(exb_model* m, const exb_model::Sorted& S, const double* buf, const double* v, double* y, int acc, int skipdiag, cudaStream_t st) {
-  CU_TRY(m, exb_fx_spmv(buf, S.ptr, S.slot, S.other, S.target, S.i32, S.runs, v, y, acc, skipdiag, st));
-  if (S.runs > 0) { m->launches++; m->last_launches++; }
+  CU_TRY(m, exb_fx_spmv(buf, S.ptr, S.slot, S.other, S.target, S.i32, S.runs, v, y, acc, skipdiag, S.lng, st));
+  if (S.runs > 0) { const int nl = S.lng ? 3 : 1; m->launches += nl; m->last_launches += nl; }   // + the two chunked long-run kernels
   return EXB_OK;
 }
 
@@ -1490,7 +1500,7 @@ int exb_jprod(exb_model* m, const double* x, const double* v, double* Jv, void* 
     if (pl.nconaug > 0) CU_TRY(m, cudaMemsetAsync(m->d_conbuf, 0, (size_t)pl.nconaug * 8, st));
     ExbCall c{}; c.x = x; c.v = v; c.th = m->d_theta; c.out = Jv; c.out2 = m->d_conbuf;
     int rc = launch(m, KN_JPROD, c, st); if (rc) return rc;
-    CU_TRY(m, exb_fx_compress(m->d_conbuf, m->a_ptr, m->a_slot, m->a_target, m->a_i32, m->a_runs, Jv, 1, st));
+    CU_TRY(m, exb_fx_compress(m->d_conbuf, m->a_ptr, m->a_slot, m->a_target, m->a_i32, m->a_runs, Jv, 1, m->a_long, st));
     if (m->a_runs > 0) { m->launches++; m->last_launches++; }
     return comm_finish_rows(m, Jv, st);
   }
@@ -1620,7 +1630,7 @@ int exb_jac_compressed(exb_model* m, const double* x, double* vals, void* stream
   int rc = ensure_sorted(m, 2, 1); if (rc) return rc;
   rc = exb_jac(m, x, m->d_jacbuf, stream); if (rc) return rc;
   const exb_model::Sorted& S = m->jcmp;
-  CU_TRY(m, exb_fx_compress(m->d_jacbuf, S.ptr, S.slot, S.target, S.i32, S.runs, vals, 0, (cudaStream_t)stream));   // ker_compress!, ext:1295-1303
+  CU_TRY(m, exb_fx_compress(m->d_jacbuf, S.ptr, S.slot, S.target, S.i32, S.runs, vals, 0, S.lng, (cudaStream_t)stream));   // ker_compress!, ext:1295-1303
   if (S.runs > 0) { m->launches++; m->last_launches++; }
   return EXB_OK;
   EXB_END
@@ -1636,7 +1646,7 @@ int exb_hess_compressed(exb_model* m, const double* x, const double* y, double o
   int rc = ensure_sorted(m, 2, 2); if (rc) return rc;
   rc = exb_hess(m, x, y, obj_weight, m->d_hessbuf, stream); if (rc) return rc;
   const exb_model::Sorted& S = m->hcmp;
-  CU_TRY(m, exb_fx_compress(m->d_hessbuf, S.ptr, S.slot, S.target, S.i32, S.runs, vals, 0, (cudaStream_t)stream));
+  CU_TRY(m, exb_fx_compress(m->d_hessbuf, S.ptr, S.slot, S.target, S.i32, S.runs, vals, 0, S.lng, (cudaStream_t)stream));
   if (S.runs > 0) { m->launches++; m->last_launches++; }
   return EXB_OK;
   EXB_END

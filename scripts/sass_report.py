@@ -14,7 +14,8 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-KERNELS = ("exb_hess_g0", "exb_hessc_g0", "exb_eval_g0", "exb_jac_g0", "exb_cons_g0", "exb_obj_g0", "exb_ggrad_g0", "exb_gradt_g0", "exb_sgrad_g0")
+KERNELS = ("exb_hess_g0", "exb_hessc_g0", "exb_eval_g0", "exb_jac_g0", "exb_cons_g0", "exb_obj_g0", "exb_ggrad_g0", "exb_gradt_g0", "exb_sgrad_g0",
+           "exb_jprod_g0", "exb_jtprod_g0", "exb_hprod_g0")
 
 
 def main():

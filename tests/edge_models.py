@@ -123,6 +123,24 @@ def special_sweep(n=257):
     return c
 
 
+def shared_targets(n=20000, k=700):
+    """Targets that thousands of slots land on: two variables at FIXED indices shared by every point (a step length: gradient,
+    Jacobian-column and Hessian row/column runs of n slots) and rows that collect n / k / 40 augmentation terms.  The one-thread-
+    per-target sums of the reference (ext:482-511,691-697) would be serial over them: runs above 64 slots are summed by a warp,
+    runs of 8192 or more by chunks (csrc/exb_fixed.cu); the fused products aggregate their atomics per block."""
+    rng = np.random.default_rng(13)
+    c = E.ExaCore(); x = c.add_var(n + 1, start=rng.uniform(0.4, 0.9, n + 1)); t = c.add_var(2, start=[0.5, 0.8])
+    c.add_obj(lambda i: t[1] * (x[i] - x[i + 1]) ** 2 + t[2] * x[i], range(1, n + 1))
+    c.add_con(lambda i: x[i + 1] - x[i] - t[1] * sin(x[i]) * t[2], range(1, n + 1))
+    g = c.add_con(dims=(3,))
+    d = np.zeros(n + k + 40, dtype=np.dtype([("r", "i8"), ("i", "i8"), ("a", "f8")]))
+    d["r"] = np.concatenate([np.full(n, 1), np.full(k, 2), np.full(40, 3)])
+    d["i"] = rng.integers(1, n + 2, len(d)); d["a"] = rng.uniform(0.5, 1.5, len(d))
+    rng.shuffle(d)
+    c.add_con_aug(lambda q: g[q.r] + q.a * x[q.i] * t[2], d)
+    return c
+
+
 EDGE = {"mixed_gradient": mixed_gradient, "only_objective": only_objective, "only_constraints": only_constraints, "empty_patterns": empty_patterns,
         "single_points_and_constants": single_points_and_constants, "self_loops": self_loops, "field_types": field_types}
 

@@ -130,3 +130,47 @@ def test_compressed_matches_reference_semantics(exa, name):
     assert np.array_equal(r.cpu().numpy(), rh) and np.array_equal(c.cpu().numpy(), ch)
     assert_close(cm.jac_coord(dx, cm.new(cm.nnzj).fill_(float("nan"))).cpu().numpy(), vj, "compressed jac")
     assert_close(cm.hess_coord(dx, dy, cm.new(cm.nnzh).fill_(float("nan")), obj_weight=0.5).cpu().numpy(), vh, "compressed hess")
+
+
+@pytest.mark.parametrize("n", [20000, 3000])
+@pytest.mark.parametrize("mode", ["fused", "sorted"])
+def test_targets_shared_by_thousands_of_slots(exa, n, mode):
+    """A variable at a fixed index shared by every point and rows collecting thousands of augmentation terms (edge_models.
+    shared_targets): the sorted (target, slot) lists have runs of n slots -- warp-summed above 64, chunked over blocks from 8192
+    (n = 20000: three chunks per run; n = 3000: the warp form only) -- in grad!, cons!, the sorted products and the sorted
+    duplicate-free forms; the fused products aggregate the atomics of such targets per block.  All against the oracle."""
+    import torch
+    from edge_models import shared_targets
+    from oracle.oracle_api import Oracle
+    core = shared_targets(n)
+    ora, m = Oracle.from_core(core), exa.ExaModel(core, sorted_products=(mode == "sorted"))
+    x, y = inputs(core)
+    rng = np.random.default_rng(14)
+    v, w = rng.standard_normal(m.nvar), rng.standard_normal(m.ncon)
+    dx, dy, dv, dw = (torch.from_numpy(a).cuda() for a in (x, y, v, w))
+    nan = float("nan")
+    g1 = m.grad(dx, m.new(m.nvar).fill_(nan)); c1 = m.cons_nln(dx, m.new(m.ncon).fill_(nan))
+    assert_close(g1.cpu().numpy(), ora.grad(x), "grad")
+    assert_close(c1.cpu().numpy(), ora.cons(x), "cons")
+    assert torch.equal(g1, m.grad(dx, m.new(m.nvar).fill_(nan))) and torch.equal(c1, m.cons_nln(dx, m.new(m.ncon).fill_(nan)))   # fixed order
+    assert_close(m.jprod_nln(dx, dv, m.new(m.ncon).fill_(nan)).cpu().numpy(), ora.jprod(x, v), "jprod")
+    assert_close(m.jtprod_nln(dx, dw, m.new(m.nvar).fill_(nan)).cpu().numpy(), ora.jtprod(x, w), "jtprod")
+    h1 = m.hprod(dx, dy, dv, m.new(m.nvar).fill_(nan), obj_weight=0.7)
+    assert_close(h1.cpu().numpy(), ora.hprod(x, y, v, 0.7), "hprod")
+    assert_close(m.hprod(dx, None, dv, m.new(m.nvar).fill_(nan), obj_weight=2.0).cpu().numpy(), ora.hprod(x, None, v, 2.0), "hprod obj-only")
+    if mode == "sorted":
+        assert torch.equal(h1, m.hprod(dx, dy, dv, m.new(m.nvar).fill_(nan), obj_weight=0.7))
+        assert torch.equal(m.jtprod_nln(dx, dw, m.new(m.nvar)), m.jtprod_nln(dx, dw, m.new(m.nvar)))
+        # all five callbacks from one sweep share the same finishing kernels
+        od, g, cv, jv, hv = m.new(1), m.new(m.nvar).fill_(nan), m.new(m.ncon).fill_(nan), m.new(m.nnzj), m.new(m.nnzh)
+        m.eval_all(dx, dy, od, g, cv, jv, hv)
+        assert torch.equal(g, g1) and torch.equal(cv, c1)
+        # duplicate-free forms through the sorted list (the step variable's column: one run per (col, row) pair, short; the
+        # augmentation rows' Jacobian entries are the long ones)
+        cm = m.compressed()
+        jr, jc = ora.jac_structure(); hr, hc = ora.hess_structure()
+        rj, cj, vj = _compress_ref(jr, jc, ora.jac_coord(x))
+        rh, ch, vh = _compress_ref(hr, hc, ora.hess_coord(x, y, 0.7))
+        assert cm.nnzj == len(rj) and cm.nnzh == len(rh)
+        assert_close(cm.jac_coord(dx, cm.new(cm.nnzj).fill_(nan)).cpu().numpy(), vj, "compressed jac")
+        assert_close(cm.hess_coord(dx, dy, cm.new(cm.nnzh).fill_(nan), obj_weight=0.7).cpu().numpy(), vh, "compressed hess")
