@@ -949,6 +949,39 @@ inline std::string gen_pattern(PatternPlan& p, int index, bool windowed, const s
     }
     emit_fn(o, "void s2(" + A + ", long long (&r)[" + std::to_string(a2) + "], long long (&c)[" + std::to_string(a2) + "])", B, tail);
   }
+  {  // hp: the point's contribution to a Hessian-vector product (kersyspmv / kersyspmv2, ext:497-511: y[r] += h v[c], and the mirror
+     // off the diagonal), grouped by DISTINCT index expression: one v load and one scattered add per distinct variable of the
+     // point instead of two per slot (LV constraint: 3 instead of 9; rocket dynamics: 9 instead of ~110).  Expressions that
+     // cannot be proved different are compared at run time (a self loop f_bus == t_bus is a diagonal entry: no mirror).
+    Body B; Gen g(p, B, 0);
+    std::vector<int> ex;                                 // distinct index expressions (node ids)
+    std::vector<int> ta((size_t)ns2), tb((size_t)ns2);
+    auto slot_of = [&](int e) {
+      for (size_t t = 0; t < ex.size(); t++) if (index_relation(p.ir, ex[t], e) == 1) return (int)t;
+      ex.push_back(e);
+      return (int)ex.size() - 1;
+    };
+    for (int j = 0; j < ns2; j++) {
+      ta[(size_t)j] = slot_of((int)p.ir.nodes[(size_t)p.leaf2[(size_t)j].first].a);
+      tb[(size_t)j] = slot_of((int)p.ir.nodes[(size_t)p.leaf2[(size_t)j].second].a);
+    }
+    const int nt = (int)ex.size(), at = nt > 0 ? nt : 1;
+    std::vector<std::string> tail;
+    for (int t = 0; t < nt; t++) {
+      NV& ix = g.real(ex[(size_t)t]);
+      tail.push_back("idx[" + std::to_string(t) + "] = " + ix.rs + "; const double vv" + std::to_string(t) + " = __ldg(v + (idx[" + std::to_string(t) + "] - 1)); val[" + std::to_string(t) + "] = 0.0;");
+    }
+    for (int j = 0; j < ns2; j++) {
+      const std::string a = std::to_string(ta[(size_t)j]), b = std::to_string(tb[(size_t)j]), sj = "s[" + std::to_string(j) + "]";
+      if (ta[(size_t)j] == tb[(size_t)j]) { tail.push_back("val[" + a + "] += " + sj + " * vv" + a + ";"); continue; }
+      tail.push_back("val[" + a + "] += " + sj + " * vv" + b + ";");
+      const int rel = index_relation(p.ir, ex[(size_t)ta[(size_t)j]], ex[(size_t)tb[(size_t)j]]);
+      tail.push_back(std::string(rel == 0 ? "" : "if (idx[" + a + "] != idx[" + b + "]) ") + "val[" + b + "] += " + sj + " * vv" + a + ";");
+    }
+    o << "  static constexpr int NT2 = " << nt << ";\n";
+    emit_fn(o, "void hp(" + A + ", const double (&s)[" + std::to_string(a2) + "], const double* __restrict__ v, long long (&idx)[" + std::to_string(at) +
+                   "], double (&val)[" + std::to_string(at) + "])", B, tail);
+  }
   o << "  static constexpr int PPT0 = " << p.ppt0 << ", PPT1 = " << p.ppt1 << ", PPT2 = " << p.ppt2 << ";\n";
   o << "  static constexpr int W0 = 0, W1 = " << ns2 << ";   // window of second-order slots an exb_hess_g0 entry keeps (ExbSplit narrows it)\n";
   o << "};\n";

@@ -10,12 +10,17 @@ pytestmark = pytest.mark.gpu
 
 def _models():
     from examodels_jl_b200 import models as M
+    from edge_models import EDGE
     return {
         "lv100": lambda: M.luksan_vlcek(100),
         "lv_aug_20x3": lambda: M.luksan_vlcek_aug(20, 3),
         "opf_300": lambda: M.ac_power(M.synthetic_power_data(300, 420, 70, seed=2)),
         "rocket_50": lambda: M.goddard_rocket(50),
         "family_1000": lambda: M.pattern_family(1000, 32),
+        # index expressions that differ symbolically but coincide for some points (a self loop is a DIAGONAL entry: no mirror
+        # term in hprod), fixed indices shared by every point, strided / data-indexed variables
+        "self_loops": EDGE["self_loops"], "mixed_gradient": EDGE["mixed_gradient"], "single_points_and_constants": EDGE["single_points_and_constants"],
+        "field_types": EDGE["field_types"],
     }
 
 
