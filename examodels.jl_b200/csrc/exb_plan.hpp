@@ -73,6 +73,7 @@ struct PatternPlan {
   i64 t_cbmin = 0, t_cbmax = 0;
   // same for the gradient (exb_tile_body in gradient mode): first-order slot j of an objective pattern lands in variable t + shift1[j]
   bool tgrad = false;
+  bool egrad = false;   // the model's only objective pattern with gradient slots, shift-indexed: exb_eval writes g from its own sweep
   i64 g_cbmin = 0, g_cbmax = 0;
 };
 
@@ -96,6 +97,7 @@ struct Plan {
   std::vector<i64> h_lo, h_len;   // per distance: the ONE interval of (1-based) columns in which the entry exists
   int tile_halo = 0, tile_ppt = 3;   // tile_ppt: columns per thread (chosen in build_plan; EXB_TUNE_TILE_PPT overrides)
   int tgrad_halo = 0, tgrad_ppt = 4;   // gradient mode of the tile kernel (exb_gradt_g0)
+  int egrad_pat = -1;                  // pattern whose gradient the fused evaluation kernels emit themselves (PatternPlan::egrad), or -1
   bool idx32 = false;          // every index (variables, points, slots) fits 31 bits: address arithmetic in 32 bits
   int block = 128, minb = 16;  // launch shape of the generated kernels (tuning knobs: EXB_TUNE_BLOCK / EXB_TUNE_MINB)
 };
@@ -739,7 +741,7 @@ inline void compute_tile(PatternPlan& p) {
   if (p.tile_ok && p.t_cbmax - p.t_cbmin > 64) p.tile_ok = false;   // halo of re-evaluated points per tile
 }
 
-inline std::string gen_pattern(PatternPlan& p, int index, bool windowed, const std::vector<i64>* hd = nullptr, int tile_stride = 0) {
+inline std::string gen_pattern(PatternPlan& p, int index, bool windowed, const std::vector<i64>* hd = nullptr, int tile_stride = 0, bool sole_obj = false) {
   std::ostringstream o;
   const int ns1 = p.o1step, ns2 = p.o2step;
   const int a1 = ns1 > 0 ? ns1 : 1, a2 = ns2 > 0 ? ns2 : 1;
@@ -805,9 +807,10 @@ inline std::string gen_pattern(PatternPlan& p, int index, bool windowed, const s
       p.gather1 = ok;
     }
     {  // tile gradient: every first-order slot of an objective pattern addresses x[t + const] (any body weight)
-      p.tgrad = false;
-      if (p.ir.kind == KIND_OBJ && shiftable(p.ir) && ns1 > 0 && getenv("EXB_NO_TGRAD") == nullptr) {
-        bool ok = true; std::vector<i64> sh;
+      p.tgrad = false; p.egrad = false;
+      std::vector<i64> sh;
+      if (p.ir.kind == KIND_OBJ && shiftable(p.ir) && ns1 > 0) {
+        bool ok = true;
         for (int j = 0; j < ns1 && ok; j++) {
           i64 cf, ct;
           ok = affine_index(p.ir, (int)p.ir.nodes[(size_t)p.leaf1[(size_t)j]].a, cf, ct) && cf == 1;
@@ -817,24 +820,28 @@ inline std::string gen_pattern(PatternPlan& p, int index, bool windowed, const s
           p.g_cbmin = *std::min_element(sh.begin(), sh.end()); p.g_cbmax = *std::max_element(sh.begin(), sh.end());
           // light bodies without data stay with the per-variable kernel (LV: 0.033-0.044 ms against 0.049 for the tile form:
           // its two barriers and the staging cost more than re-evaluating a 10-flop body twice); everything else is tiled
-          p.tgrad = !p.gather1 && p.g_cbmax - p.g_cbmin <= 64;
-          if (p.tgrad) p.shift1 = sh;
+          p.tgrad = !p.gather1 && p.g_cbmax - p.g_cbmin <= 64 && getenv("EXB_NO_TGRAD") == nullptr;
+          // the model's ONLY objective pattern with gradient slots: the fused evaluation kernels (exb_eval) have its first-order
+          // slots in registers anyway -- they stage them and write g themselves (exb_eval_block), no gradient launch at all
+          p.egrad = sole_obj && p.g_cbmax - p.g_cbmin <= 64 && getenv("EXB_NO_EGRAD") == nullptr;
+          if (p.tgrad || p.egrad) p.shift1 = sh;
         }
       }
-      if (p.tgrad) {
+      if (p.tgrad || p.egrad) {
         const int ts1 = ns1 | 1;
         std::vector<int> ord((size_t)ns1);
         for (int j = 0; j < ns1; j++) ord[(size_t)j] = j;
-        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return p.shift1[(size_t)a] > p.shift1[(size_t)b]; });
-        o << "  static constexpr bool TGRAD = true; static constexpr int TS1 = " << ts1 << "; static constexpr long long GBMIN = " << p.g_cbmin << ", GBMAX = " << p.g_cbmax << ";\n";
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return sh[(size_t)a] > sh[(size_t)b]; });
+        o << "  static constexpr bool TGRAD = " << (p.tgrad ? "true" : "false") << ", EGRAD = " << (p.egrad ? "true" : "false") << "; static constexpr int TS1 = " << ts1
+          << "; static constexpr long long GBMIN = " << p.g_cbmin << ", GBMAX = " << p.g_cbmax << ";\n";
         o << "  template <bool CHECK> __device__ static __forceinline__ void ggather(const double* __restrict__ rp, const int ql, const int qlo, const int qhi, double (&acc)[1]) {\n";
         for (int j : ord) {
-          const long long off = (long long)j - (long long)p.shift1[(size_t)j] * ts1;
-          o << "    if (!CHECK || (ql - (" << p.shift1[(size_t)j] << ") >= qlo && ql - (" << p.shift1[(size_t)j] << ") < qhi)) acc[0] += rp[" << off << "];\n";
+          const long long off = (long long)j - (long long)sh[(size_t)j] * ts1;
+          o << "    if (!CHECK || (ql - (" << sh[(size_t)j] << ") >= qlo && ql - (" << sh[(size_t)j] << ") < qhi)) acc[0] += rp[" << off << "];\n";
         }
         o << "  }\n";
       } else {
-        o << "  static constexpr bool TGRAD = false; static constexpr int TS1 = 1; static constexpr long long GBMIN = 0, GBMAX = 0;\n";
+        o << "  static constexpr bool TGRAD = false, EGRAD = false; static constexpr int TS1 = 1; static constexpr long long GBMIN = 0, GBMAX = 0;\n";
         o << "  template <bool CHECK> __device__ static __forceinline__ void ggather(const double* __restrict__, const int, const int, const int, double (&)[1]) {}\n";
       }
     }
@@ -1105,9 +1112,12 @@ inline bool build_plan(Plan& pl, const void* ir, size_t bytes, const void* const
     }
     if (!pl.tile_ok) { pl.hd.clear(); pl.h_lo.clear(); pl.h_len.clear(); }
   }
+  int nobj1 = 0;   // objective patterns with gradient slots
+  for (auto& p : pl.pats) if (p.ir.kind == KIND_OBJ && p.o1step > 0) nobj1++;
   for (size_t k = 0; k < pl.pats.size(); k++) {
     int stride = pl.pats[k].o2step | 1;   // odd word stride: conflict-free 64-bit shared-memory accesses
-    o << gen_pattern(pl.pats[k], (int)k, pl.hess_windowed && pl.pats[k].win, pl.tile_ok ? &pl.hd : nullptr, stride);
+    o << gen_pattern(pl.pats[k], (int)k, pl.hess_windowed && pl.pats[k].win, pl.tile_ok ? &pl.hd : nullptr, stride, nobj1 == 1);
+    if (pl.pats[k].egrad) pl.egrad_pat = (int)k;
   }
   // kernel pattern lists
   for (size_t k = 0; k < pl.pats.size(); k++) {

@@ -719,6 +719,11 @@ int build_model(exb_model* m, const void* const* host_data, int n_data) {
         if (nw != p.o2step) ns = nw | 1;
       }
       if (ns <= EXB_TILE_MAX_NS && ns * ppt > maxns) maxns = ns * ppt;   // tile words per thread
+      if ((kn == KN_EVAL || kn == KN_EVAL1) && p.egrad) {   // staging rows of the in-sweep gradient: (block's points + halo) x odd stride
+        const long long words = (BLK * ppt + (p.g_cbmax - p.g_cbmin)) * (long long)(p.o1step | 1);
+        const int per_thread = (int)((words + BLK - 1) / BLK);
+        if (per_thread > maxns) maxns = per_thread;
+      }
     }
     if (kn == KN_HESSC || kn == KN_GRADT) {   // one block per tile of T consecutive COLUMNS of the owned range (exb_tile_body), no block -> pattern map
       void* d_args = nullptr;
@@ -1303,6 +1308,23 @@ static int obj_join(exb_model* m, cudaStream_t st) {
   return EXB_OK;
 }
 
+// Gradient written by the fused evaluation kernels themselves (exb_eval_block, P::EGRAD): an unsharded handle whose model has ONE
+// objective pattern with gradient slots, shift-indexed.  Returns the pointer the sweep writes g through (nullptr: separate
+// gradient launch as before) after zeroing the variables no point of the pattern reaches.
+static int egrad_prepare(exb_model* m, double* g, cudaStream_t st, double** e_g) {
+  *e_g = nullptr;
+  const exb::Plan& pl = m->plan->pl;
+  static const bool off = getenv("EXB_NO_EGRAD") != nullptr;
+  if (off || m->world != 1 || pl.egrad_pat < 0 || !g) return EXB_OK;
+  const exb::PatternPlan& p = pl.pats[(size_t)pl.egrad_pat];
+  const long long lo = p.ir.range_start + p.g_cbmin, hi = p.ir.range_start + p.ir.nitr - 1 + p.g_cbmax;   // 1-based variables reached
+  if (p.ir.nitr <= 0 || lo < 1 || hi > pl.m.nvar) return EXB_OK;
+  if (lo > 1) CU_TRY(m, cudaMemsetAsync(g, 0, (size_t)(lo - 1) * 8, st));
+  if (hi < pl.m.nvar) CU_TRY(m, cudaMemsetAsync(g + hi, 0, (size_t)(pl.m.nvar - hi) * 8, st));
+  *e_g = g;
+  return EXB_OK;
+}
+
 // One sweep for several callbacks at the same x (the composition of src/nlp.jl:1827-1940).  With every bit of `mask` set each
 // data point is evaluated ONCE by exb_eval_g0 (value + first-order + second-order slots; csrc/exb_device.cuh exb_eval_block):
 // c / conbuffer, the objective's block partials, jac, the gradient slots and hess are written by that one launch; what
@@ -1328,12 +1350,13 @@ int exb_eval(exb_model* m, unsigned mask, const double* x, const double* y, doub
     int rc = cons_prepare(m, cvals, st); if (rc) return rc;
     ExbCall c{}; c.x = x; c.th = m->d_theta;
     c.e_jac = jac; c.e_c = cvals; c.e_gb = m->d_gradbuf; c.e_cb = m->d_conbuf; c.e_obj = level == 1 ? m->d_objpart_e1 : m->d_objpart_e0;
+    if (level == 1) { rc = egrad_prepare(m, g, st, &c.e_g); if (rc) return rc; }
     rc = launch(m, knl, c, st); if (rc) return rc;
     CU_TRY(m, exb_fx_sum(c.e_obj, m->k[knl].nblocks, obj_dev, st));
     m->launches++; m->last_launches++;
     const bool side = comm_on(m);
     if (side) { rc = obj_fork(m, obj_dev, st); if (rc) return rc; }
-    if (level == 1) { rc = grad_impl(m, x, g, st, true); if (rc) return rc; }
+    if (level == 1 && !c.e_g) { rc = grad_impl(m, x, g, st, true); if (rc) return rc; }
     rc = cons_finish(m, cvals, st); if (rc) return rc;
     return side ? obj_join(m, st) : EXB_OK;
   }
@@ -1352,12 +1375,13 @@ int exb_eval(exb_model* m, unsigned mask, const double* x, const double* y, doub
   int rc = cons_prepare(m, cvals, st); if (rc) return rc;
   ExbCall c{}; c.x = x; c.y = y; c.th = m->d_theta; c.sigma = obj_weight; c.out = hess;
   c.e_jac = jac; c.e_c = cvals; c.e_gb = m->d_gradbuf; c.e_cb = m->d_conbuf; c.e_obj = m->d_objpart_e;
+  rc = egrad_prepare(m, g, st, &c.e_g); if (rc) return rc;
   rc = launch(m, KN_EVAL, c, st); if (rc) return rc;
   CU_TRY(m, exb_fx_sum(m->d_objpart_e, m->n_objpart_e, obj_dev, st));
   m->launches++; m->last_launches++;
   const bool side = comm_on(m);
   if (side) { rc = obj_fork(m, obj_dev, st); if (rc) return rc; }
-  rc = grad_impl(m, x, g, st, true); if (rc) return rc;
+  if (!c.e_g) { rc = grad_impl(m, x, g, st, true); if (rc) return rc; }
   rc = cons_finish(m, cvals, st); if (rc) return rc;
   return side ? obj_join(m, st) : EXB_OK;
   EXB_END

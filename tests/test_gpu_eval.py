@@ -86,8 +86,10 @@ def test_fused_evaluation_matches_oracle_and_separate_callbacks(exa, name):
 
 
 def test_fused_evaluation_is_one_sweep(exa):
-    """LV: the fused call is 3 launches (sweep, fixed-order sum of the objective partials, owner-computed gradient) against 6
-    for the five separate callbacks, and bitwise equal to them where the generated slot code is shared."""
+    """LV: the fused call is 2 launches (the sweep -- which also writes g, the model having one shift-indexed objective pattern --
+    and the fixed-order sum of the objective partials) against 6 for the five separate callbacks, and bitwise equal to them
+    where the generated slot code is shared.  With EXB_NO_EGRAD-style models (several objective patterns) the owner-computed
+    gradient kernel is the third launch."""
     import torch
     from examodels_jl_b200 import models as M
     core = M.luksan_vlcek(50_000)
@@ -97,11 +99,11 @@ def test_fused_evaluation_is_one_sweep(exa):
     outs = [m.new(n) for n in (1, m.nvar, m.ncon, m.nnzj, m.nnzh)]
     m.eval_all(dx, dy, *outs)     # tunes
     m.eval_all(dx, dy, *outs)
-    assert m.stats()["last_launches"] == 3
+    assert m.stats()["last_launches"] == 2
     sep = _separate(m, dx, dy, 1.0)
     same = {w: bool(torch.equal(a, b)) for a, b, w in zip(outs[1:], sep[1:], ("grad", "cons", "jac", "hess"))}
     print("bitwise equal to the separate callbacks:", same)
-    assert same["grad"]           # the gradient kernel is literally the same launch
+    assert same["grad"]           # same first-order slots summed in the same order (ascending point, then slot)
 
 
 def test_fused_evaluation_on_sharded_handles(exa):
@@ -126,3 +128,50 @@ def test_fused_evaluation_on_sharded_handles(exa):
         assert_close(tot[2].cpu().numpy(), ora.cons(x), "sharded eval cons")
         assert_close(jac.cpu().numpy(), ora.jac_coord(x), "sharded eval jac")
         assert_close(hess.cpu().numpy(), ora.hess_coord(x, y, 0.5), "sharded eval hess")
+
+
+def _egrad_models():
+    from examodels_jl_b200 import models as M
+    from edge_models import EDGE, tile_fuzz
+    return {
+        "lv_5": lambda: M.luksan_vlcek(5),                  # one ragged block: first and last at once
+        "lv_129": lambda: M.luksan_vlcek(129),
+        "lv_1003": lambda: M.luksan_vlcek(1003),
+        "lv_guide_700": lambda: M.luksan_vlcek(700, order="guide"),
+        "lv_100k": lambda: M.luksan_vlcek(100_003),         # interior blocks (unchecked gather) + a ragged tail
+        "lv_param_300": lambda: M.luksan_vlcek_param(300),
+        "only_objective": EDGE["only_objective"],
+        "fuzz_99": lambda: tile_fuzz(99),                   # objective over range(100, 140) of 150+ variables: the rest of g is zero-filled
+        "fuzz_0": lambda: tile_fuzz(0), "fuzz_1": lambda: tile_fuzz(1), "fuzz_3": lambda: tile_fuzz(3),
+    }
+
+
+@pytest.mark.parametrize("name", list(_egrad_models().keys()))
+def test_gradient_written_by_the_sweep_itself(exa, name):
+    """A model with ONE shift-indexed objective pattern: exb_eval (all five, and the first-order form) writes g from the
+    first-order slots its sweep already holds -- no gradient launch.  Against the oracle, against grad! (same summation order:
+    ascending point, then slot), and the launch count drops by one."""
+    import torch
+    from oracle.oracle_api import Oracle
+    core = _egrad_models()[name]()
+    plan = exa.Plan(core)
+    nobj1 = sum(1 for k in range(plan.npatterns()) if plan.pattern_info(k)["kind"] == 0 and plan.pattern_info(k)["o1step"] > 0)
+    has = "EGRAD = true" in plan.source()
+    assert has == (nobj1 == 1), (nobj1, has)
+    ora, m = Oracle.from_core(core), exa.ExaModel(core)
+    x, y = inputs(core)
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    nan = float("nan")
+    g_sep = m.grad(dx, m.new(m.nvar).fill_(nan))
+    for mask in (31, 15):
+        outs = [m.new(n).fill_(nan) for n in (1, m.nvar, m.ncon, m.nnzj, m.nnzh)]
+        for _ in range(2):   # first call tunes
+            outs[1].fill_(nan)
+            m.eval_all(dx, dy if mask == 31 else None, outs[0], outs[1], outs[2], outs[3], outs[4] if mask == 31 else None, mask=mask)
+        launches = m.stats()["last_launches"]
+        assert_close(outs[1].cpu().numpy(), ora.grad(x), f"sweep gradient (mask {mask})")
+        assert_close(outs[1].cpu().numpy(), g_sep.cpu().numpy(), f"sweep gradient vs grad! (mask {mask})", rtol=1e-13)
+        if has:
+            assert launches == 2 + (1 if m.nconaug > 0 else 0), launches      # sweep + objective sum: no gradient launch
+            if name.startswith("lv"):   # same slots, same order; bitwise where the compiler contracts a*b+c alike in d012 / d01 and d1
+                assert torch.equal(outs[1], g_sep)

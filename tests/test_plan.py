@@ -300,3 +300,15 @@ def test_duplicate_free_hessian_closed_form_counts():
     assert not E.Plan(tile_fuzz(99)).tile_info()["fused"]
     for core in (M.goddard_rocket(20), M.ac_power(M.synthetic_power_data(30, 41, 6, seed=5)), M.luksan_vlcek_aug(9, 3)):
         assert not E.Plan(core).tile_info()["fused"]        # fixed-index variable / data-indexed / product iterators
+
+
+def test_sweep_gradient_is_planned_for_a_sole_shift_indexed_objective():
+    """exb_eval writes g from its own sweep (P::EGRAD) exactly when the model has ONE objective pattern with gradient slots and
+    that pattern is shift-indexed; several objective patterns, or indices from data / at fixed positions, keep the gradient launch."""
+    import examodels_jl_b200 as E
+    from examodels_jl_b200 import models as M
+    from edge_models import EDGE, shared_targets
+    assert "EGRAD = true" in E.Plan(M.luksan_vlcek(50)).source()
+    assert "EGRAD = true" in E.Plan(EDGE["only_objective"]()).source()
+    for core in (EDGE["mixed_gradient"](), shared_targets(100, 10), M.pattern_family(100, 32), M.goddard_rocket(10)):
+        assert "EGRAD = true" not in E.Plan(core).source()
