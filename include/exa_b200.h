@@ -178,7 +178,9 @@ int exb_hess(exb_model* m, const double* x, const double* y, double obj_weight, 
  * and hess_coord! at the same x, and the reference walks every pattern's tree once per callback).  mask = EXB_EVAL_ALL: every
  * data point is evaluated once by one generated launch (exb_eval_g0) that writes c, jac, hess, the gradient slots and the
  * objective's partial sums; the small finishing steps of the separate callbacks follow (fixed-order sum, owner-computed
- * gradient, segmented sums, collectives of a sharded model).  mask = EXB_EVAL_FIRST / EXB_EVAL_VALUES: the same with a first-order /
+ * gradient, segmented sums, collectives of a sharded model).  On an unsharded handle whose model has ONE objective pattern with
+ * gradient slots, shift-indexed, the sweep writes g itself (no gradient launch; same summation order as exb_grad).
+ * mask = EXB_EVAL_FIRST / EXB_EVAL_VALUES: the same with a first-order /
  * value-only sweep.  Any other mask: the requested callbacks one by one.  Outputs not
  * requested may be NULL; *obj_dev is a DEVICE double (no synchronisation); y == NULL is the objective-only Hessian form. */
 #define EXB_EVAL_OBJ 1u
