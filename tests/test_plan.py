@@ -312,3 +312,24 @@ def test_sweep_gradient_is_planned_for_a_sole_shift_indexed_objective():
     assert "EGRAD = true" in E.Plan(EDGE["only_objective"]()).source()
     for core in (EDGE["mixed_gradient"](), shared_targets(100, 10), M.pattern_family(100, 32), M.goddard_rocket(10)):
         assert "EGRAD = true" not in E.Plan(core).source()
+
+
+def test_hprod_contributions_are_grouped_per_distinct_variable():
+    """P::hp (the point's Hessian-vector contributions): one entry per DISTINCT index expression -- LV constraint 3 (x[i], x[i+1],
+    x[i+2]) for 6 slots, LV objective 2 for 3 slots -- with no run-time index compare where the shifts prove the indices different;
+    data-indexed endpoints that may coincide (self loops) keep the compare so that the entry stays a diagonal one."""
+    import re
+    import examodels_jl_b200 as E
+    from examodels_jl_b200 import models as M
+    from edge_models import EDGE
+    src = E.Plan(M.luksan_vlcek(50)).source()
+    assert sorted(int(v) for v in re.findall(r"static constexpr int NT2 = (\d+);", src)) == [2, 3]
+    hp = [src[m.start():src.index("static constexpr int PPT0", m.start())] for m in re.finditer(r"void hp\(", src)]
+    assert len(hp) == 2 and all("if (idx[" not in h for h in hp)
+    assert sum(h.count("__ldg(v +") for h in hp) == 5          # one v load per distinct variable of a point
+    loops = E.Plan(EDGE["self_loops"]()).source()
+    hp = [loops[m.start():loops.index("static constexpr int PPT0", m.start())] for m in re.finditer(r"void hp\(", loops)]
+    assert any("if (idx[" in h for h in hp)
+    rocket = E.Plan(M.goddard_rocket(10)).source()
+    nt = [int(v) for v in re.findall(r"static constexpr int NT2 = (\d+);", rocket)]
+    assert max(nt) <= 9            # h, v, m, T at two steps + the step variable: 9 scattered adds for the 47-slot dynamics pattern
